@@ -1,0 +1,82 @@
+/*
+ * libssa_b200.h - additive, GPU-specific entry points of libssa_b200.so.
+ *
+ * Nothing here is needed by a program written against libssa.h; these calls
+ * expose what the reference has no notion of: device selection, sharding of
+ * the database over several GPUs (one process per GPU), the collective used to
+ * merge per-GPU results, and counters/timers of the last search (the
+ * reference only prints its overflow counters at OUTPUT_INFO,
+ * reference src/algo/manager.c:147-160).
+ */
+#ifndef LIBSSA_B200_H_
+#define LIBSSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "libssa.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* counters and timers of the last sw_align/nw_align call (and of the last database build) */
+typedef struct {
+    uint64_t n_seqs;          /* non-empty database records (all shards) */
+    uint64_t n_residues;      /* their total length */
+    uint64_t local_seqs;      /* records held by this process' shard */
+    uint64_t local_residues;
+    uint64_t cells;           /* query length x local_residues: real DP cells of the last search */
+    uint64_t overflow_8;      /* records the reference would have re-aligned at 16 bit (manager.c:157-160) */
+    uint64_t overflow_16;     /* ... and at 64 bit */
+    uint64_t wide_tier_seqs;  /* records this library scored with its exact 32-bit kernel */
+    uint64_t launches;        /* CUDA kernels launched by the last search */
+    uint64_t h2d_bytes;       /* host->device bytes of the last search (query profile etc.) */
+    uint64_t d2h_bytes;       /* device->host bytes of the last search (scores, hits) */
+    double score_kernel_ms;   /* device time of the scoring kernels, CUDA events on the library stream */
+    double device_ms;         /* device time of everything the search enqueued */
+    double call_ms;           /* host wall-clock of the whole *_align call */
+    double pack_ms;           /* last database build: host packing */
+    double upload_ms;         /* last database build: host->device upload */
+    uint64_t db_device_bytes; /* resident packed database size on this device */
+} ssa_b200_stats_t;
+
+/* CUDA device this process uses (default: $LOCAL_RANK if set, else 0).  Call before the first search. */
+void ssa_b200_set_device( int device );
+
+/*
+ * Shard the database over `world_size` processes (one per GPU): the records are sorted by length
+ * and dealt round-robin, so every shard holds the same residue count to within one record
+ * (SURVEY.md 8e).  Each process scores its shard only.
+ */
+void ssa_b200_set_shard( int rank, int world_size );
+
+/*
+ * Collective used to merge shard results: all-gather `bytes` bytes from every rank's DEVICE buffer
+ * `d_send` into `d_recv` (world_size * bytes, rank order), ordered on CUDA stream `stream`.
+ * The host language supplies it (torch.distributed/NCCL in bench.py and the tests; ncclAllGather in C).
+ */
+typedef void (*ssa_b200_allgather_fn)( void * ctx, const void * d_send, void * d_recv, size_t bytes, void * stream );
+void ssa_b200_set_allgather( ssa_b200_allgather_fn fn, void * ctx );
+
+/* builds (packs + uploads) the device-resident database now instead of lazily in the first search */
+void ssa_b200_prepare_db( void );
+
+void ssa_b200_get_stats( ssa_b200_stats_t * out );
+
+/*
+ * Exact score of every local database record against the query, without hit selection:
+ * writes `local_seqs` entries, index = position in this shard's record list; ids[] receives the
+ * provider IDs.  Either pointer may be NULL.  nw = 0 Smith-Waterman, 1 Needleman-Wunsch.
+ * Returns local_seqs.
+ */
+size_t ssa_b200_score_all( p_query p, int nw, int64_t * scores, uint64_t * ids );
+
+/* library/ABI version: major*10000 + minor*100 + patch */
+int ssa_b200_version( void );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* LIBSSA_B200_H_ */

@@ -1,0 +1,190 @@
+// The libssa.h entry points (reference src/libssa.c:41-271) on top of the GPU search.
+// Process-global state and "fatal = exit(1)" error handling are kept exactly as in the reference:
+// the library is not re-entrant and one search runs at a time.
+#include "common.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#define API extern "C" __attribute__( ( visibility( "default" ) ) )
+
+int8_t g_gapO = 0;  // reference src/libssa.c:35-36
+int8_t g_gapE = 0;
+size_t g_chunk_size = DEFAULT_CHUNK_SIZE;  // reference src/algo/manager.c:40
+size_t g_thread_count = (size_t) -1;       // reference src/util/thread_pool.c:37
+uint64_t g_db_epoch = 1;
+
+API void set_output_mode( int mode ) { g_output_mode = mode; }
+
+// reference: selects the CPU ISA (src/cpu_config.c:39-51).  There is one GPU code path; accepted and ignored.
+API void set_simd_compute_mode( int ) {}
+
+API void set_chunk_size( size_t size ) {
+    if( size == 0 ) {
+        print_error( "Only non zero chunk sizes are allowed. Using the default size of 1000 sequences.", size );
+        size = DEFAULT_CHUNK_SIZE;
+    }
+    g_chunk_size = size;
+}
+
+// accepted; the result is always the reference's deterministic one-thread result
+API void set_thread_count( size_t nr ) { g_thread_count = nr; }
+
+API void init_score_matrix( int mode, const char * matrix ) {
+    if( mode == READ_FROM_FILE )
+        mat_init_from_file( matrix );
+    else if( mode == READ_FROM_STRING )
+        mat_init_from_string( matrix );
+    else if( mode == MATRIX_BUILDIN )
+        mat_init_buildin( matrix );
+    else
+        fatal( "Unknown mode for reading score matrices: %d", mode );
+}
+
+API void init_gap_penalties( const int8_t gap_open, const int8_t gap_extend ) {
+    g_gapO = gap_open;
+    g_gapE = gap_extend;
+}
+
+// first argument = match score, second = mismatch score (src/libssa.c:115-117 -> src/matrices.c:447)
+API void init_constant_scores( const int8_t p, const int8_t m ) { mat_init_constant_scoring( p, m ); }
+
+API void init_db( const char * fasta_db_file ) {
+    ssa_db_close();
+    ssa_db_init( fasta_db_file );
+    g_db_epoch++;
+    print_info( "DB read %lu sequences\n", (unsigned long) ssa_db_get_sequence_count() );
+}
+
+API void init_symbol_translation( int type, int strands, int d_gencode, int q_gencode ) {
+    if( !gencode_is_valid( q_gencode ) ) fatal( "Illegal query genetic code specified." );
+    if( !gencode_is_valid( d_gencode ) ) fatal( "Illegal database genetic code specified." );
+    // The reference validates the PREVIOUS global values here (src/libssa.c:144-149), i.e. it accepts any
+    // argument; we check the arguments themselves.
+    if( type < 0 || type > 4 ) fatal( "Illegal symbol type specified." );
+    if( strands < 1 || strands > 3 ) fatal( "Illegal strands specified." );
+    g_symtype = type;
+    g_query_strands = strands;
+    g_db_epoch++;
+}
+
+API p_query init_sequence_fasta( int mode, const char * fasta_sequence ) {
+    if( mode == READ_FROM_FILE ) return query_read_from_file( fasta_sequence );
+    if( mode == READ_FROM_STRING ) return query_read_from_string( fasta_sequence );
+    fatal( "Unknown mode for reading query sequences: %d", mode );
+}
+
+API void free_sequence( p_query p ) { query_free( p ); }
+
+static void test_configuration( p_query query ) {  // reference src/libssa.c:196-219
+    if( !g_gapO && !g_gapE ) print_warning( "Gap opening and gap extension cost set to zero. Possible error." );
+    if( !g_matrix.set ) fatal( "Scoring not initialized." );
+    if( !query ) fatal( "Query not initialized." );
+    if( ssa_db_get_sequence_count() == 0 ) print_warning( "Database contains zero sequences. Possible error." );
+    if( !is_constant_scoring() && g_symtype == NUCLEOTIDE )
+        fatal( "Nucleotide sequences can only be aligned using constant scores." );
+}
+
+// The query frames a search runs over (reference src/algo/searcher.c:42-90).  Only the un-translated
+// modes are served by the GPU path so far, i.e. exactly one frame.
+static sequence_t query_frame( p_query query, int * strand, int * frame ) {
+    *strand = 0;
+    *frame = 0;
+    if( g_symtype == NUCLEOTIDE ) {
+        if( g_query_strands != FORWARD_STRAND )
+            fatal( "Nucleotide searches on the complementary strand are not available in the GPU library yet." );
+        return query->nt[0];
+    }
+    if( g_symtype == AMINOACID ) return query->aa[0];
+    fatal( "Translated searches (TRANS_QUERY/TRANS_DB/TRANS_BOTH) are not available in the GPU library yet." );
+}
+
+static p_alignment_list run_search( p_query query, size_t hitcount, int bit_width, int align_type, int search_type ) {
+    test_configuration( query );
+    if( bit_width != BIT_WIDTH_64 && bit_width != BIT_WIDTH_16 && bit_width != BIT_WIDTH_8 )
+        fatal( "\nunknown bit width provided: %d\n\n", bit_width );  // reference src/algo/searcher.c:115-117
+
+    SearchRequest req;
+    sequence_t q = query_frame( query, &req.q_strand, &req.q_frame );
+    req.query = (const uint8_t *) q.seq;
+    req.qlen = q.len;
+    req.search_type = search_type;
+    req.bit_width = bit_width;
+    req.hitcount = hitcount;
+    req.align_type = align_type;
+
+    std::vector<HitAlignment> hits;
+    gpu_search( req, hits );
+
+    // result records: reference src/algo/aligner.c:62-93 (init_alignment), src/algo/manager.c:83-113
+    p_alignment_list alist = (p_alignment_list) xmalloc( sizeof( alignment_list_t ) );
+    alist->len = hits.size();
+    alist->alignments = (p_alignment *) xmalloc( ( hits.size() ? hits.size() : 1 ) * sizeof( p_alignment ) );
+    for( size_t i = 0; i < hits.size(); i++ ) {
+        const HitAlignment & h = hits[i];
+        p_alignment a = (p_alignment) xmalloc( sizeof( alignment_t ) );
+        a->db_seq.seq = (char *) xmalloc( h.db_codes.size() + 1 );
+        memcpy( a->db_seq.seq, h.db_codes.data(), h.db_codes.size() );
+        a->db_seq.seq[h.db_codes.size()] = 0;
+        a->db_seq.len = h.db_codes.size();
+        a->db_seq.ID = h.hit.db_id;
+        a->db_seq.strand = 0;
+        a->db_seq.frame = 0;
+        a->query.seq = q.seq;  // borrowed, not freed by free_alignment (aligner.c:80,118)
+        a->query.len = q.len;
+        a->query.strand = req.q_strand;
+        a->query.frame = req.q_frame;
+        a->score = (long) h.hit.score;
+        a->alignment = nullptr;
+        a->alignment_len = 0;  // left uninitialised by the reference for COMPUTE_SCORE; we define it as 0
+        a->align_q_start = a->align_q_end = a->align_d_start = a->align_d_end = 0;
+        if( align_type != COMPUTE_SCORE ) {
+            a->alignment = (char *) xmalloc( h.cigar.size() + 1 );
+            memcpy( a->alignment, h.cigar.c_str(), h.cigar.size() + 1 );
+            a->alignment_len = h.cigar.size();
+            a->align_q_start = h.q_start;
+            a->align_q_end = h.q_end;
+            a->align_d_start = h.d_start;
+            a->align_d_end = h.d_end;
+        }
+        alist->alignments[i] = a;
+    }
+    return alist;
+}
+
+API p_alignment_list sw_align( p_query query, size_t hitcount, int bit_width, int align_type ) {
+    return run_search( query, hitcount, bit_width, align_type, SMITH_WATERMAN );
+}
+
+API p_alignment_list nw_align( p_query query, size_t hitcount, int bit_width, int align_type ) {
+    return run_search( query, hitcount, bit_width, align_type, NEEDLEMAN_WUNSCH );
+}
+
+API void free_alignment( p_alignment_list alist ) {  // reference src/algo/aligner.c:101-143
+    if( !alist ) return;
+    if( alist->alignments ) {
+        for( size_t i = 0; i < alist->len; i++ ) {
+            p_alignment a = alist->alignments[i];
+            if( !a ) continue;
+            free( a->db_seq.seq );
+            free( a->alignment );
+            free( a );
+        }
+        free( alist->alignments );
+    }
+    free( alist );
+}
+
+API void ssa_exit( void ) {  // reference src/libssa.c:266-271
+    mat_free();
+    ssa_db_close();
+    g_db_epoch++;
+    gpu_release();
+}
+
+API size_t ssa_b200_score_all( p_query query, int nw, int64_t * scores, uint64_t * ids ) {
+    test_configuration( query );
+    int strand, frame;
+    sequence_t q = query_frame( query, &strand, &frame );
+    return gpu_score_all( (const uint8_t *) q.seq, q.len, nw ? NEEDLEMAN_WUNSCH : SMITH_WATERMAN, scores, ids );
+}

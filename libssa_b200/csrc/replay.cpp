@@ -1,0 +1,159 @@
+// Hit selection with the reference's exact tie behaviour.
+//
+// Which of several records tied at the cut-off score are reported depends, in the reference, on the
+// ORDER in which scores reach a bounded min-heap that drops a newcomer equal to its current minimum
+// (reference src/util/minheap.c:75-91, src/util/util.c:120-123).  With one thread that order is a
+// deterministic function of the record lengths, the chunk size, the entry bit width and of which
+// records overflow a narrow tier:
+//   * chunks of `chunk` records in provider order, empty records skipped (src/db_adapter.c:212-239);
+//     a chunk without any non-empty record ends the search (src/algo/8/search_8.c:135);
+//   * 64-bit entry: provider order within the chunk (src/algo/64/search_64.c:44-56);
+//   * 8/16-bit entry: the SIMD channel scheduler (src/algo/simd/search_simd_sw.c:338-428): 32 resp. 16
+//     channels, each busy for ceil(len/4) blocks (fewer if the record overflows), finished channels
+//     are emitted and refilled in channel order at the start of the next loop iteration;
+//   * records that overflow are collected in emission order and re-run through the next tier after
+//     the chunk (src/algo/8/search_8.c:94-124, src/algo/16/search_16.c:92-114).
+// The GPU computes exact scores; this file only reproduces the order and the heap.
+#include "common.h"
+
+#include <algorithm>
+
+namespace {
+
+// Emission order of one chunk through `channels` SIMD channels; blocks[i] = blocks record i occupies.
+void simd_emission( const std::vector<uint64_t> & blocks, int channels, std::vector<uint32_t> & emit ) {
+    const size_t n = blocks.size();
+    emit.clear();
+    emit.reserve( n );
+    std::vector<int64_t> cur( channels, -1 );
+    std::vector<uint64_t> left( channels, 0 );
+    size_t next = 0;
+    while( emit.size() < n ) {
+        for( int c = 0; c < channels; c++ ) {
+            if( left[c] != 0 ) continue;
+            if( cur[c] >= 0 ) {
+                emit.push_back( (uint32_t) cur[c] );
+                cur[c] = -1;
+            }
+            if( next < n ) {
+                cur[c] = (int64_t) next;
+                left[c] = blocks[next++];
+            }
+        }
+        if( emit.size() == n ) break;
+        uint64_t step = UINT64_MAX;
+        for( int c = 0; c < channels; c++ )
+            if( cur[c] >= 0 ) step = std::min( step, left[c] );
+        for( int c = 0; c < channels; c++ )
+            if( cur[c] >= 0 ) left[c] -= step;
+    }
+}
+
+struct Heap {  // reference src/util/minheap.c:30-91, comparisons on the score only
+    size_t cap;
+    std::vector<Hit> a;
+    explicit Heap( size_t k ) : cap( k ) { a.reserve( k ); }
+    void add( const Hit & e ) {
+        if( a.size() < cap ) {
+            size_t i = a.size();
+            a.push_back( e );
+            while( i > 0 ) {
+                size_t p = ( i - 1 ) / 2;
+                if( !( e.score < a[p].score ) ) break;
+                a[i] = a[p];
+                i = p;
+            }
+            a[i] = e;
+        }
+        else if( cap > 0 && a[0].score < e.score ) {
+            size_t p = 0, c = 1, n = a.size();
+            while( c < n ) {
+                if( c + 1 < n && a[c + 1].score < a[c].score ) c++;
+                if( !( a[c].score < e.score ) ) break;
+                a[p] = a[c];
+                p = c;
+                c = 2 * p + 1;
+            }
+            a[p] = e;
+        }
+    }
+};
+
+}  // namespace
+
+void arrival_order( const std::vector<uint64_t> & lens, const int64_t * ovf8, const int64_t * ovf16, size_t chunk,
+        int bit_width, std::vector<uint32_t> & order ) {
+    const size_t n = lens.size();
+    order.clear();
+    order.reserve( n );
+    if( chunk == 0 ) chunk = DEFAULT_CHUNK_SIZE;
+    std::vector<uint32_t> idx, emit, t16, t64;
+    std::vector<uint64_t> blocks;
+    for( size_t start = 0; start < n; start += chunk ) {
+        idx.clear();
+        for( size_t i = start; i < std::min( n, start + chunk ); i++ )
+            if( lens[i] > 0 ) idx.push_back( (uint32_t) i );
+        if( idx.empty() ) break;
+        if( bit_width == 64 ) {
+            order.insert( order.end(), idx.begin(), idx.end() );
+            continue;
+        }
+        t16.clear();
+        t64.clear();
+        if( bit_width == 8 ) {
+            blocks.resize( idx.size() );
+            for( size_t i = 0; i < idx.size(); i++ ) {
+                uint64_t b = ( lens[idx[i]] + 3 ) / 4;
+                if( ovf8 && ovf8[idx[i]] >= 0 ) b = std::min<uint64_t>( b, (uint64_t) ovf8[idx[i]] + 1 );
+                blocks[i] = b;
+            }
+            simd_emission( blocks, 32, emit );
+            for( uint32_t e : emit ) {
+                uint32_t s = idx[e];
+                if( ovf8 && ovf8[s] >= 0 )
+                    t16.push_back( s );
+                else
+                    order.push_back( s );
+            }
+        }
+        else {
+            t16 = idx;
+        }
+        if( !t16.empty() ) {
+            blocks.resize( t16.size() );
+            for( size_t i = 0; i < t16.size(); i++ ) {
+                uint64_t b = ( lens[t16[i]] + 3 ) / 4;
+                if( ovf16 && ovf16[t16[i]] >= 0 ) b = std::min<uint64_t>( b, (uint64_t) ovf16[t16[i]] + 1 );
+                blocks[i] = b;
+            }
+            simd_emission( blocks, 16, emit );
+            for( uint32_t e : emit ) {
+                uint32_t s = t16[e];
+                if( ovf16 && ovf16[s] >= 0 )
+                    t64.push_back( s );
+                else
+                    order.push_back( s );
+            }
+        }
+        order.insert( order.end(), t64.begin(), t64.end() );
+    }
+}
+
+void replay_topk( const int32_t * scores, const uint32_t * order, size_t n, size_t k, std::vector<Hit> & out ) {
+    Heap thread_heap( k );
+    if( k > 0 ) {
+        size_t i = 0;
+        // fill phase
+        for( ; i < n && thread_heap.a.size() < k; i++ ) thread_heap.add( Hit{ order[i], scores[i] } );
+        // steady state: almost every record is rejected by one comparison with the root
+        for( ; i < n; i++ )
+            if( scores[i] > thread_heap.a[0].score ) thread_heap.add( Hit{ order[i], scores[i] } );
+    }
+    Heap result( k );  // manager.c:141-146: thread heap re-inserted in heap-array order
+    for( const Hit & h : thread_heap.a ) result.add( h );
+    out = result.a;
+    std::sort( out.begin(), out.end(), []( const Hit & x, const Hit & y ) {
+        if( x.score != y.score ) return x.score > y.score;  // minheap.c:93-102, manager.c:68-77
+        return x.db_id > y.db_id;
+    } );
+}

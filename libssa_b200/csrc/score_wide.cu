@@ -1,0 +1,45 @@
+// Instantiations + launcher of the wide (int32) scoring kernels: the exact tier for sequences whose
+// scores may not fit 16 bits, and the overflow-position tracker used to emulate the reference's
+// 8/16-bit tier order.
+#include "score_launch.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace ssa {
+
+template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArgs & args, cudaStream_t stream ) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice( &dev );
+    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
+    if( per_sm < 1 ) per_sm = 1;
+    long want = ( (long) args.nbatches + ( SCORE_THREADS / 32 ) - 1 ) / ( SCORE_THREADS / 32 );
+    int grid = sms * per_sm;
+    if( want < grid ) grid = (int) ( want < 1 ? 1 : want );
+    kernel<<<grid, SCORE_THREADS, smem_bytes, stream>>>( args );
+    return grid;
+}
+
+template<int R> static int pick( bool nw, bool multi, bool track, const ScoreArgs & a, cudaStream_t s ) {
+    const int smem = profile_words<false, R>() * 4;
+    if( nw ) return multi ? launch( score_kernel<false, R, true, true, false>, smem, a, s )
+                          : launch( score_kernel<false, R, true, false, false>, smem, a, s );
+    if( track ) return multi ? launch( score_kernel<false, R, false, true, true>, smem, a, s )
+                             : launch( score_kernel<false, R, false, false, true>, smem, a, s );
+    return multi ? launch( score_kernel<false, R, false, true, false>, smem, a, s )
+                 : launch( score_kernel<false, R, false, false, false>, smem, a, s );
+}
+
+int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & a, cudaStream_t s ) {
+    switch( R ) {
+    case 8: return pick<8>( nw, multi, track, a, s );
+    case 16: return pick<16>( nw, multi, track, a, s );
+    case 32: return pick<32>( nw, multi, track, a, s );
+    }
+    fprintf( stderr, "libssa_b200: no wide kernel for R=%d\n", R );
+    exit( 1 );
+}
+
+}  // namespace ssa

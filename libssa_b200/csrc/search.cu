@@ -1,0 +1,882 @@
+// Device side of a search: resident packed database, query profile, tier selection, kernel launches,
+// arrival-order scatter and the hand-off to the host replay.  Replaces reference
+// src/db_adapter.c (per-search chunking and re-mapping), src/algo/searcher.c + src/algo/{8,16,64}/search_*.c
+// (tier drivers) and the search half of src/algo/manager.c:120-172.
+#include "common.h"
+#include "score_launch.h"
+#include "traceback.h"
+
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <thread>
+
+using namespace ssa;
+
+#define CUDA_OK( call )                                                                                     \
+    do {                                                                                                    \
+        cudaError_t e_ = ( call );                                                                          \
+        if( e_ != cudaSuccess ) fatal( "CUDA error %s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString( e_ ) ); \
+    } while( 0 )
+
+namespace {
+
+constexpr uint32_t BATCH_COLS = 4096;  // columns per work batch of the packed tier (fill/drain = 31 steps)
+
+template<typename T> struct DevBuf {  // grow-only device buffer
+    T * p = nullptr;
+    size_t cap = 0;
+    void reserve( size_t n ) {
+        if( n <= cap ) return;
+        if( p ) cudaFree( p );
+        size_t want = n + n / 4 + 64;
+        CUDA_OK( cudaMalloc( &p, want * sizeof( T ) ) );
+        cap = want;
+    }
+    void release() {
+        if( p ) cudaFree( p );
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template<typename T> struct PinBuf {  // grow-only pinned host buffer
+    T * p = nullptr;
+    size_t cap = 0;
+    void reserve( size_t n ) {
+        if( n <= cap ) return;
+        if( p ) cudaFreeHost( p );
+        size_t want = n + n / 4 + 64;
+        CUDA_OK( cudaMallocHost( &p, want * sizeof( T ) ) );
+        cap = want;
+    }
+    void release() {
+        if( p ) cudaFreeHost( p );
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PackedDb {
+    bool valid = false;
+    uint64_t epoch = 0;
+    int symtype = -1;
+    int rank = 0, world = 1;
+    // provider order (all shards): lengths, 0 = skipped record
+    std::vector<uint64_t> lens_all;
+    uint64_t n_seqs = 0, n_residues = 0;
+    // this shard, sorted by length (descending, provider index ascending)
+    std::vector<uint32_t> sorted_id;   // provider index of sorted position s
+    std::vector<uint32_t> sorted_len;
+    uint64_t local_residues = 0;
+    size_t npairs = 0;
+    uint64_t total_cols = 0;
+    std::vector<uint64_t> pair_col;    // [npairs+1] first column of pair p in the stream
+    std::vector<Batch> batches;        // packed-tier work batches (whole pairs)
+    std::vector<uint32_t> batch_pair0; // first pair of each batch
+    DevBuf<uint16_t> d_stream;
+    DevBuf<Batch> d_batches;
+    double pack_ms = 0, upload_ms = 0;
+    // arrival order caches, keyed by (bit_width, chunk): provider indices in heap-arrival order
+    struct Arrival {
+        std::vector<uint32_t> order;       // arrival position -> provider index
+        DevBuf<int32_t> d_pos_of_sorted;   // sorted position -> arrival position (-1 = never processed)
+        bool uploaded = false;
+    };
+    std::map<std::pair<int, size_t>, Arrival> arrival;
+};
+
+struct Ctx {
+    bool init = false;
+    int device = -1;
+    int rank = 0, world = 1;
+    ssa_b200_allgather_fn allgather = nullptr;
+    void * allgather_ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+    PackedDb db;
+    DevBuf<uint32_t> d_profile, d_out_packed, d_counter, d_bnd;
+    DevBuf<int32_t> d_scores, d_arrival_scores, d_first, d_guard;
+    DevBuf<Batch> d_wide_batches;
+    DevBuf<uint32_t> d_flag_list;
+    PinBuf<uint32_t> h_profile, h_list;
+    PinBuf<int32_t> h_scores, h_first;
+    PinBuf<Batch> h_wide_batches;
+    ssa_b200_stats_t stats;
+};
+
+Ctx ctx;
+
+void ensure_ctx() {
+    if( ctx.init ) return;
+    int dev = ctx.device;
+    if( dev < 0 ) {
+        const char * lr = getenv( "LOCAL_RANK" );
+        dev = lr ? atoi( lr ) : 0;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount( &count );
+        if( e != cudaSuccess || count == 0 )
+            fatal( "libssa_b200: no CUDA device available (%s). This library has no CPU fallback.",
+                    e != cudaSuccess ? cudaGetErrorString( e ) : "device count is 0" );
+        dev %= count;
+    }
+    CUDA_OK( cudaSetDevice( dev ) );
+    ctx.device = dev;
+    CUDA_OK( cudaStreamCreateWithFlags( &ctx.stream, cudaStreamNonBlocking ) );
+    CUDA_OK( cudaEventCreate( &ctx.ev_begin ) );
+    CUDA_OK( cudaEventCreate( &ctx.ev_k0 ) );
+    CUDA_OK( cudaEventCreate( &ctx.ev_k1 ) );
+    CUDA_OK( cudaEventCreate( &ctx.ev_end ) );
+    memset( &ctx.stats, 0, sizeof( ctx.stats ) );
+    ctx.init = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// database packing: once per init_db / init_symbol_translation / shard change
+// ------------------------------------------------------------------------------------------------
+
+void parallel_for( size_t n, size_t grain, const std::function<void( size_t, size_t )> & fn );
+
+void build_db() {
+    ensure_ctx();
+    PackedDb & db = ctx.db;
+    if( db.valid && db.epoch == g_db_epoch && db.symtype == g_symtype && db.rank == ctx.rank && db.world == ctx.world ) return;
+
+    const double t0 = wall_ms();
+    if( g_symtype != NUCLEOTIDE && g_symtype != AMINOACID )
+        fatal( "Translated searches (TRANS_QUERY/TRANS_DB/TRANS_BOTH) are not available in the GPU library yet." );
+    if( g_symtype == NUCLEOTIDE && g_query_strands != FORWARD_STRAND )
+        fatal( "Nucleotide searches on the complementary strand are not available in the GPU library yet." );
+    const signed char * map = ( g_symtype == NUCLEOTIDE ) ? map_ncbi_nt16 : map_ncbi_aa;
+
+    db.arrival.clear();
+    db.lens_all.clear();
+    std::vector<const char *> text;
+    for( size_t i = 0;; i++ ) {  // the reference walks ids until the provider returns NULL (db_adapter.c:224-229)
+        p_seqinfo rec = ssa_db_get_sequence( i );
+        if( !rec ) break;
+        db.lens_all.push_back( rec->seqlen );
+        text.push_back( rec->seq );
+    }
+    const size_t nall = db.lens_all.size();
+    if( nall > 0xfffffff0ull ) fatal( "libssa_b200: more than 2^32 database records are not supported." );
+
+    std::vector<uint32_t> sorted;
+    sorted.reserve( nall );
+    db.n_residues = 0;
+    for( size_t i = 0; i < nall; i++ )
+        if( db.lens_all[i] > 0 ) {
+            sorted.push_back( (uint32_t) i );
+            db.n_residues += db.lens_all[i];
+            if( db.lens_all[i] > 0x7fffffffull ) fatal( "libssa_b200: database record %ld is too long.", (long) i );
+        }
+    db.n_seqs = sorted.size();
+    std::stable_sort( sorted.begin(), sorted.end(),
+            [&]( uint32_t a, uint32_t b ) { return db.lens_all[a] > db.lens_all[b]; } );
+
+    // shard: deal the length-sorted records round-robin
+    db.sorted_id.clear();
+    db.sorted_len.clear();
+    db.local_residues = 0;
+    for( size_t s = (size_t) ctx.rank; s < sorted.size(); s += (size_t) ctx.world ) {
+        db.sorted_id.push_back( sorted[s] );
+        db.sorted_len.push_back( (uint32_t) db.lens_all[sorted[s]] );
+        db.local_residues += db.lens_all[sorted[s]];
+    }
+    const size_t nloc = db.sorted_id.size();
+    db.npairs = ( nloc + 1 ) / 2;
+    db.pair_col.assign( db.npairs + 1, 0 );
+    for( size_t p = 0; p < db.npairs; p++ ) db.pair_col[p + 1] = db.pair_col[p] + db.sorted_len[2 * p];
+    db.total_cols = db.pair_col[db.npairs];
+
+    // column stream: bits 0-4 residue of A, 5-9 residue of B (0 past its end, like the reference's padding,
+    // src/algo/8/search_8_util.h:60-74), 10 first column, 11 last column of B, 12 last column of A
+    PinBuf<uint16_t> h_stream;
+    h_stream.reserve( db.total_cols + 64 );
+    std::vector<size_t> unknown_per_chunk( ( db.npairs + 1023 ) / 1024 + 1, 0 );
+    parallel_for( db.npairs, 1024, [&]( size_t p0, size_t p1 ) {
+        size_t unknown = 0;
+        for( size_t p = p0; p < p1; p++ ) {
+            const uint32_t la = db.sorted_len[2 * p];
+            const bool has_b = 2 * p + 1 < nloc;
+            const uint32_t lb = has_b ? db.sorted_len[2 * p + 1] : 0;
+            const unsigned char * ta = (const unsigned char *) text[db.sorted_id[2 * p]];
+            const unsigned char * tb = has_b ? (const unsigned char *) text[db.sorted_id[2 * p + 1]] : nullptr;
+            uint16_t * out = h_stream.p + db.pair_col[p];
+            for( uint32_t c = 0; c < la; c++ ) {
+                int a = map[ta[c]];
+                if( a < 0 ) {
+                    a = 0;
+                    unknown++;
+                }
+                int b = 0;
+                if( c < lb ) {
+                    b = map[tb[c]];
+                    if( b < 0 ) {
+                        b = 0;
+                        unknown++;
+                    }
+                }
+                uint32_t v = (uint32_t) a | ( (uint32_t) b << 5 );
+                if( c == 0 ) v |= COL_FIRST;
+                if( c + 1 == lb ) v |= COL_LAST_B;
+                if( c + 1 == la ) v |= COL_LAST_A;
+                out[c] = (uint16_t) v;
+            }
+        }
+        unknown_per_chunk[p0 / 1024] = unknown;
+    } );
+    size_t unknown = std::accumulate( unknown_per_chunk.begin(), unknown_per_chunk.end(), (size_t) 0 );
+    if( unknown > 0 ) print_warning( "%ld unknown symbols found and set to zero", (long) unknown );
+    for( size_t i = db.total_cols; i < db.total_cols + 64; i++ ) h_stream.p[i] = 0;
+
+    // work batches of the packed tier: whole pairs, >= BATCH_COLS columns each
+    db.batches.clear();
+    db.batch_pair0.clear();
+    for( size_t p = 0; p < db.npairs; ) {
+        Batch b;
+        memset( &b, 0, sizeof( b ) );
+        b.col0 = db.pair_col[p];
+        b.bnd0 = db.pair_col[p];
+        b.out0 = (uint32_t) p;
+        size_t q = p;
+        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < BATCH_COLS ) q++;
+        if( db.pair_col[q] - db.pair_col[p] > 0x7fffffffull ) fatal( "libssa_b200: batch too long." );
+        b.ncols = (uint32_t) ( db.pair_col[q] - db.pair_col[p] );
+        db.batches.push_back( b );
+        db.batch_pair0.push_back( (uint32_t) p );
+        p = q;
+    }
+    db.pack_ms = wall_ms() - t0;
+
+    const double t1 = wall_ms();
+    db.d_stream.reserve( db.total_cols + 64 );
+    CUDA_OK( cudaMemcpyAsync( db.d_stream.p, h_stream.p, ( db.total_cols + 64 ) * sizeof( uint16_t ), cudaMemcpyHostToDevice,
+            ctx.stream ) );
+    db.d_batches.reserve( db.batches.size() + 1 );
+    if( !db.batches.empty() )
+        CUDA_OK( cudaMemcpyAsync( db.d_batches.p, db.batches.data(), db.batches.size() * sizeof( Batch ), cudaMemcpyHostToDevice,
+                ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    h_stream.release();
+    db.upload_ms = wall_ms() - t1;
+
+    db.epoch = g_db_epoch;
+    db.symtype = g_symtype;
+    db.rank = ctx.rank;
+    db.world = ctx.world;
+    db.valid = true;
+    ctx.stats.n_seqs = db.n_seqs;
+    ctx.stats.n_residues = db.n_residues;
+    ctx.stats.local_seqs = nloc;
+    ctx.stats.local_residues = db.local_residues;
+    ctx.stats.pack_ms = db.pack_ms;
+    ctx.stats.upload_ms = db.upload_ms;
+    ctx.stats.db_device_bytes = ( db.total_cols + 64 ) * sizeof( uint16_t ) + db.batches.size() * sizeof( Batch );
+    print_info( "GPU database: %ld sequences, %ld residues, %ld columns in %ld pairs, packed in %.1f ms, uploaded in %.1f ms\n",
+            (long) nloc, (long) db.local_residues, (long) db.total_cols, (long) db.npairs, db.pack_ms, db.upload_ms );
+}
+
+void parallel_for( size_t n, size_t grain, const std::function<void( size_t, size_t )> & fn ) {
+    size_t nchunks = ( n + grain - 1 ) / grain;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = std::min<size_t>( hw ? hw : 4, nchunks );
+    if( nthreads <= 1 ) {
+        for( size_t c = 0; c < nchunks; c++ ) fn( c * grain, std::min( n, ( c + 1 ) * grain ) );
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next( 0 );
+    for( size_t t = 0; t < nthreads; t++ )
+        pool.emplace_back( [&]() {
+            for( ;; ) {
+                size_t c = next.fetch_add( 1 );
+                if( c >= nchunks ) break;
+                fn( c * grain, std::min( n, ( c + 1 ) * grain ) );
+            }
+        } );
+    for( auto & th : pool ) th.join();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels around the scoring kernels
+// ------------------------------------------------------------------------------------------------
+
+// (A:B) int16 pairs -> one int32 score per sorted position
+__global__ void unpack_scores_kernel( const uint32_t * packed, int32_t * scores, uint32_t pair0, uint32_t npairs, uint32_t nseq,
+        int32_t offset ) {
+    uint32_t p = pair0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if( p >= npairs ) return;
+    uint32_t w = packed[p];
+    scores[2 * p] = (int32_t) (int16_t) ( w >> 16 ) + offset;
+    if( 2 * p + 1 < nseq ) scores[2 * p + 1] = (int32_t) (int16_t) ( w & 0xffffu ) + offset;
+}
+
+// scores by sorted position -> scores by heap-arrival position
+__global__ void scatter_arrival_kernel( const int32_t * scores, const int32_t * pos, int32_t * out, uint32_t n ) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if( s >= n ) return;
+    int32_t a = pos[s];
+    if( a >= 0 ) out[a] = scores[s];
+}
+
+// list of sorted positions whose score reaches thr (candidates for the reference's overflow cascade)
+__global__ void flag_overflow_kernel( const int32_t * scores, uint32_t n, int32_t thr, uint32_t * list, uint32_t * count,
+        uint32_t cap ) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if( s >= n ) return;
+    if( scores[s] >= thr ) {
+        uint32_t k = atomicAdd( count, 1u );
+        if( k < cap ) list[k] = s;
+    }
+}
+
+__global__ void fill_i32_kernel( int32_t * p, int32_t v, uint32_t n ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n ) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// query profile
+// ------------------------------------------------------------------------------------------------
+
+struct Plan {
+    int npass = 1;
+    int R = 4;          // rows per lane of the packed tier
+    int wide_R = 8;
+    int wide_npass = 1;
+    int qpad = 0, wide_qpad = 0;
+    int pad_score = 0;
+    int64_t lo = 0, hi = 0;  // matrix extremes over the symbols that can occur
+};
+
+int pick_R( const int * options, int n, int rows_per_lane ) {
+    for( int i = 0; i < n; i++ )
+        if( options[i] >= rows_per_lane ) return options[i];
+    return options[n - 1];
+}
+
+Plan make_plan( size_t qlen ) {
+    Plan pl;
+    const int maxR = PACKED_R[sizeof( PACKED_R ) / sizeof( int ) - 1];
+    pl.npass = (int) ( ( qlen + 32 * maxR - 1 ) / ( 32 * maxR ) );
+    if( pl.npass < 1 ) pl.npass = 1;
+    int rows_per_pass = (int) ( ( qlen + pl.npass - 1 ) / pl.npass );
+    pl.R = pick_R( PACKED_R, sizeof( PACKED_R ) / sizeof( int ), ( rows_per_pass + 31 ) / 32 );
+    pl.qpad = pl.npass * 32 * pl.R;
+    const int wmaxR = WIDE_R[sizeof( WIDE_R ) / sizeof( int ) - 1];
+    pl.wide_npass = (int) ( ( qlen + 32 * wmaxR - 1 ) / ( 32 * wmaxR ) );
+    if( pl.wide_npass < 1 ) pl.wide_npass = 1;
+    rows_per_pass = (int) ( ( qlen + pl.wide_npass - 1 ) / pl.wide_npass );
+    pl.wide_R = pick_R( WIDE_R, sizeof( WIDE_R ) / sizeof( int ), ( rows_per_pass + 31 ) / 32 );
+    pl.wide_qpad = pl.wide_npass * 32 * pl.wide_R;
+    pl.lo = g_matrix.lo;
+    pl.hi = g_matrix.hi;
+    pl.pad_score = (int) std::min<int64_t>( pl.lo, 0 );
+    return pl;
+}
+
+// Packed profile of pass `pass`: word [(k*32 + d)*32 + lane] = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as int16,
+// rows counted from rowbase + lane*R; rows beyond the query get pad_score for every residue.
+void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
+    const int R = pl.R;
+    for( int k = 0; k < R / 2; k++ )
+        for( int d = 0; d < 32; d++ )
+            for( int lane = 0; lane < 32; lane++ ) {
+                size_t r0 = (size_t) pass * 32 * R + (size_t) lane * R + 2 * k;
+                int v0 = r0 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0]] : pl.pad_score;
+                int v1 = r0 + 1 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0 + 1]] : pl.pad_score;
+                out[( k * 32 + d ) * 32 + lane] = ( (uint32_t) (uint16_t) (int16_t) v1 << 16 ) | (uint32_t) (uint16_t) (int16_t) v0;
+            }
+}
+
+void fill_profile_wide( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
+    const int R = pl.wide_R;
+    for( int r = 0; r < R; r++ )
+        for( int d = 0; d < 32; d++ )
+            for( int lane = 0; lane < 32; lane++ ) {
+                size_t row = (size_t) pass * 32 * R + (size_t) lane * R + r;
+                int v = row < qlen ? (int) g_matrix.m[( d << 5 ) + q[row]] : pl.pad_score;
+                out[( r * 32 + d ) * 32 + lane] = (uint32_t) v;
+            }
+}
+
+// Longest database sequence the packed (int16) tier is guaranteed exact for, and the NW offset.
+// SW: 0 <= H <= hi+ * min(q, d); E, F >= gapO + gapE.  NW: with L(i,j) = 2 gapO + (i+j+2) gapE
+// a lower bound of every H (all-gap path) and hi+ * min(i+1, j+1) an upper bound, all of H, E, F and the diagonal
+// candidates stay inside [ L(q-1,d-1) + min(lo, gapO+gapE), hi+ * (min(q,d) + 1) ].
+int64_t packed_safe_len( const Plan & pl, bool nw, int qrows, int32_t * offset ) {
+    const int64_t hip = std::max<int64_t>( pl.hi, 0 );
+    const int64_t lom = std::min<int64_t>( std::min<int64_t>( pl.lo, 0 ), (int64_t) g_gapO + g_gapE );
+    *offset = 0;
+    if( !nw ) {
+        if( hip == 0 ) return INT64_MAX;
+        // hi+ * (min(q,d) + 1) <= 32767
+        int64_t m = 32767 / hip - 1;
+        if( m >= qrows ) return INT64_MAX;
+        return m < 0 ? 0 : m;
+    }
+    // find the largest d with hi(d) - lo(d) <= 65000
+    auto span = [&]( int64_t d, int64_t * lo_out, int64_t * hi_out ) {
+        int64_t hi = hip * ( std::min<int64_t>( qrows, d ) + 1 );
+        int64_t lo = 2 * (int64_t) g_gapO + ( (int64_t) qrows + d + 2 ) * (int64_t) g_gapE + lom + std::min<int64_t>( 2 * (int64_t) g_gapO, 0 );
+        if( lo > 0 ) lo = 0;
+        *lo_out = lo;
+        *hi_out = hi;
+        return hi - lo;
+    };
+    int64_t lo, hi;
+    int64_t d_lo = 0, d_hi = 1 << 30;
+    if( span( 1, &lo, &hi ) > 65000 ) return 0;
+    while( d_lo + 1 < d_hi ) {  // span is monotone in d
+        int64_t mid = ( d_lo + d_hi ) / 2;
+        if( span( mid, &lo, &hi ) <= 65000 )
+            d_lo = mid;
+        else
+            d_hi = mid;
+    }
+    return d_lo;
+}
+
+int32_t nw_offset_for( const Plan & pl, int qrows, int64_t dmax ) {
+    const int64_t hip = std::max<int64_t>( pl.hi, 0 );
+    const int64_t lom = std::min<int64_t>( std::min<int64_t>( pl.lo, 0 ), (int64_t) g_gapO + g_gapE );
+    int64_t hi = hip * ( std::min<int64_t>( qrows, dmax ) + 1 );
+    int64_t lo = 2 * (int64_t) g_gapO + ( (int64_t) qrows + dmax + 2 ) * (int64_t) g_gapE + lom + std::min<int64_t>( 2 * (int64_t) g_gapO, 0 );
+    if( lo > 0 ) lo = 0;
+    return (int32_t) ( ( hi + lo ) / 2 );  // centre the value range on 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// scoring of the whole shard: scores by sorted position in ctx.d_scores
+// ------------------------------------------------------------------------------------------------
+
+void launch_fill( int32_t * p, int32_t v, size_t n ) {
+    if( n == 0 ) return;
+    fill_i32_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx.stream>>>( p, v, (uint32_t) n );
+    ctx.stats.launches++;
+}
+
+// runs the wide tier over `items` (slots = sorted positions); optional first-crossing tracking
+void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t qlen, const Plan & pl, bool nw, bool track,
+        int32_t * d_first8, int32_t * d_first16 ) {
+    PackedDb & db = ctx.db;
+    if( slots.empty() ) return;
+    const size_t n = slots.size();
+    ctx.h_wide_batches.reserve( n );
+    uint64_t bnd = 0;
+    for( size_t i = 0; i < n; i++ ) {
+        Batch b;
+        memset( &b, 0, sizeof( b ) );
+        uint32_t s = slots[i];
+        b.col0 = db.pair_col[s / 2];
+        b.bnd0 = bnd;
+        b.ncols = db.sorted_len[s];
+        b.out0 = s;
+        b.half = s & 1;
+        bnd += b.ncols;
+        ctx.h_wide_batches.p[i] = b;
+    }
+    ctx.d_wide_batches.reserve( n );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches.p, ctx.h_wide_batches.p, n * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
+    ctx.stats.h2d_bytes += n * sizeof( Batch );
+    const int npass = pl.wide_npass, R = pl.wide_R;
+    const size_t words = (size_t) R * 1024;
+    ctx.h_profile.reserve( words * npass );
+    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile.p + p * words, q, qlen, pl, p );
+    ctx.d_profile.reserve( words * npass );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_profile.p, ctx.h_profile.p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
+    ctx.stats.h2d_bytes += words * npass * 4;
+    if( npass > 1 ) ctx.d_bnd.reserve( 4 * bnd + 256 );
+    ctx.d_counter.reserve( 64 );
+    for( int p = 0; p < npass; p++ ) {
+        CUDA_OK( cudaMemsetAsync( ctx.d_counter.p, 0, 4, ctx.stream ) );
+        ScoreArgs a;
+        memset( &a, 0, sizeof( a ) );
+        a.stream = db.d_stream.p;
+        a.batches = ctx.d_wide_batches.p;
+        a.nbatches = (uint32_t) n;
+        a.counter = ctx.d_counter.p;
+        a.profile = ctx.d_profile.p + p * words;
+        a.gap_open_extend = (int) g_gapO + (int) g_gapE;
+        a.gap_extend = g_gapE;
+        a.gap_open = g_gapO;
+        a.offset = 0;
+        a.rowbase = p * 32 * R;
+        a.cap_lane = -1;
+        a.cap_row = 0;
+        if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + 32 * R ) {
+            a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
+            a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
+        }
+        a.first_pass = ( p == 0 );
+        a.out = ctx.d_scores.p;
+        a.first8 = d_first8;
+        a.first16 = d_first16;
+        a.thr8 = 255;
+        a.thr16 = 65535;
+        if( npass > 1 ) {
+            uint32_t * base = ctx.d_bnd.p;
+            uint32_t * h0 = base, * f0 = base + bnd, * h1 = base + 2 * bnd, * f1 = base + 3 * bnd;
+            a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
+            a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
+            a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
+            a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
+        }
+        launch_score_wide( R, nw, npass > 1, track, a, ctx.stream );
+        ctx.stats.launches++;
+    }
+    ctx.stats.wide_tier_seqs += n;
+}
+
+void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    ctx.d_scores.reserve( nloc + 2 );
+    if( nloc == 0 ) return;
+    if( qlen == 0 ) fatal( "libssa_b200: empty query." );
+    if( qlen > ( 1u << 24 ) || ( qlen + db.sorted_len[0] ) > ( 1ull << 24 ) )
+        fatal( "libssa_b200: query/database sequences beyond 2^24 symbols are not supported by the 32-bit tier." );
+    Plan pl = make_plan( qlen );
+
+    // tier split: pairs whose longer sequence exceeds the packed tier's guaranteed range go to the wide tier
+    int32_t offset = 0;
+    int64_t safe = packed_safe_len( pl, nw, pl.qpad, &offset );
+    if( (int) g_gapO + (int) g_gapE > 0 || g_gapE > 0 ) safe = 0;  // positive "penalties": only the wide tier is valid
+    size_t p0 = 0;  // first pair that is safe (pairs are sorted by descending length of A)
+    {
+        size_t lo = 0, hi = db.npairs;
+        while( lo < hi ) {
+            size_t mid = ( lo + hi ) / 2;
+            if( (int64_t) db.sorted_len[2 * mid] > safe )
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        p0 = lo;
+    }
+    size_t b0 = std::lower_bound( db.batch_pair0.begin(), db.batch_pair0.end(), (uint32_t) p0 ) - db.batch_pair0.begin();
+    size_t pair_start = b0 < db.batches.size() ? db.batch_pair0[b0] : db.npairs;
+    if( nw && pair_start < db.npairs ) offset = nw_offset_for( pl, pl.qpad, db.sorted_len[2 * pair_start] );
+
+    CUDA_OK( cudaEventRecord( ctx.ev_k0, ctx.stream ) );
+    // ---- packed tier ----
+    if( b0 < db.batches.size() ) {
+        const int npass = pl.npass, R = pl.R;
+        const size_t words = (size_t) ( R / 2 ) * 1024;
+        ctx.h_profile.reserve( words * npass );
+        for( int p = 0; p < npass; p++ ) fill_profile_packed( ctx.h_profile.p + p * words, q, qlen, pl, p );
+        ctx.d_profile.reserve( words * npass );
+        CUDA_OK( cudaMemcpyAsync( ctx.d_profile.p, ctx.h_profile.p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
+        ctx.stats.h2d_bytes += words * npass * 4;
+        ctx.d_out_packed.reserve( db.npairs + 1 );
+        ctx.d_counter.reserve( 64 );
+        ctx.d_guard.reserve( 4 );
+        if( npass > 1 ) ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
+        for( int p = 0; p < npass; p++ ) {
+            CUDA_OK( cudaMemsetAsync( ctx.d_counter.p, 0, 4, ctx.stream ) );
+            ScoreArgs a;
+            memset( &a, 0, sizeof( a ) );
+            a.stream = db.d_stream.p;
+            a.batches = db.d_batches.p + b0;
+            a.nbatches = (uint32_t) ( db.batches.size() - b0 );
+            a.counter = ctx.d_counter.p;
+            a.profile = ctx.d_profile.p + p * words;
+            a.gap_open_extend = (int) g_gapO + (int) g_gapE;
+            a.gap_extend = g_gapE;
+            a.gap_open = g_gapO;
+            a.offset = offset;
+            a.rowbase = p * 32 * R;
+            a.cap_lane = -1;
+            if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + 32 * R ) {
+                a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
+                a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
+            }
+            a.first_pass = ( p == 0 );
+            a.out = ctx.d_out_packed.p;
+            a.guard = nullptr;
+            if( npass > 1 ) {
+                uint32_t * base = ctx.d_bnd.p;
+                const uint64_t n = db.total_cols;
+                uint32_t * h0 = base, * f0 = base + n, * h1 = base + 2 * n, * f1 = base + 3 * n;
+                a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
+                a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
+                a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
+                a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
+            }
+            launch_score_packed( R, nw, npass > 1, a, ctx.stream );
+            ctx.stats.launches++;
+        }
+        const uint32_t np = (uint32_t) ( db.npairs - pair_start );
+        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_out_packed.p, ctx.d_scores.p, (uint32_t) pair_start,
+                (uint32_t) db.npairs, (uint32_t) nloc, offset );
+        ctx.stats.launches++;
+    }
+    // ---- wide tier for the unsafe prefix ----
+    if( pair_start > 0 ) {
+        std::vector<uint32_t> slots;
+        for( size_t s = 0; s < std::min( nloc, 2 * pair_start ); s++ ) slots.push_back( (uint32_t) s );
+        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr );
+    }
+    CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
+}
+
+PackedDb::Arrival & arrival_for( int bit_width, size_t chunk ) {
+    PackedDb & db = ctx.db;
+    auto key = std::make_pair( bit_width, chunk );
+    auto it = db.arrival.find( key );
+    if( it != db.arrival.end() ) return it->second;
+    PackedDb::Arrival & ar = db.arrival[key];
+    arrival_order( db.lens_all, nullptr, nullptr, chunk, bit_width, ar.order );
+    return ar;
+}
+
+void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_pos ) {
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    std::vector<int32_t> pos_of_id( db.lens_all.size(), -1 );
+    for( size_t a = 0; a < order.size(); a++ ) pos_of_id[order[a]] = (int32_t) a;
+    std::vector<int32_t> pos( nloc );
+    for( size_t s = 0; s < nloc; s++ ) pos[s] = pos_of_id[db.sorted_id[s]];
+    d_pos.reserve( nloc + 1 );
+    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos.data(), nloc * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    ctx.stats.h2d_bytes += nloc * sizeof( int32_t );
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// entry points used by api.cpp
+// ------------------------------------------------------------------------------------------------
+
+void gpu_prepare_db() { build_db(); }
+
+void gpu_release() {
+    if( !ctx.init ) return;
+    cudaStreamSynchronize( ctx.stream );
+    ctx.db.d_stream.release();
+    ctx.db.d_batches.release();
+    for( auto & kv : ctx.db.arrival ) kv.second.d_pos_of_sorted.release();
+    ctx.db.arrival.clear();
+    ctx.db.valid = false;
+    ctx.d_profile.release();
+    ctx.d_out_packed.release();
+    ctx.d_counter.release();
+    ctx.d_bnd.release();
+    ctx.d_scores.release();
+    ctx.d_arrival_scores.release();
+    ctx.d_first.release();
+    ctx.d_guard.release();
+    ctx.d_wide_batches.release();
+    ctx.d_flag_list.release();
+    ctx.h_profile.release();
+    ctx.h_list.release();
+    ctx.h_scores.release();
+    ctx.h_first.release();
+    ctx.h_wide_batches.release();
+    traceback_release();
+    cudaEventDestroy( ctx.ev_begin );
+    cudaEventDestroy( ctx.ev_k0 );
+    cudaEventDestroy( ctx.ev_k1 );
+    cudaEventDestroy( ctx.ev_end );
+    cudaStreamDestroy( ctx.stream );
+    ctx.init = false;
+}
+
+size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64_t * scores, uint64_t * ids ) {
+    build_db();
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    ctx.stats.launches = 0;
+    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
+    ctx.stats.wide_tier_seqs = 0;
+    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    score_shard( query, qlen, search_type == NEEDLEMAN_WUNSCH );
+    ctx.h_scores.reserve( nloc + 1 );
+    if( nloc ) CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_scores.p, nloc * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    ctx.stats.d2h_bytes += nloc * sizeof( int32_t );
+    float ms = 0;
+    if( nloc ) {
+        cudaEventElapsedTime( &ms, ctx.ev_k0, ctx.ev_k1 );
+        ctx.stats.score_kernel_ms = ms;
+    }
+    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
+    ctx.stats.device_ms = ms;
+    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
+    // provider order of this shard
+    std::vector<uint32_t> by_id( nloc );
+    std::iota( by_id.begin(), by_id.end(), 0u );
+    std::sort( by_id.begin(), by_id.end(), [&]( uint32_t a, uint32_t b ) { return db.sorted_id[a] < db.sorted_id[b]; } );
+    for( size_t i = 0; i < nloc; i++ ) {
+        if( scores ) scores[i] = ctx.h_scores.p[by_id[i]];
+        if( ids ) ids[i] = db.sorted_id[by_id[i]];
+    }
+    return nloc;
+}
+
+void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
+    const double t_call = wall_ms();
+    build_db();
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
+    out.clear();
+    ctx.stats.launches = 0;
+    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
+    ctx.stats.wide_tier_seqs = 0;
+    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
+    ctx.stats.cells = (uint64_t) req.qlen * db.local_residues;
+    if( ctx.world > 1 ) fatal( "libssa_b200: sharded searches are driven through the multi-GPU entry points." );
+
+    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    score_shard( req.query, req.qlen, nw );
+
+    // ---- which records would the reference have pushed through its overflow cascade? (SW only) ----
+    std::vector<int64_t> ovf8, ovf16;
+    bool have_overflow = false;
+    if( !nw && nloc > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+        const int32_t thr = req.bit_width == 8 ? 255 : 65535;
+        const uint32_t cap = (uint32_t) nloc;
+        ctx.d_flag_list.reserve( cap + 2 );
+        uint32_t * d_count = ctx.d_flag_list.p + cap;
+        CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx.stream ) );
+        flag_overflow_kernel<<<( cap + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_scores.p, cap, thr, ctx.d_flag_list.p, d_count, cap );
+        ctx.stats.launches++;
+        ctx.h_list.reserve( cap + 2 );
+        CUDA_OK( cudaMemcpyAsync( ctx.h_list.p + cap, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        const uint32_t count = ctx.h_list.p[cap];
+        ctx.stats.d2h_bytes += 4;
+        if( count > 0 ) {
+            have_overflow = true;
+            CUDA_OK( cudaMemcpyAsync( ctx.h_list.p, ctx.d_flag_list.p, count * 4, cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            ctx.stats.d2h_bytes += count * 4;
+            std::vector<uint32_t> slots( ctx.h_list.p, ctx.h_list.p + count );
+            std::sort( slots.begin(), slots.end() );
+            // first columns at which the running maximum reaches 255 / 65535, via the tracking wide kernel
+            ctx.d_first.reserve( 2 * nloc + 2 );
+            int32_t * d_f8 = ctx.d_first.p, * d_f16 = ctx.d_first.p + nloc;
+            launch_fill( ctx.d_first.p, INT_MAX, 2 * nloc );
+            Plan pl = make_plan( req.qlen );
+            // the tracking launch rewrites d_scores for these slots with the same exact values
+            run_wide( slots, req.query, req.qlen, pl, false, true, d_f8, d_f16 );
+            ctx.h_first.reserve( 2 * nloc + 2 );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, ctx.d_first.p, 2 * nloc * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            ctx.stats.d2h_bytes += 2 * nloc * sizeof( int32_t );
+            ovf8.assign( db.lens_all.size(), -1 );
+            ovf16.assign( db.lens_all.size(), -1 );
+            for( uint32_t s : slots ) {
+                const uint32_t id = db.sorted_id[s];
+                const int32_t c8 = ctx.h_first.p[s], c16 = ctx.h_first.p[nloc + s];
+                if( req.bit_width == 8 && c8 != INT_MAX ) {
+                    ovf8[id] = c8 / 4;
+                    ctx.stats.overflow_8++;
+                }
+                if( c16 != INT_MAX ) {
+                    ovf16[id] = c16 / 4;
+                    ctx.stats.overflow_16++;
+                }
+            }
+        }
+    }
+
+    // ---- heap-arrival order of the emulated one-thread reference run ----
+    const std::vector<uint32_t> * order = nullptr;
+    std::vector<uint32_t> order_ovf;
+    DevBuf<int32_t> * d_pos = nullptr;
+    DevBuf<int32_t> d_pos_tmp;
+    if( !have_overflow ) {
+        PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size );
+        if( !ar.uploaded ) {
+            upload_positions( ar.order, ar.d_pos_of_sorted );
+            ar.uploaded = true;
+        }
+        order = &ar.order;
+        d_pos = &ar.d_pos_of_sorted;
+    }
+    else {
+        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), g_chunk_size, req.bit_width, order_ovf );
+        upload_positions( order_ovf, d_pos_tmp );
+        order = &order_ovf;
+        d_pos = &d_pos_tmp;
+    }
+    const size_t narr = order->size();
+    std::vector<Hit> hits;
+    if( narr > 0 && nloc > 0 ) {
+        ctx.d_arrival_scores.reserve( narr + 1 );
+        scatter_arrival_kernel<<<(unsigned) ( ( nloc + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_scores.p, d_pos->p,
+                ctx.d_arrival_scores.p, (uint32_t) nloc );
+        ctx.stats.launches++;
+        ctx.h_scores.reserve( narr + 1 );
+        CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+        CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        ctx.stats.d2h_bytes += narr * sizeof( int32_t );
+        replay_topk( ctx.h_scores.p, order->data(), narr, req.hitcount, hits );
+    }
+    else {
+        CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    }
+    d_pos_tmp.release();
+
+    if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
+        print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
+                (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
+
+    // ---- result records ----
+    const signed char * map = ( g_symtype == NUCLEOTIDE ) ? map_ncbi_nt16 : map_ncbi_aa;
+    out.resize( hits.size() );
+    for( size_t i = 0; i < hits.size(); i++ ) {
+        out[i].hit = hits[i];
+        p_seqinfo rec = ssa_db_get_sequence( hits[i].db_id );
+        if( !rec ) fatal( "Could not get sequence from DB: %ld", (long) hits[i].db_id );  // aligner.c:66-68
+        out[i].db_codes.resize( rec->seqlen );
+        map_db_sequence( rec->seq, rec->seqlen, out[i].db_codes.data(), map );
+    }
+    if( req.align_type == COMPUTE_ALIGNMENT && !out.empty() ) {
+        traceback_hits( ctx.stream, req.query, req.qlen, nw, out, &ctx.stats );
+    }
+
+    float ms = 0;
+    if( nloc ) {
+        cudaEventElapsedTime( &ms, ctx.ev_k0, ctx.ev_k1 );
+        ctx.stats.score_kernel_ms = ms;
+    }
+    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
+    ctx.stats.device_ms = ms;
+    ctx.stats.call_ms = wall_ms() - t_call;
+}
+
+// ---- additive API (include/libssa_b200.h) ----
+extern "C" {
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_device( int device ) {
+    if( ctx.init && ctx.device != device ) gpu_release();
+    ctx.device = device;
+}
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_shard( int rank, int world_size ) {
+    if( world_size < 1 || rank < 0 || rank >= world_size ) fatal( "libssa_b200: invalid shard %d of %d", rank, world_size );
+    ctx.rank = rank;
+    ctx.world = world_size;
+}
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_allgather( ssa_b200_allgather_fn fn, void * c ) {
+    ctx.allgather = fn;
+    ctx.allgather_ctx = c;
+}
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_prepare_db( void ) { build_db(); }
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_get_stats( ssa_b200_stats_t * out ) {
+    if( out ) *out = ctx.stats;
+}
+__attribute__( ( visibility( "default" ) ) ) int ssa_b200_version( void ) { return 100; }
+}
