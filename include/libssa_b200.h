@@ -72,6 +72,18 @@ void ssa_b200_get_stats( ssa_b200_stats_t * out );
  */
 size_t ssa_b200_score_all( p_query p, int nw, int64_t * scores, uint64_t * ids );
 
+/*
+ * Host-only pieces of the hit selection (no GPU involved): the one-thread heap-arrival order of the
+ * reference scheduler, the bounded-heap replay, and the global length-sorted order that defines the
+ * shards.  The multi-process merge is built from these; exposed so it can be tested on CPU.
+ * lens[n] are record lengths in provider order (0 = skipped record); ovf8/ovf16 may be NULL.
+ */
+size_t ssa_b200_host_arrival_order( const uint64_t * lens, size_t n, size_t chunk, int bit_width, const int64_t * ovf8,
+        const int64_t * ovf16, uint32_t * order_out );
+size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
+        uint64_t * ids_out, int64_t * scores_out );
+size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out );
+
 /* library/ABI version: major*10000 + minor*100 + patch */
 int ssa_b200_version( void );
 

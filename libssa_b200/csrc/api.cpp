@@ -5,6 +5,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #define API extern "C" __attribute__( ( visibility( "default" ) ) )
 
@@ -187,4 +188,35 @@ API size_t ssa_b200_score_all( p_query query, int nw, int64_t * scores, uint64_t
     int strand, frame;
     sequence_t q = query_frame( query, &strand, &frame );
     return gpu_score_all( (const uint8_t *) q.seq, q.len, nw ? NEEDLEMAN_WUNSCH : SMITH_WATERMAN, scores, ids );
+}
+
+// ---- host-only helpers of the hit selection (no GPU needed): used by the multi-process merge and its CPU tests ----
+API size_t ssa_b200_host_arrival_order( const uint64_t * lens, size_t n, size_t chunk, int bit_width, const int64_t * ovf8,
+        const int64_t * ovf16, uint32_t * order_out ) {
+    std::vector<uint64_t> l( lens, lens + n );
+    std::vector<uint32_t> order;
+    arrival_order( l, ovf8, ovf16, chunk, bit_width, order );
+    for( size_t i = 0; i < order.size(); i++ ) order_out[i] = order[i];
+    return order.size();
+}
+
+API size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
+        uint64_t * ids_out, int64_t * scores_out ) {
+    std::vector<Hit> hits;
+    replay_topk( scores_in_arrival_order, order, n, hitcount, hits );
+    for( size_t i = 0; i < hits.size(); i++ ) {
+        ids_out[i] = hits[i].db_id;
+        scores_out[i] = hits[i].score;
+    }
+    return hits.size();
+}
+
+// global length-sorted order (descending length, provider index ascending); shard r owns positions r, r+world, ...
+API size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out ) {
+    std::vector<uint32_t> sorted;
+    for( size_t i = 0; i < n; i++ )
+        if( lens[i] > 0 ) sorted.push_back( (uint32_t) i );
+    std::stable_sort( sorted.begin(), sorted.end(), [&]( uint32_t a, uint32_t b ) { return lens[a] > lens[b]; } );
+    for( size_t i = 0; i < sorted.size(); i++ ) sorted_out[i] = sorted[i];
+    return sorted.size();
 }

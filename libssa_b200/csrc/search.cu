@@ -72,7 +72,8 @@ struct PackedDb {
     std::vector<uint64_t> lens_all;
     uint64_t n_seqs = 0, n_residues = 0;
     // this shard, sorted by length (descending, provider index ascending)
-    std::vector<uint32_t> sorted_id;   // provider index of sorted position s
+    std::vector<uint32_t> sorted_all;  // provider index of GLOBAL sorted position g (all shards); shard r holds g = s*world + r
+    std::vector<uint32_t> sorted_id;   // provider index of local sorted position s
     std::vector<uint32_t> sorted_len;
     uint64_t local_residues = 0;
     size_t npairs = 0;
@@ -86,7 +87,7 @@ struct PackedDb {
     // arrival order caches, keyed by (bit_width, chunk): provider indices in heap-arrival order
     struct Arrival {
         std::vector<uint32_t> order;       // arrival position -> provider index
-        DevBuf<int32_t> d_pos_of_sorted;   // sorted position -> arrival position (-1 = never processed)
+        DevBuf<int32_t> d_pos_of_sorted;   // GLOBAL sorted position -> arrival position (-1 = never processed)
         bool uploaded = false;
     };
     std::map<std::pair<int, size_t>, Arrival> arrival;
@@ -102,7 +103,8 @@ struct Ctx {
     cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
     PackedDb db;
     DevBuf<uint32_t> d_profile, d_out_packed, d_counter, d_bnd;
-    DevBuf<int32_t> d_scores, d_arrival_scores, d_first, d_guard;
+    DevBuf<int32_t> d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
+    std::vector<uint32_t> order_tmp;
     DevBuf<Batch> d_wide_batches;
     DevBuf<uint32_t> d_flag_list;
     PinBuf<uint32_t> h_profile, h_list;
@@ -181,6 +183,7 @@ void build_db() {
             [&]( uint32_t a, uint32_t b ) { return db.lens_all[a] > db.lens_all[b]; } );
 
     // shard: deal the length-sorted records round-robin
+    db.sorted_all = sorted;
     db.sorted_id.clear();
     db.sorted_len.clear();
     db.local_residues = 0;
@@ -318,22 +321,30 @@ __global__ void unpack_scores_kernel( const uint32_t * packed, int32_t * scores,
     if( 2 * p + 1 < nseq ) scores[2 * p + 1] = (int32_t) (int16_t) ( w & 0xffffu ) + offset;
 }
 
-// scores by sorted position -> scores by heap-arrival position
-__global__ void scatter_arrival_kernel( const int32_t * scores, const int32_t * pos, int32_t * out, uint32_t n ) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if( s >= n ) return;
-    int32_t a = pos[s];
-    if( a >= 0 ) out[a] = scores[s];
+// scores by (rank, local sorted position) -> scores by heap-arrival position.  `gathered` holds `world` blocks of
+// `stride` scores (the all-gathered shard results; world = 1: the local scores); shard r's local position s is the
+// global sorted position s*world + r.
+__global__ void scatter_arrival_kernel( const int32_t * gathered, const int32_t * pos, int32_t * out, uint32_t stride,
+        uint32_t world, uint32_t nglobal ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= stride * world ) return;
+    uint32_t r = i / stride, sl = i % stride;
+    uint64_t g = (uint64_t) sl * world + r;
+    if( g >= nglobal ) return;
+    int32_t a = pos[g];
+    if( a >= 0 ) out[a] = gathered[i];
 }
 
-// list of sorted positions whose score reaches thr (candidates for the reference's overflow cascade)
-__global__ void flag_overflow_kernel( const int32_t * scores, uint32_t n, int32_t thr, uint32_t * list, uint32_t * count,
-        uint32_t cap ) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if( s >= n ) return;
-    if( scores[s] >= thr ) {
+// gathered indices (r*stride + s) of the records whose score reaches thr: candidates of the reference's overflow cascade
+__global__ void flag_overflow_kernel( const int32_t * gathered, uint32_t stride, uint32_t world, uint32_t nglobal, int32_t thr,
+        uint32_t * list, uint32_t * count, uint32_t cap ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= stride * world ) return;
+    uint32_t r = i / stride, sl = i % stride;
+    if( (uint64_t) sl * world + r >= nglobal ) return;
+    if( gathered[i] >= thr ) {
         uint32_t k = atomicAdd( count, 1u );
-        if( k < cap ) list[k] = s;
+        if( k < cap ) list[k] = i;
     }
 }
 
@@ -538,7 +549,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
 void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     PackedDb & db = ctx.db;
     const size_t nloc = db.sorted_id.size();
-    ctx.d_scores.reserve( nloc + 2 );
+    ctx.d_scores.reserve( ( db.sorted_all.size() + ctx.world - 1 ) / ctx.world + 2 );
     if( nloc == 0 ) return;
     if( qlen == 0 ) fatal( "libssa_b200: empty query." );
     if( qlen > ( 1u << 24 ) || ( qlen + db.sorted_len[0] ) > ( 1ull << 24 ) )
@@ -639,15 +650,28 @@ PackedDb::Arrival & arrival_for( int bit_width, size_t chunk ) {
 
 void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_pos ) {
     PackedDb & db = ctx.db;
-    const size_t nloc = db.sorted_id.size();
+    const size_t nglob = db.sorted_all.size();
     std::vector<int32_t> pos_of_id( db.lens_all.size(), -1 );
     for( size_t a = 0; a < order.size(); a++ ) pos_of_id[order[a]] = (int32_t) a;
-    std::vector<int32_t> pos( nloc );
-    for( size_t s = 0; s < nloc; s++ ) pos[s] = pos_of_id[db.sorted_id[s]];
-    d_pos.reserve( nloc + 1 );
-    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos.data(), nloc * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
+    std::vector<int32_t> pos( nglob );
+    for( size_t g = 0; g < nglob; g++ ) pos[g] = pos_of_id[db.sorted_all[g]];
+    d_pos.reserve( nglob + 1 );
+    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos.data(), nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
     CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-    ctx.stats.h2d_bytes += nloc * sizeof( int32_t );
+    ctx.stats.h2d_bytes += nglob * sizeof( int32_t );
+}
+
+// all-gather `count` int32 per rank from d_send into d_recv (rank-major); world = 1: plain copy
+void gather_i32( const int32_t * d_send, int32_t * d_recv, size_t count ) {
+    if( ctx.world == 1 ) {
+        if( d_send != d_recv )
+            CUDA_OK( cudaMemcpyAsync( d_recv, d_send, count * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx.stream ) );
+        return;
+    }
+    if( !ctx.allgather )
+        fatal( "libssa_b200: the database is sharded over %d processes but no all-gather collective was registered "
+               "(ssa_b200_set_allgather).", ctx.world );
+    ctx.allgather( ctx.allgather_ctx, d_send, d_recv, count * sizeof( int32_t ), (void *) ctx.stream );
 }
 
 }  // namespace
@@ -673,6 +697,8 @@ void gpu_release() {
     ctx.d_scores.release();
     ctx.d_arrival_scores.release();
     ctx.d_first.release();
+    ctx.d_gathered.release();
+    ctx.d_pos_tmp.release();
     ctx.d_guard.release();
     ctx.d_wide_batches.release();
     ctx.d_flag_list.release();
@@ -728,6 +754,9 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     build_db();
     PackedDb & db = ctx.db;
     const size_t nloc = db.sorted_id.size();
+    const size_t nglob = db.sorted_all.size();
+    const size_t world = (size_t) ctx.world;
+    const size_t stride = ( nglob + world - 1 ) / world;  // local positions per rank, padded
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     out.clear();
     ctx.stats.launches = 0;
@@ -735,50 +764,70 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     ctx.stats.wide_tier_seqs = 0;
     ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
     ctx.stats.cells = (uint64_t) req.qlen * db.local_residues;
-    if( ctx.world > 1 ) fatal( "libssa_b200: sharded searches are driven through the multi-GPU entry points." );
 
     CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    ctx.d_scores.reserve( stride + 2 );
     score_shard( req.query, req.qlen, nw );
 
+    // ---- shard results -> every rank (NCCL all-gather over NVLink, supplied by the host language) ----
+    int32_t * d_all = ctx.d_scores.p;
+    if( world > 1 ) {
+        ctx.d_gathered.reserve( stride * world + 2 );
+        gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
+        d_all = ctx.d_gathered.p;
+    }
+
     // ---- which records would the reference have pushed through its overflow cascade? (SW only) ----
+    // A record overflows the 8-bit tier when its score reaches 255 and the 16-bit tier at 65535
+    // (reference src/algo/simd/search_simd_sw.c:372-379,422-423); it then leaves its SIMD channel after the 4-column
+    // block in which the running maximum got there, which changes the order in which scores reach the heap.
     std::vector<int64_t> ovf8, ovf16;
     bool have_overflow = false;
-    if( !nw && nloc > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+    if( !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const int32_t thr = req.bit_width == 8 ? 255 : 65535;
-        const uint32_t cap = (uint32_t) nloc;
-        ctx.d_flag_list.reserve( cap + 2 );
-        uint32_t * d_count = ctx.d_flag_list.p + cap;
+        const uint32_t total = (uint32_t) ( stride * world );
+        ctx.d_flag_list.reserve( total + 2 );
+        uint32_t * d_count = ctx.d_flag_list.p + total;
         CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx.stream ) );
-        flag_overflow_kernel<<<( cap + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_scores.p, cap, thr, ctx.d_flag_list.p, d_count, cap );
+        flag_overflow_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world,
+                (uint32_t) nglob, thr, ctx.d_flag_list.p, d_count, total );
         ctx.stats.launches++;
-        ctx.h_list.reserve( cap + 2 );
-        CUDA_OK( cudaMemcpyAsync( ctx.h_list.p + cap, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
+        ctx.h_list.reserve( total + 2 );
+        CUDA_OK( cudaMemcpyAsync( ctx.h_list.p + total, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
         CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        const uint32_t count = ctx.h_list.p[cap];
+        const uint32_t count = ctx.h_list.p[total];
         ctx.stats.d2h_bytes += 4;
-        if( count > 0 ) {
+        if( count > 0 ) {  // every rank sees the same gathered scores, so every rank takes this branch together
             have_overflow = true;
             CUDA_OK( cudaMemcpyAsync( ctx.h_list.p, ctx.d_flag_list.p, count * 4, cudaMemcpyDeviceToHost, ctx.stream ) );
             CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
             ctx.stats.d2h_bytes += count * 4;
-            std::vector<uint32_t> slots( ctx.h_list.p, ctx.h_list.p + count );
-            std::sort( slots.begin(), slots.end() );
+            std::vector<uint32_t> flagged( ctx.h_list.p, ctx.h_list.p + count );  // gathered indices r*stride + s
+            std::sort( flagged.begin(), flagged.end() );
+            std::vector<uint32_t> slots;  // this rank's own flagged local positions
+            for( uint32_t i : flagged )
+                if( i / stride == (uint32_t) ctx.rank ) slots.push_back( (uint32_t) ( i % stride ) );
             // first columns at which the running maximum reaches 255 / 65535, via the tracking wide kernel
-            ctx.d_first.reserve( 2 * nloc + 2 );
-            int32_t * d_f8 = ctx.d_first.p, * d_f16 = ctx.d_first.p + nloc;
-            launch_fill( ctx.d_first.p, INT_MAX, 2 * nloc );
+            ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+            int32_t * d_f = ctx.d_first.p;  // [stride] first8 | [stride] first16
+            launch_fill( d_f, INT_MAX, 2 * stride );
             Plan pl = make_plan( req.qlen );
-            // the tracking launch rewrites d_scores for these slots with the same exact values
-            run_wide( slots, req.query, req.qlen, pl, false, true, d_f8, d_f16 );
-            ctx.h_first.reserve( 2 * nloc + 2 );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, ctx.d_first.p, 2 * nloc * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride );  // rewrites the same exact scores
+            int32_t * d_f_all = d_f;
+            if( world > 1 ) {
+                d_f_all = ctx.d_first.p + 2 * stride;
+                gather_i32( d_f, d_f_all, 2 * stride );
+            }
+            ctx.h_first.reserve( 2 * stride * world + 2 );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_f_all, 2 * stride * world * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
             CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += 2 * nloc * sizeof( int32_t );
+            ctx.stats.d2h_bytes += 2 * stride * world * sizeof( int32_t );
             ovf8.assign( db.lens_all.size(), -1 );
             ovf16.assign( db.lens_all.size(), -1 );
-            for( uint32_t s : slots ) {
-                const uint32_t id = db.sorted_id[s];
-                const int32_t c8 = ctx.h_first.p[s], c16 = ctx.h_first.p[nloc + s];
+            for( uint32_t i : flagged ) {
+                const size_t r = i / stride, sl = i % stride;
+                const uint32_t id = db.sorted_all[sl * world + r];
+                const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
                 if( req.bit_width == 8 && c8 != INT_MAX ) {
                     ovf8[id] = c8 / 4;
                     ctx.stats.overflow_8++;
@@ -793,9 +842,7 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
 
     // ---- heap-arrival order of the emulated one-thread reference run ----
     const std::vector<uint32_t> * order = nullptr;
-    std::vector<uint32_t> order_ovf;
     DevBuf<int32_t> * d_pos = nullptr;
-    DevBuf<int32_t> d_pos_tmp;
     if( !have_overflow ) {
         PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size );
         if( !ar.uploaded ) {
@@ -806,17 +853,18 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         d_pos = &ar.d_pos_of_sorted;
     }
     else {
-        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), g_chunk_size, req.bit_width, order_ovf );
-        upload_positions( order_ovf, d_pos_tmp );
-        order = &order_ovf;
-        d_pos = &d_pos_tmp;
+        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), g_chunk_size, req.bit_width, ctx.order_tmp );
+        upload_positions( ctx.order_tmp, ctx.d_pos_tmp );
+        order = &ctx.order_tmp;
+        d_pos = &ctx.d_pos_tmp;
     }
     const size_t narr = order->size();
     std::vector<Hit> hits;
-    if( narr > 0 && nloc > 0 ) {
+    if( narr > 0 && nglob > 0 ) {
         ctx.d_arrival_scores.reserve( narr + 1 );
-        scatter_arrival_kernel<<<(unsigned) ( ( nloc + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_scores.p, d_pos->p,
-                ctx.d_arrival_scores.p, (uint32_t) nloc );
+        const uint32_t total = (uint32_t) ( stride * world );
+        scatter_arrival_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, d_pos->p, ctx.d_arrival_scores.p,
+                (uint32_t) stride, (uint32_t) world, (uint32_t) nglob );
         ctx.stats.launches++;
         ctx.h_scores.reserve( narr + 1 );
         CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
@@ -829,7 +877,6 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
         CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     }
-    d_pos_tmp.release();
 
     if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
         print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",

@@ -48,5 +48,28 @@ for n, seed in ((3000, 7), (20000, 20150403)):
     compare("synth%d blosum62 P07327" % n, AMINOACID, "blosum62", (-11, -1), path, D + "/P07327", k=25)
     compare("synth%d blosum62 O74807" % n, AMINOACID, "blosum62", (-11, -1), path, D + "/O74807", k=25, widths=(16, 8))
 compare("synth20000 blosum50 P33450", AMINOACID, "blosum50", (-3, -1), path, D + "/P33450", k=10, widths=(16,), modes=("sw",))
+
+def compare_align(name, sym, scoring, gaps, db, qfile, k=10, widths=(16,), modes=("sw", "nw")):
+    global fails
+    qp = setup(prod, sym, scoring, gaps, db, qfile)
+    qr = setup(ref, sym, scoring, gaps, db, qfile)
+    for mode in modes:
+        for bw in widths:
+            t0 = time.time(); hp = getattr(prod, mode + "_align")(qp, k, bw, COMPUTE_ALIGNMENT); tp = time.time() - t0
+            t0 = time.time(); hr = getattr(ref, mode + "_align")(qr, k, bw, COMPUTE_ALIGNMENT); tr = time.time() - t0
+            a = [h.key() for h in hp]; b = [h.key() for h in hr]
+            ok = a == b
+            fails += (not ok)
+            print("ALIGN %-28s %s %2d  %s  prod %.3fs ref %.3fs" % (name, mode, bw, "OK" if ok else "MISMATCH", tp, tr))
+            if not ok:
+                for x, y in zip(a, b):
+                    if x != y: print("   prod", x); print("   ref ", y); break
+
+compare_align("AF091148 const(5,-4)", NUCLEOTIDE, (5, -4), (-4, -2), D + "/AF091148.fas", D + "/one_seq.fas", k=5, widths=(64, 16))
+compare_align("AF091148 const(2,-2)", NUCLEOTIDE, (2, -2), (-4, -2), D + "/AF091148.fas", D + "/one_seq.fas", k=20)
+compare_align("test.fas const(1,-1)", NUCLEOTIDE, (1, -1), (-1, -1), D + "/test.fas", D + "/one_seq.fas", k=5)
+compare_align("synth20000 blosum62 P07327", AMINOACID, "blosum62", (-11, -1), path, D + "/P07327", k=25)
+compare_align("synth20000 blosum62 O74807", AMINOACID, "blosum62", (-11, -1), path, D + "/O74807", k=25)
+compare_align("synth20000 blosum50 P27895", AMINOACID, "blosum50", (-3, -1), path, D + "/P27895", k=10)
 print("FAILS", fails)
 sys.exit(1 if fails else 0)
