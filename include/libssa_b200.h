@@ -84,6 +84,9 @@ size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint
         uint64_t * ids_out, int64_t * scores_out );
 size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out );
 
+/* copies the current 32x32 score table (index (db_symbol << 5) + query_symbol); 0 if scoring is not initialised */
+int ssa_b200_get_score_matrix( int64_t * out_1024 );
+
 /* library/ABI version: major*10000 + minor*100 + patch */
 int ssa_b200_version( void );
 

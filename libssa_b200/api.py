@@ -185,6 +185,59 @@ class LibSSA:
 
     def version(self): return self.lib.ssa_b200_version()
 
+    def score_matrix(self):
+        """The current 32x32 score table as a numpy int64 array ([db_symbol, query_symbol]), or None."""
+        import numpy as np
+        m = np.zeros(1024, dtype=np.int64)
+        self.lib.ssa_b200_get_score_matrix.argtypes = [C.POINTER(C.c_int64)]
+        self.lib.ssa_b200_get_score_matrix.restype = C.c_int
+        ok = self.lib.ssa_b200_get_score_matrix(m.ctypes.data_as(C.POINTER(C.c_int64)))
+        return m.reshape(32, 32) if ok else None
+
+    # ---- host-only pieces of the hit selection (no GPU involved) ----
+    def host_arrival_order(self, lens, chunk, bit_width, ovf8=None, ovf16=None):
+        import numpy as np
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        out = np.zeros(max(len(lens), 1), dtype=np.uint32)
+        f = self.lib.ssa_b200_host_arrival_order
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        o8 = None if ovf8 is None else np.ascontiguousarray(ovf8, dtype=np.int64)
+        o16 = None if ovf16 is None else np.ascontiguousarray(ovf16, dtype=np.int64)
+        n = f(lens.ctypes.data, len(lens), chunk, bit_width, None if o8 is None else o8.ctypes.data,
+              None if o16 is None else o16.ctypes.data, out.ctypes.data)
+        return out[:n]
+
+    def host_replay(self, scores_in_arrival_order, order, hitcount):
+        import numpy as np
+        sc = np.ascontiguousarray(scores_in_arrival_order, dtype=np.int32)
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        ids = np.zeros(max(hitcount, 1), dtype=np.uint64)
+        out = np.zeros(max(hitcount, 1), dtype=np.int64)
+        f = self.lib.ssa_b200_host_replay
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        n = f(sc.ctypes.data, order.ctypes.data, len(order), hitcount, ids.ctypes.data, out.ctypes.data)
+        return [(int(out[i]), int(ids[i])) for i in range(n)]
+
+    def host_sorted_order(self, lens):
+        import numpy as np
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        out = np.zeros(max(len(lens), 1), dtype=np.uint32)
+        f = self.lib.ssa_b200_host_sorted_order
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        n = f(lens.ctypes.data, len(lens), out.ctypes.data)
+        return out[:n]
+
+    def set_allgather(self, fn):
+        """Register the collective that merges shard results: fn(send_ptr, recv_ptr, nbytes, cuda_stream_ptr)."""
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+        self._allgather_cb = proto(lambda ctx, s, r, n, st: fn(s, r, n, st)) if fn else proto()
+        self.lib.ssa_b200_set_allgather.argtypes = [proto, C.c_void_p]
+        self.lib.ssa_b200_set_allgather.restype = None
+        self.lib.ssa_b200_set_allgather(self._allgather_cb, None)
+
 
 _loaded = None
 

@@ -220,3 +220,10 @@ API size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t
     for( size_t i = 0; i < sorted.size(); i++ ) sorted_out[i] = sorted[i];
     return sorted.size();
 }
+
+// the current 32x32 score table, index (db_symbol << 5) + query_symbol; returns 0 if no scoring is set
+API int ssa_b200_get_score_matrix( int64_t * out ) {
+    if( !g_matrix.set ) return 0;
+    memcpy( out, g_matrix.m, sizeof( g_matrix.m ) );
+    return 1;
+}

@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (libssa.h entry points of libssa_b200.so),
+against (1) the committed fixtures generated from the compiled reference, (2) the compiled reference live
+on fresh random inputs, (3) the oracle port's exact scores, and (4) size-independent properties on a
+database of BASELINE scale.  Integer work: every comparison is bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SEARCHES = json.load(open(os.path.join(GOLD, "searches.json")))
+MATS = json.load(open(os.path.join(GOLD, "matrices.json")))
+
+
+def matrix_of(scoring):
+    key = scoring if isinstance(scoring, str) else "const_%d_%d" % tuple(scoring)
+    return np.array(MATS[key], dtype=np.int64).reshape(32, 32)
+
+
+def assert_same_hits(got, exp, mode, bw, what):
+    if cases.TIE_AWARE(mode, bw):
+        # scores identical; identical records above the cut-off score
+        assert [g[0] for g in got] == [e[0] for e in exp], what
+        if exp:
+            cut = exp[-1][0]
+            assert [g[:2] for g in got if g[0] > cut] == [e[:2] for e in exp if e[0] > cut], what
+    else:
+        assert got == exp, what
+
+
+@pytest.mark.parametrize("entry", SEARCHES, ids=[e["case"]["name"] for e in SEARCHES])
+def test_fixtures_through_c_abi(prod, entry):
+    case, expected = entry["case"], entry["result"]
+    got = cases.run_case(prod, case)
+    for run, g, e in zip(case["runs"], got, expected):
+        assert_same_hits(g, e, run[0], run[1], (case["name"], run))
+
+
+def test_live_reference_random_inputs(prod, ref, tmp_path):
+    from libssa_b200 import synth
+    rng = np.random.default_rng(2024)
+    for trial in range(6):
+        n = int(rng.integers(1, 3000))
+        qlen = int(rng.choice([1, 2, 17, 33, 128, 129, 250, 700, 1300]))
+        q = synth.random_protein(rng, qlen)
+        seqs = synth.protein_db(n, int(rng.integers(1, 1 << 30)), query=q, homolog_frac=0.03, n_dup=min(20, n // 3),
+                                mu=float(rng.choice([3.0, 5.0])), sigma=0.7, min_len=0, max_len=4000)
+        path = tmp_path / ("live%d.fas" % trial)
+        synth.write_fasta(str(path), seqs)
+        scoring = ["blosum62", "blosum45", "pam30", [4, -3]][trial % 4]
+        gaps = [[-11, -1], [-3, -1], [-5, -5], [0, -2]][trial % 4]
+        case = {"symtype": cases.AMINOACID, "scoring": scoring, "gaps": gaps, "db": str(path), "query_string": q,
+                "chunk": [1000, 64][trial % 2],
+                "runs": [[m, w, 30, cases.COMPUTE_SCORE] for m in ("sw", "nw") for w in (64, 16, 8)]
+                        + [["sw", 16, 6, cases.COMPUTE_ALIGNMENT], ["nw", 16, 6, cases.COMPUTE_ALIGNMENT]]}
+        exp = cases.run_case(ref, case)
+        got = cases.run_case(prod, case)
+        for run, g, e in zip(case["runs"], got, exp):
+            assert_same_hits(g, e, run[0], run[1], ("trial", trial, n, qlen, scoring, gaps, run))
+
+
+@pytest.mark.parametrize("qlen", [1, 3, 64, 127, 128, 130, 255, 384, 385, 500, 768, 1024, 1025, 2100])
+def test_exact_scores_vs_oracle_port(prod, port, tmp_path, qlen):
+    """every kernel shape (rows per lane 4..32, one and several passes), both tiers, SW and NW"""
+    from libssa_b200 import synth
+    rng = np.random.default_rng(qlen)
+    q = synth.random_protein(rng, qlen)
+    seqs = synth.protein_db(300, qlen + 1, query=q, homolog_frac=0.1, n_dup=10, mu=4.8, sigma=0.9, min_len=1, max_len=3000)
+    path = tmp_path / "db.fas"
+    synth.write_fasta(str(path), seqs)
+    codes = [port.map_db(s, False) for s in seqs]
+    qc = port.map_query(q, False)
+    for scoring, gaps in (("blosum62", (-11, -1)), ([127, -1], (-1, -1)), ([2, -100], (-120, -7))):
+        prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+        if isinstance(scoring, str):
+            prod.init_score_matrix(cases.MATRIX_BUILDIN, scoring)
+        else:
+            prod.init_constant_scores(*scoring)
+        prod.init_gap_penalties(*gaps)
+        prod.init_db(str(path))
+        qh = prod.init_sequence_fasta(cases.READ_FROM_STRING, q)
+        M = matrix_of(scoring) if isinstance(scoring, str) or "const_%d_%d" % tuple(scoring) in MATS else port.constant_matrix(*scoring)
+        for nw in (False, True):
+            ids, sc = prod.score_all(qh, nw)
+            assert ids.tolist() == list(range(len(seqs)))
+            exp = port.score_db(codes, qc, M, gaps[0], gaps[1], nw)
+            bad = np.nonzero(sc != exp)[0]
+            assert len(bad) == 0, (qlen, scoring, gaps, nw, bad[:5], sc[bad[:5]], exp[bad[:5]])
+        prod.free_sequence(qh)
+
+
+def test_nucleotide_long_query_wide_tier(prod, port, tmp_path):
+    """BASELINE config 5 in small: 3 kbp query, match 5: NW leaves the 16-bit range for the long homologs"""
+    from libssa_b200 import synth
+    q = synth.random_nucleotide(5, 3000, iupac_rate=0.02)
+    seqs = synth.nucleotide_db(120, 6, query=q, n_homologs=12, mu=6.5, sigma=0.6, min_len=20, max_len=6000)
+    seqs[3] = q                                   # exact copy: SW = NW = 5 * (number of unambiguous-match columns...)
+    path = tmp_path / "nt.fas"
+    synth.write_fasta(str(path), seqs)
+    prod.init_symbol_translation(cases.NUCLEOTIDE, 1, 1, 1)
+    prod.init_constant_scores(5, -4)
+    prod.init_gap_penalties(-4, -2)
+    prod.init_db(str(path))
+    qh = prod.init_sequence_fasta(cases.READ_FROM_STRING, q)
+    codes = [port.map_db(s, True) for s in seqs]
+    qc = port.map_query(q, True)
+    M = matrix_of([5, -4])
+    for nw in (False, True):
+        _, sc = prod.score_all(qh, nw)
+        assert (sc == port.score_db(codes, qc, M, -4, -2, nw)).all()
+    hits = prod.sw_align(qh, 3, 16, cases.COMPUTE_ALIGNMENT)
+    assert hits[0].db_id == 3 and hits[0].cigar == "3000M" and hits[0].score == sc.max()
+    for h in hits:
+        region, cig = port.cigar(qc, codes[h.db_id], M, -4, -2, False)
+        assert (cig, region) == (h.cigar, (h.q_start, h.q_end, h.d_start, h.d_end))
+    prod.free_sequence(qh)
+
+
+def test_result_record_contract(prod):
+    """reference src/algo/aligner.c:62-93, src/libssa.h:85-117: code strings, lengths, COMPUTE_SCORE leaves the alignment empty,
+    hitcount larger than the database shortens the list, order = score desc then ID desc"""
+    case = SEARCHES[3]["case"]          # test.fas, 5 records
+    q = cases.configure(prod, case)
+    hits = prod.sw_align(q, 50, 16, cases.COMPUTE_SCORE)
+    assert len(hits) == 5
+    assert all(h.cigar is None and h.cigar_len == 0 and h.q_start == h.q_end == h.d_start == h.d_end == 0 for h in hits)
+    assert all(len(h.db_seq) == h.db_len and max(h.db_seq) < 16 for h in hits)
+    keys = [(h.score, h.db_id) for h in hits]
+    assert keys == sorted(keys, reverse=True)
+    hits = prod.nw_align(q, 2, 64, cases.COMPUTE_ALIGNMENT)
+    assert len(hits) == 2 and all(h.cigar and h.cigar_len == len(h.cigar) for h in hits)
+    assert prod.sw_align(q, 0, 16, cases.COMPUTE_SCORE) == []
+    prod.free_sequence(q)
+
+
+@pytest.fixture(scope="module")
+def big_db(tmp_path_factory):
+    """100 000 records / 33 M residues: BASELINE-scale database for the property tests (larger than L2 once packed)."""
+    from libssa_b200 import synth
+    q = cases.query_text("P07327")
+    seqs = synth.protein_db(100000, 20150402, query=q)
+    path = tmp_path_factory.mktemp("big") / "s100k.fas"
+    synth.write_fasta(str(path), seqs)
+    return str(path), seqs, q
+
+
+def test_full_size_properties(prod, port, big_db, tmp_path):
+    path, seqs, qtext = big_db
+    prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    prod.init_score_matrix(cases.MATRIX_BUILDIN, "blosum62")
+    prod.init_gap_penalties(-11, -1)
+    prod.init_db(path)
+    q = prod.init_sequence_fasta(cases.READ_FROM_FILE, os.path.join(cases.DATA, "P07327"))
+    ids, sw = prod.score_all(q, False)
+    _, nw = prod.score_all(q, True)
+    assert len(ids) == len(seqs) and (ids == np.arange(len(seqs))).all()
+    # (1) a sample of the records, exact against the oracle port
+    rng = np.random.default_rng(1)
+    sample = np.concatenate([rng.choice(len(seqs), 300, replace=False), np.argsort(sw)[-20:]])
+    codes = [port.map_db(seqs[i], False) for i in sample]
+    qc = port.map_query(qtext, False)
+    M = matrix_of("blosum62")
+    assert (sw[sample] == port.score_db(codes, qc, M, -11, -1, False)).all()
+    assert (nw[sample] == port.score_db(codes, qc, M, -11, -1, True)).all()
+    # (2) bounds that hold for every record: 0 <= SW <= 11 * min(len), NW <= SW, SW >= score of the best diagonal start
+    lens = np.array([len(s) for s in seqs])
+    assert (sw >= 0).all() and (sw <= 11 * np.minimum(lens, 375)).all() and (nw <= sw).all()
+    # (3) exact duplicates of a record score identically (the generator plants 50)
+    first = {}
+    dup = 0
+    for i, s in enumerate(seqs):
+        if s in first:
+            dup += 1
+            assert sw[i] == sw[first[s]] and nw[i] == nw[first[s]]
+        else:
+            first[s] = i
+    assert dup >= 40
+    # (4) hit lists: identical for every entry bit width above the cut-off score, and equal to a replay of the score vector
+    lists = {bw: [(h.score, h.db_id) for h in prod.sw_align(q, 100, bw, cases.COMPUTE_SCORE)] for bw in (64, 16, 8)}
+    cut = lists[64][-1][0]
+    for bw in (16, 8):
+        assert [x for x in lists[bw] if x[0] > cut] == [x for x in lists[64] if x[0] > cut]
+        assert [x[0] for x in lists[bw]] == [x[0] for x in lists[64]]
+    order = prod.host_arrival_order(lens, 1000, 64)
+    assert lists[64] == prod.host_replay(sw[order], order, 100)
+    assert prod.stats().overflow_8 == int((sw >= 255).sum())          # counted during the bw = 8 search above
+    # (5) permutation invariance: the same records in another provider order get the same scores
+    perm = rng.permutation(len(seqs))
+    from libssa_b200 import synth
+    p2 = tmp_path / "perm.fas"
+    synth.write_fasta(str(p2), [seqs[i] for i in perm])
+    prod.init_db(str(p2))
+    _, sw2 = prod.score_all(q, False)
+    assert (sw2 == sw[perm]).all()
+    prod.free_sequence(q)

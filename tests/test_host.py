@@ -1,0 +1,185 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the headers
+declare, and its host logic (matrices, query parsing, arrival-order emulation, heap replay, shard plan)
+agrees with the oracle.  No search is run here - that needs a GPU (tests/test_gpu_parity.py)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+MATS = json.load(open(os.path.join(GOLD, "matrices.json")))
+
+
+def declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b([a-z_0-9]+)\s*\([^;{}]*\)\s*;", txt)
+    txt = re.sub(r"typedef[^;]*;", "", txt)
+    names = re.findall(r"\b([a-z_0-9]+)\s*\([^;{}]*\)\s*;", txt)
+    return sorted(set(n for n in names if n not in ("void", "int", "size_t")))
+
+
+def test_library_exports_every_declared_symbol(prod_host):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", prod_host.path]).decode()
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    for header in ("libssa.h", "libssa_b200.h", "libssa_extern_db.h"):
+        fns = declared_functions(header)
+        assert len(fns) >= 4, header
+        missing = [f for f in fns if f not in exported]
+        assert not missing, (header, missing)
+    # nothing but the API is exported (internal names of the reference like `fatal` or `xmalloc` stay hidden)
+    stray = [s for s in exported if not re.match(r"^(ssa_|set_|init_|free_|sw_align|nw_align)", s)]
+    assert not stray, stray
+
+
+def test_sass_is_sm100a_and_uses_dpx(prod_host):
+    out = subprocess.run(["cuobjdump", "-sass", prod_host.path], capture_output=True, text=True).stdout
+    assert "EF_CUDA_SM100" in out
+    for mnemonic in ("VIADDMNMX.S16x2", "VIMNMX3.S16x2", "VIADD.16x2", "SHFL.UP", "PRMT"):
+        assert mnemonic in out, mnemonic
+
+
+@pytest.mark.parametrize("name", ["blosum45", "blosum50", "blosum62", "blosum80", "blosum90", "pam30", "pam70", "pam250"])
+def test_builtin_matrices_equal_reference(prod_host, name):
+    prod_host.init_score_matrix(cases.MATRIX_BUILDIN, name)
+    assert prod_host.score_matrix().reshape(-1).tolist() == MATS[name]
+
+
+@pytest.mark.parametrize("pair", [(1, -1), (2, -2), (5, -4), (127, -1)])
+def test_constant_matrices_equal_reference(prod_host, pair):
+    """first argument = match score (reference src/libssa.c:115-117); row/column 0 stay -1 (tests/test_matrices.c:115-124)"""
+    prod_host.init_constant_scores(*pair)
+    m = prod_host.score_matrix()
+    assert m.reshape(-1).tolist() == MATS["const_%d_%d" % pair]
+    assert m[3, 3] == pair[0] and m[3, 4] == pair[1] and m[0, 5] == -1 and m[5, 0] == -1
+
+
+def test_matrix_from_string_and_file(prod_host, tmp_path):
+    text = "# comment\n   A  R  N\nA  4 -1 -2\nR -1  5  0\nN -2  0  6\n"
+    prod_host.init_score_matrix(cases.READ_FROM_STRING, text)
+    m = prod_host.score_matrix()
+    A, R, N = 1, 16, 13
+    assert (m[A, A], m[A, R], m[R, N], m[N, N], m[2, 2]) == (4, -1, 0, 6, -1)
+    p = tmp_path / "m.txt"
+    p.write_text(text)
+    prod_host.init_score_matrix(cases.READ_FROM_FILE, str(p))
+    assert (prod_host.score_matrix() == m).all()
+
+
+class _Seq(C.Structure):
+    _fields_ = [("seq", C.POINTER(C.c_char)), ("len", C.c_size_t)]
+
+
+class _Query(C.Structure):  # reference src/libssa_datatypes.h:100-107
+    _fields_ = [("nt", _Seq * 2), ("aa", _Seq * 6), ("header", C.c_char_p), ("headerlen", C.c_size_t),
+                ("map", C.c_void_p), ("sym", C.c_void_p)]
+
+
+def _codes(seq):
+    return list(C.string_at(seq.seq, seq.len))
+
+
+def test_query_mapping_matches_oracle(prod_host, port):
+    prod_host.set_output_mode(0)
+    prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    text = "MKV-LA?x b*UOJz\n"
+    q = prod_host.init_sequence_fasta(cases.READ_FROM_STRING, text)
+    got = _codes(C.cast(q, C.POINTER(_Query)).contents.aa[0])
+    assert got == port.map_query(text, False).tolist()      # unknown symbols removed (query.c:102-130)
+    prod_host.free_sequence(q)
+    prod_host.init_symbol_translation(cases.NUCLEOTIDE, 1, 1, 1)
+    q = prod_host.init_sequence_fasta(cases.READ_FROM_STRING, "ACGTUacgtu-NRYKM#")
+    got = _codes(C.cast(q, C.POINTER(_Query)).contents.nt[0])
+    assert got == port.map_query("ACGTUacgtu-NRYKM#", True).tolist()
+    prod_host.free_sequence(q)
+
+
+def test_query_from_fasta_file(prod_host, port):
+    prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    q = prod_host.init_sequence_fasta(cases.READ_FROM_FILE, os.path.join(cases.DATA, "P07327"))
+    s = C.cast(q, C.POINTER(_Query)).contents
+    assert s.aa[0].len == 375                               # reference benchmark/results/query_length:16
+    assert _codes(s.aa[0]) == port.map_query(cases.query_text("P07327"), False).tolist()
+    assert s.header.startswith(b"sp|P07327")
+    prod_host.free_sequence(q)
+    assert prod_host.init_sequence_fasta(cases.READ_FROM_FILE, "/nonexistent/file") is None
+
+
+def test_default_fasta_provider_contract(prod_host):
+    """reference tests/test_libssa_extern_db.c:12-58"""
+    L = prod_host.lib
+
+    class SeqInfo(C.Structure):
+        _fields_ = [("ID", C.c_size_t), ("seqlen", C.c_size_t), ("seq", C.c_char_p)]
+    L.ssa_db_get_sequence.restype = C.POINTER(SeqInfo)
+    L.ssa_db_get_sequence.argtypes = [C.c_size_t]
+    L.ssa_db_get_sequence_count.restype = C.c_size_t
+    L.ssa_db_close()
+    L.ssa_db_close()                                         # tolerates "nothing open"
+    prod_host.init_db(os.path.join(cases.DATA, "AF091148.fas"))
+    assert L.ssa_db_get_sequence_count() == 1403
+    for i in (0, 1, 700, 1402):
+        assert L.ssa_db_get_sequence(i).contents.ID == i
+    assert not L.ssa_db_get_sequence(1403) and not L.ssa_db_get_sequence(1404)
+    prod_host.init_db(os.path.join(cases.DATA, "one_seq.fas"))
+    assert L.ssa_db_get_sequence(0).contents.seqlen == 54 and not L.ssa_db_get_sequence(1)
+
+
+def _random_lens(rng, n):
+    lens = np.clip(np.rint(rng.lognormal(4.5, 0.8, n)), 0, 3000).astype(np.uint64)
+    lens[rng.random(n) < 0.03] = 0                          # skipped records
+    return lens
+
+
+@pytest.mark.parametrize("bit_width", [8, 16, 64])
+@pytest.mark.parametrize("chunk", [1000, 100, 7])
+def test_arrival_order_matches_oracle(prod_host, port, bit_width, chunk):
+    rng = np.random.default_rng(bit_width * 1000 + chunk)
+    for n in (1, 5, 31, 33, 257, 2500):
+        lens = _random_lens(rng, n)
+        ovf8 = np.where(rng.random(n) < 0.1, rng.integers(0, 40, n), -1).astype(np.int64)
+        ovf16 = np.where((ovf8 >= 0) & (rng.random(n) < 0.3), ovf8 + rng.integers(0, 5, n), -1).astype(np.int64)
+        for o8, o16 in ((None, None), (ovf8, ovf16)):
+            a = prod_host.host_arrival_order(lens, chunk, bit_width, o8, o16)
+            b = port.arrival_order(lens, chunk, bit_width, o8, o16)
+            assert a.tolist() == b.tolist()
+
+
+def test_arrival_order_stops_at_empty_chunk(prod_host):
+    """a chunk without a non-empty record ends the reference's search loop (src/algo/16/search_16.c:123)"""
+    lens = np.array([5, 6, 0, 0, 7, 8], dtype=np.uint64)
+    assert prod_host.host_arrival_order(lens, 2, 64).tolist() == [0, 1]
+    assert prod_host.host_arrival_order(lens, 3, 64).tolist() == [0, 1, 4, 5]
+
+
+def test_replay_matches_oracle_with_ties(prod_host, port):
+    rng = np.random.default_rng(5)
+    for n, k in ((1, 1), (10, 20), (500, 10), (5000, 50), (5000, 1)):
+        scores = rng.integers(-5, 12, n).astype(np.int64)       # many ties at the cut-off
+        order = rng.permutation(n).astype(np.uint64)
+        got = prod_host.host_replay(scores[order], order, k)
+        assert got == port.topk_replay(scores, order, k)
+    assert prod_host.host_replay(np.arange(20), np.arange(20), 5) == [(19, 19), (18, 18), (17, 17), (16, 16), (15, 15)]
+    assert prod_host.host_replay(np.zeros(0), np.zeros(0), 5) == []
+
+
+def test_sharded_merge_two_ranks_gloo(tmp_path):
+    """World-size-2 run of the shard/all-gather/replay logic on CPU (gloo): each rank scores its shard
+    with the oracle standing in for the GPU kernels, the shard scores are all-gathered exactly as
+    libssa_b200 does it (rank-major blocks of `stride` scores), and both ranks must reproduce the
+    one-process hit list."""
+    script = os.path.join(ROOT, "tests", "dist_merge_worker.py")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", script, str(tmp_path)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("MERGE_OK") == 2, out.stdout
