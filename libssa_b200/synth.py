@@ -5,6 +5,8 @@ background frequencies; a fraction of the records are mutated copies of the quer
 homologs, so that scores cross the 8-bit tier limit) and a few exact duplicates are added so that
 ties straddle the top-k cut-off.
 """
+import os
+
 import numpy as np
 
 AA = "ARNDCQEGHILKMFPSTWYV"
@@ -100,3 +102,39 @@ def write_fasta(path, seqs, prefix="seq"):
                 f.write("\n")
             if len(s) == 0:
                 f.write("\n")
+
+
+# ---- large databases: chunked, multi-process, deterministic per (seed, chunk) ----
+
+_CHUNK = 50000
+
+
+def _protein_chunk(args):
+    n, seed, chunk_idx, query, homolog_frac, n_dup = args
+    seqs = protein_db(n, [seed, chunk_idx], query=query, homolog_frac=homolog_frac, n_dup=n_dup)
+    base = chunk_idx * _CHUNK
+    return "".join(">s%d\n%s\n" % (base + i, s) for i, s in enumerate(seqs)).encode(), sum(len(s) for s in seqs)
+
+
+def write_protein_db(path, n, seed, query=None, homolog_frac=0.01, n_dup=50, workers=None):
+    """Writes an n-record synthetic protein FASTA file (one line per sequence); returns the residue count.
+    Record i lives in chunk i // 50000, generated from the RNG stream (seed, chunk)."""
+    import multiprocessing as mp
+    jobs = []
+    for c in range((n + _CHUNK - 1) // _CHUNK):
+        m = min(_CHUNK, n - c * _CHUNK)
+        jobs.append((m, seed, c, query, homolog_frac, n_dup if m > 2 * n_dup else 0))
+    workers = workers or min(len(jobs), max(1, (os.cpu_count() or 2) - 1))
+    total = 0
+    with open(path, "wb") as f:
+        if workers > 1:
+            with mp.get_context("fork").Pool(workers) as pool:
+                for blob, res in pool.imap(_protein_chunk, jobs):
+                    f.write(blob)
+                    total += res
+        else:
+            for j in jobs:
+                blob, res = _protein_chunk(j)
+                f.write(blob)
+                total += res
+    return total
