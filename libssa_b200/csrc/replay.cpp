@@ -20,32 +20,35 @@
 
 namespace {
 
-// Emission order of one chunk through `channels` SIMD channels; blocks[i] = blocks record i occupies.
+// Emission order of one chunk through `channels` SIMD channels; blocks[i] = blocks record i occupies its channel.
+// Event-driven form of the reference loop: a channel loaded at iteration T with a record of b blocks is found
+// finished at the scan of iteration T + b; scans visit channels in index order, emitting and refilling as they go.
+// A binary heap keyed by (finish iteration, channel) yields exactly that order in O(n log channels).
 void simd_emission( const std::vector<uint64_t> & blocks, int channels, std::vector<uint32_t> & emit ) {
     const size_t n = blocks.size();
     emit.clear();
     emit.reserve( n );
-    std::vector<int64_t> cur( channels, -1 );
-    std::vector<uint64_t> left( channels, 0 );
+    typedef std::pair<uint64_t, uint32_t> Event;  // (finish iteration << 6 | channel, record)
+    std::vector<Event> heap;
+    heap.reserve( channels );
+    auto cmp = []( const Event & a, const Event & b ) { return a.first > b.first; };
     size_t next = 0;
-    while( emit.size() < n ) {
-        for( int c = 0; c < channels; c++ ) {
-            if( left[c] != 0 ) continue;
-            if( cur[c] >= 0 ) {
-                emit.push_back( (uint32_t) cur[c] );
-                cur[c] = -1;
-            }
-            if( next < n ) {
-                cur[c] = (int64_t) next;
-                left[c] = blocks[next++];
-            }
+    for( int c = 0; c < channels && next < n; c++ ) {  // first scan: all channels are empty and are filled in order
+        heap.push_back( Event( ( blocks[next] << 6 ) | (uint64_t) c, (uint32_t) next ) );
+        next++;
+    }
+    std::make_heap( heap.begin(), heap.end(), cmp );
+    while( !heap.empty() ) {
+        std::pop_heap( heap.begin(), heap.end(), cmp );
+        const Event e = heap.back();
+        heap.pop_back();
+        emit.push_back( e.second );
+        if( next < n ) {
+            const uint64_t now = e.first >> 6, c = e.first & 63;
+            heap.push_back( Event( ( ( now + blocks[next] ) << 6 ) | c, (uint32_t) next ) );
+            std::push_heap( heap.begin(), heap.end(), cmp );
+            next++;
         }
-        if( emit.size() == n ) break;
-        uint64_t step = UINT64_MAX;
-        for( int c = 0; c < channels; c++ )
-            if( cur[c] >= 0 ) step = std::min( step, left[c] );
-        for( int c = 0; c < channels; c++ )
-            if( cur[c] >= 0 ) left[c] -= step;
     }
 }
 

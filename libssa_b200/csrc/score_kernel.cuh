@@ -53,6 +53,9 @@ struct ScoreArgs {
     uint32_t nbatches;
     uint32_t * counter;        // work queue head
     const uint32_t * profile;  // this pass' query profile, laid out for shared memory
+    uint32_t group;            // lanes per systolic array: 4, 8, 16 or 32
+    uint32_t qr_word;          // gapO + gapE as the tier's register word (packed: replicated in both halves)
+    uint32_t rg_word;          // gapE likewise
     int32_t gap_open_extend;   // gapO + gapE (negative)
     int32_t gap_extend;        // gapE
     int32_t gap_open;          // gapO
@@ -113,12 +116,20 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
     for( int i = threadIdx.x; i < profile_words<PACKED, R>(); i += blockDim.x ) prof[i] = a.profile[i];
     __syncthreads();
 
+    // A warp is split into 32/G independent systolic arrays of G lanes (G = 4, 8, 16 or 32, chosen per query so
+    // that G*R covers the query with few padded rows while R stays large enough to amortise the per-step work).
     const int lane = threadIdx.x & 31;
+    const int G = (int) a.group;
+    const int gmask = G - 1;
+    const int gl = lane & gmask;                                   // lane within the group
+    const unsigned group_mask = ( G == 32 ? FULL : ( ( 1u << G ) - 1u ) << ( lane & ~gmask ) );
+    const bool is_top = gl == 0;
+    const bool is_bottom = gl == gmask;
     const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * 4;
-    const T QR = A::bcast( a.gap_open_extend );
-    const T RG = A::bcast( a.gap_extend );
-    const int row0 = a.rowbase + lane * R;
-    const bool gen_top = ( lane == 0 ) && ( a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
+    const T QR = (T) a.qr_word;   // gapO + gapE, replicated per half for the packed tier
+    const T RG = (T) a.rg_word;   // gapE
+    const int row0 = a.rowbase + gl * R;
+    const bool gen_top = is_top && ( a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
 
     // per-lane constants of a sequence start (NW: reference needleman_wunsch_64.c:39-42,51-52)
     T diag_init, h_init, e_init, top_h_init, top_f_init;
@@ -133,248 +144,268 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
         diag_init = h_init = e_init = top_h_init = top_f_init = A::bcast( 0 );
     }
 
+    T Hp[R], E[R];
+#pragma unroll
+    for( int r = 0; r < R; r++ ) {
+        Hp[r] = A::bcast( 0 );
+        E[r] = A::bcast( 0 );
+    }
+    T S = A::bcast( NW ? -32768 : 0 );  // SW: running maximum of this lane's rows; NW: range guard
+    T diag = A::bcast( 0 );             // H of (row0-1, previous column)
+    T top_h = top_h_init, top_f = top_f_init;
+    T h_out = A::bcast( 0 ), f_out = A::bcast( 0 ), s_out = A::bcast( 0 );
+    T cap_b = A::bcast( 0 );            // NW PACKED: score of sequence B, kept until the pair ends
+    int jcol = 0;                       // TRACK: column index within the sequence
+    int f8 = 0x7fffffff, f16 = 0x7fffffff, f8_out = 0x7fffffff, f16_out = 0x7fffffff;
     int guard_max = -0x7fffffff;
+
+    // current work batch of this group
+    const uint16_t * st = a.stream;
+    const uint32_t * bnd_h_in = nullptr, * bnd_f_in = nullptr;
+    uint32_t * bnd_h_out = nullptr, * bnd_f_out = nullptr;
+    int ncols = 0, nsteps = 0, t = 0, out_idx = 0;
+    uint32_t half = 0;
+    bool done = false;
+    uint32_t ci_n1 = 0, ci_n2 = 0;                  // column words of the next two steps (software prefetch)
+    uint32_t bh_n1 = 0, bf_n1 = 0, bh_n2 = 0, bf_n2 = 0, wh = 0, wf = 0;
+
     while( true ) {
-        uint32_t b = 0;
-        if( lane == 0 ) b = atomicAdd( a.counter, 1u );
-        b = __shfl_sync( FULL, b, 0 );
-        if( b >= a.nbatches ) break;
-        const Batch bt = a.batches[b];
-        const uint16_t * st = a.stream + bt.col0;
-        const int ncols = (int) bt.ncols;
-        const int nsteps = ncols + 31;
-
-        T Hp[R], E[R];
-#pragma unroll
-        for( int r = 0; r < R; r++ ) {
-            Hp[r] = A::bcast( 0 );
-            E[r] = A::bcast( 0 );
-        }
-        T S = A::bcast( NW ? -32768 : 0 );  // SW: running maximum of this lane's rows; NW: range guard
-        T diag = A::bcast( 0 );        // H of (row0-1, previous column)
-        T top_h = top_h_init, top_f = top_f_init;
-        T h_out = A::bcast( 0 ), f_out = A::bcast( 0 ), s_out = A::bcast( 0 );
-        uint32_t ci_out = 0;
-        T cap_b = A::bcast( 0 );       // NW PACKED: score of sequence B, kept until the pair ends
-        int out_idx = (int) bt.out0;   // advanced by the reporting lane at every pair end
-        int jcol = 0;                  // TRACK: column index within the sequence
-        int f8 = 0x7fffffff, f16 = 0x7fffffff, f8_out = 0x7fffffff, f16_out = 0x7fffffff;
-
-        uint32_t buf = ( lane < ncols ) ? st[lane] : 0, buf_next = 0;
-        uint32_t bh = 0, bf = 0, bh_next = 0, bf_next = 0, wh = 0, wf = 0;
-        if( MULTI && a.bnd_h_in ) {
-            bh = ( lane < ncols ) ? a.bnd_h_in[bt.bnd0 + lane] : 0;
-            bf = ( lane < ncols ) ? a.bnd_f_in[bt.bnd0 + lane] : 0;
-        }
-
-        for( int t = 0; t < nsteps; t++ ) {
-            if( ( t & 31 ) == 0 ) {  // prefetch the next 32 columns one block ahead
-                const int c = t + 32 + lane;
-                buf_next = ( c < ncols ) ? st[c] : 0;
-                if( MULTI && a.bnd_h_in ) {
-                    bh_next = ( c < ncols ) ? a.bnd_h_in[bt.bnd0 + c] : 0;
-                    bf_next = ( c < ncols ) ? a.bnd_f_in[bt.bnd0 + c] : 0;
+        if( t >= nsteps ) {  // group-uniform: this group's batch is finished, pull the next one from the queue
+            uint32_t b = 0xffffffffu;
+            if( is_top && !done ) b = atomicAdd( a.counter, 1u );
+            b = __shfl_sync( group_mask, b, 0, G );
+            if( b >= a.nbatches ) {
+                done = true;
+                ncols = 0;
+                nsteps = 0x7fffffff;
+                ci_n1 = 0;
+                ci_n2 = 0;
+            }
+            else {
+                const Batch bt = a.batches[b];
+                st = a.stream + bt.col0;
+                ncols = (int) bt.ncols;
+                nsteps = ncols + gmask;
+                out_idx = (int) bt.out0;
+                half = bt.half;
+                if( MULTI ) {
+                    bnd_h_in = a.bnd_h_in ? a.bnd_h_in + bt.bnd0 : nullptr;
+                    bnd_f_in = a.bnd_f_in ? a.bnd_f_in + bt.bnd0 : nullptr;
+                    bnd_h_out = a.bnd_h_out ? a.bnd_h_out + bt.bnd0 : nullptr;
+                    bnd_f_out = a.bnd_f_out ? a.bnd_f_out + bt.bnd0 : nullptr;
+                }
+                // lane gl works on column t - gl at step t: preload the columns of steps 0 and 1
+                ci_n1 = ( gl == 0 ) ? ( (uint32_t) st[0] | COL_VALID ) : 0;
+                ci_n2 = ( 1 - gl >= 0 && 1 - gl < ncols ) ? ( (uint32_t) st[1 - gl] | COL_VALID ) : 0;
+                if( MULTI && bnd_h_in && is_top ) {
+                    bh_n1 = bnd_h_in[0];
+                    bf_n1 = bnd_f_in[0];
+                    bh_n2 = ncols > 1 ? bnd_h_in[1] : 0;
+                    bf_n2 = ncols > 1 ? bnd_f_in[1] : 0;
                 }
             }
-            const uint32_t feed = __shfl_sync( FULL, buf, t & 31 );
-            uint32_t feed_h = 0, feed_f = 0;
-            if( MULTI ) {
-                feed_h = __shfl_sync( FULL, bh, t & 31 );
-                feed_f = __shfl_sync( FULL, bf, t & 31 );
-            }
-            if( ( t & 31 ) == 31 ) {
-                buf = buf_next;
-                bh = bh_next;
-                bf = bf_next;
-            }
+            t = 0;
+        }
+        if( __all_sync( FULL, done ) ) break;
 
-            uint32_t ci = __shfl_up_sync( FULL, ci_out, 1 );
-            T h_in = (T) __shfl_up_sync( FULL, h_out, 1 );
-            T f_in = (T) __shfl_up_sync( FULL, f_out, 1 );
-            T s_in = A::bcast( 0 );
-            int f8_in = 0x7fffffff, f16_in = 0x7fffffff;
-            if( !NW ) s_in = (T) __shfl_up_sync( FULL, s_out, 1 );
-            if( TRACK ) {
-                f8_in = __shfl_up_sync( FULL, f8_out, 1 );
-                f16_in = __shfl_up_sync( FULL, f16_out, 1 );
+        // Every lane reads the column word of ITS column (t - gl) straight from the stream, two steps ahead of use:
+        // the G lanes of a group touch G consecutive 16-bit words, all groups run the same instruction stream.
+        const uint32_t ci = ci_n1;
+        ci_n1 = ci_n2;
+        {
+            const int c = t + 2 - gl;
+            ci_n2 = ( c >= 0 && c < ncols ) ? ( (uint32_t) st[c] | COL_VALID ) : 0;
+        }
+        T h_in = (T) __shfl_up_sync( FULL, h_out, 1, G );
+        T f_in = (T) __shfl_up_sync( FULL, f_out, 1, G );
+        T s_in = A::bcast( 0 );
+        int f8_in = 0x7fffffff, f16_in = 0x7fffffff;
+        if( !NW ) s_in = (T) __shfl_up_sync( FULL, s_out, 1, G );
+        if( TRACK ) {
+            f8_in = __shfl_up_sync( FULL, f8_out, 1, G );
+            f16_in = __shfl_up_sync( FULL, f16_out, 1, G );
+        }
+        if( is_top ) {
+            s_in = A::bcast( 0 );
+            f8_in = 0x7fffffff;
+            f16_in = 0x7fffffff;
+            if( gen_top ) {
+                if( ci & COL_FIRST ) {
+                    top_h = top_h_init;
+                    top_f = top_f_init;
+                }
+                h_in = top_h;
+                f_in = top_f;
+                if( NW ) {
+                    top_h = A::add( top_h, RG );
+                    top_f = A::add( top_f, RG );
+                }
             }
-            if( lane == 0 ) {
-                ci = ( t < ncols ) ? ( feed | COL_VALID ) : 0;
-                s_in = A::bcast( 0 );
-                f8_in = 0x7fffffff;
-                f16_in = 0x7fffffff;
-                if( gen_top ) {
-                    if( ci & COL_FIRST ) {
-                        top_h = top_h_init;
-                        top_f = top_f_init;
-                    }
-                    h_in = top_h;
-                    f_in = top_f;
+            else if( MULTI ) {
+                h_in = (T) bh_n1;
+                f_in = (T) bf_n1;
+                bh_n1 = bh_n2;
+                bf_n1 = bf_n2;
+                if( bnd_h_in && t + 2 < ncols ) {
+                    bh_n2 = bnd_h_in[t + 2];
+                    bf_n2 = bnd_f_in[t + 2];
+                }
+            }
+        }
+
+        T h_last = A::bcast( 0 ), f_last = A::bcast( 0 );
+        if( ci & COL_VALID ) {
+            if( ci & COL_FIRST ) {  // a new sequence (pair) starts in this lane
+                T hv = h_init, ev = e_init;
+#pragma unroll
+                for( int r = 0; r < R; r++ ) {
+                    Hp[r] = hv;
+                    E[r] = ev;
                     if( NW ) {
-                        top_h = A::add( top_h, RG );
-                        top_f = A::add( top_f, RG );
+                        hv = A::add( hv, RG );
+                        ev = A::add( ev, RG );
                     }
                 }
-                else if( MULTI ) {
-                    h_in = (T) feed_h;
-                    f_in = (T) feed_f;
-                }
+                diag = diag_init;
+                if( !NW ) S = A::bcast( 0 );
+                jcol = 0;
+                f8 = 0x7fffffff;
+                f16 = 0x7fffffff;
             }
 
-            T h_last = A::bcast( 0 ), f_last = A::bcast( 0 );
-            if( ci & COL_VALID ) {
-                if( ci & COL_FIRST ) {  // a new sequence (pair) starts in this lane
-                    T hv = h_init, ev = e_init;
+            T f = f_in;
+            T hd = diag;
+            diag = h_in;
+            T colmax = A::bcast( 0 );
+            if( PACKED ) {
+                const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
+                const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
 #pragma unroll
-                    for( int r = 0; r < R; r++ ) {
-                        Hp[r] = hv;
-                        E[r] = ev;
-                        if( NW ) {
-                            hv = A::add( hv, RG );
-                            ev = A::add( ev, RG );
+                for( int k = 0; k < R / 2; k++ ) {
+                    const uint32_t la = lds32( pa + k * 4096 );
+                    const uint32_t lb = lds32( pb + k * 4096 );
+                    const T v0 = (T) __byte_perm( lb, la, 0x5410 );
+                    const T v1 = (T) __byte_perm( lb, la, 0x7632 );
+                    T h0, h1, hq;
+                    const T t0 = A::add( hd, v0 );
+                    hd = Hp[2 * k];
+                    h0 = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                    hq = A::add( h0, QR );
+                    E[2 * k] = A::addmax( E[2 * k], RG, hq );
+                    f = A::addmax( f, RG, hq );
+                    Hp[2 * k] = h0;
+                    const T t1 = A::add( hd, v1 );
+                    hd = Hp[2 * k + 1];
+                    h1 = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                    hq = A::add( h1, QR );
+                    E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
+                    f = A::addmax( f, RG, hq );
+                    Hp[2 * k + 1] = h1;
+                    // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over
+                    // H: with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).
+                    // Giving t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it
+                    // stays a VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same
+                    // accumulator as an upper range guard.
+                    S = A::max3( S, t0, t1 );
+                }
+            }
+            else {
+                const uint32_t d = half ? ( ( ci >> 5 ) & 31u ) : ( ci & 31u );
+                const uint32_t pa = prof_base + ( d << 7 );
+#pragma unroll
+                for( int r = 0; r < R; r++ ) {
+                    const T v = (T) lds32( pa + r * 4096 );
+                    const T tt = A::add( hd, v );
+                    hd = Hp[r];
+                    const T h = NW ? A::max3( tt, E[r], f ) : A::max3_relu( tt, E[r], f );
+                    const T hq = A::add( h, QR );
+                    E[r] = A::addmax( E[r], RG, hq );
+                    f = A::addmax( f, RG, hq );
+                    Hp[r] = h;
+                    if( !NW ) colmax = A::max2( colmax, h );
+                }
+                if( !NW ) S = A::max2( S, colmax );
+                if( TRACK ) {
+                    if( (int) colmax >= a.thr8 && f8 == 0x7fffffff ) f8 = jcol;
+                    if( (int) colmax >= a.thr16 && f16 == 0x7fffffff ) f16 = jcol;
+                    jcol++;
+                }
+            }
+            h_last = Hp[R - 1];
+            f_last = f;
+
+            // ---- results at sequence ends (rare, divergent) ----
+            if( NW ) {
+                if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
+                    T sel = Hp[0];
+#pragma unroll
+                    for( int r = 1; r < R; r++ )
+                        if( r == a.cap_row ) sel = Hp[r];
+                    if( PACKED ) {
+                        if( ci & COL_LAST_B ) cap_b = sel;
+                        if( ci & COL_LAST_A ) {
+                            ( (uint32_t *) a.out )[out_idx++] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
                         }
                     }
-                    diag = diag_init;
-                    if( !NW ) S = A::bcast( 0 );
-                    jcol = 0;
-                    f8 = 0x7fffffff;
-                    f16 = 0x7fffffff;
-                }
-
-                T f = f_in;
-                T hd = diag;
-                diag = h_in;
-                T colmax = A::bcast( 0 );
-                if( PACKED ) {
-                    const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
-                    const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
-#pragma unroll
-                    for( int k = 0; k < R / 2; k++ ) {
-                        const uint32_t la = lds32( pa + k * 4096 );
-                        const uint32_t lb = lds32( pb + k * 4096 );
-                        const T v0 = (T) __byte_perm( lb, la, 0x5410 );
-                        const T v1 = (T) __byte_perm( lb, la, 0x7632 );
-                        T h0, h1, hq;
-                        const T t0 = A::add( hd, v0 );
-                        hd = Hp[2 * k];
-                        h0 = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
-                        hq = A::add( h0, QR );
-                        E[2 * k] = A::addmax( E[2 * k], RG, hq );
-                        f = A::addmax( f, RG, hq );
-                        Hp[2 * k] = h0;
-                        const T t1 = A::add( hd, v1 );
-                        hd = Hp[2 * k + 1];
-                        h1 = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
-                        hq = A::add( h1, QR );
-                        E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
-                        f = A::addmax( f, RG, hq );
-                        Hp[2 * k + 1] = h1;
-                        // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over
-                        // H: with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).
-                        // Giving t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it
-                        // stays a VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same
-                        // accumulator as an upper range guard.
-                        S = A::max3( S, t0, t1 );
+                    else {
+                        if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
                     }
                 }
-                else {
-                    const uint32_t d = bt.half ? ( ( ci >> 5 ) & 31u ) : ( ci & 31u );
-                    const uint32_t pa = prof_base + ( d << 7 );
-#pragma unroll
-                    for( int r = 0; r < R; r++ ) {
-                        const T v = (T) lds32( pa + r * 4096 );
-                        const T tt = A::add( hd, v );
-                        hd = Hp[r];
-                        const T h = NW ? A::max3( tt, E[r], f ) : A::max3_relu( tt, E[r], f );
-                        const T hq = A::add( h, QR );
-                        E[r] = A::addmax( E[r], RG, hq );
-                        f = A::addmax( f, RG, hq );
-                        Hp[r] = h;
-                        if( !NW ) colmax = A::max2( colmax, h );
-                    }
-                    if( !NW ) S = A::max2( S, colmax );
+            }
+            else {
+                const uint32_t last_mask = PACKED ? COL_LAST_A : ( half ? COL_LAST_B : COL_LAST_A );
+                s_out = A::bcast( 0 );
+                f8_out = 0x7fffffff;
+                f16_out = 0x7fffffff;
+                if( ci & last_mask ) {
+                    s_out = A::max2( s_in, S );
                     if( TRACK ) {
-                        if( (int) colmax >= a.thr8 && f8 == 0x7fffffff ) f8 = jcol;
-                        if( (int) colmax >= a.thr16 && f16 == 0x7fffffff ) f16 = jcol;
-                        jcol++;
+                        f8_out = min( f8_in, f8 );
+                        f16_out = min( f16_in, f16 );
                     }
-                }
-                h_last = Hp[R - 1];
-                f_last = f;
-
-                // ---- results at sequence ends (rare, divergent) ----
-                if( NW ) {
-                    if( lane == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
-                        T sel = Hp[0];
-#pragma unroll
-                        for( int r = 1; r < R; r++ )
-                            if( r == a.cap_row ) sel = Hp[r];
+                    if( is_bottom ) {
                         if( PACKED ) {
-                            if( ci & COL_LAST_B ) cap_b = sel;
-                            if( ci & COL_LAST_A ) {
-                                ( (uint32_t *) a.out )[out_idx++] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
-                            }
+                            uint32_t * o = (uint32_t *) a.out + out_idx++;
+                            *o = a.first_pass ? (uint32_t) s_out : __vmaxs2( *o, (uint32_t) s_out );
                         }
                         else {
-                            if( ci & ( bt.half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
-                        }
-                    }
-                }
-                else {
-                    const uint32_t last_mask = PACKED ? COL_LAST_A : ( bt.half ? COL_LAST_B : COL_LAST_A );
-                    s_out = A::bcast( 0 );
-                    f8_out = 0x7fffffff;
-                    f16_out = 0x7fffffff;
-                    if( ci & last_mask ) {
-                        s_out = A::max2( s_in, S );
-                        if( TRACK ) {
-                            f8_out = min( f8_in, f8 );
-                            f16_out = min( f16_in, f16 );
-                        }
-                        if( lane == 31 ) {
-                            if( PACKED ) {
-                                uint32_t * o = (uint32_t *) a.out + out_idx++;
-                                *o = a.first_pass ? (uint32_t) s_out : __vmaxs2( *o, (uint32_t) s_out );
+                            int32_t * o = (int32_t *) a.out + out_idx;
+                            *o = a.first_pass ? (int32_t) s_out : max( *o, (int32_t) s_out );
+                            if( TRACK ) {
+                                atomicMin( a.first8 + out_idx, f8_out );
+                                atomicMin( a.first16 + out_idx, f16_out );
                             }
-                            else {
-                                int32_t * o = (int32_t *) a.out + out_idx;
-                                *o = a.first_pass ? (int32_t) s_out : max( *o, (int32_t) s_out );
-                                if( TRACK ) {
-                                    atomicMin( a.first8 + out_idx, f8_out );
-                                    atomicMin( a.first16 + out_idx, f16_out );
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            ci_out = ci;
-            h_out = h_last;
-            f_out = f_last;
-
-            if( MULTI && a.bnd_h_out ) {  // lane 31's last row becomes the next pass' top boundary
-                const int c31 = t - 31;
-                const uint32_t vh = __shfl_sync( FULL, (uint32_t) h_out, 31 );
-                const uint32_t vf = __shfl_sync( FULL, (uint32_t) f_out, 31 );
-                if( c31 >= 0 ) {
-                    if( lane == ( c31 & 31 ) ) {
-                        wh = vh;
-                        wf = vf;
-                    }
-                    if( ( c31 & 31 ) == 31 || c31 == ncols - 1 ) {
-                        const int c = ( c31 & ~31 ) + lane;
-                        if( c <= c31 ) {
-                            a.bnd_h_out[bt.bnd0 + c] = wh;
-                            a.bnd_f_out[bt.bnd0 + c] = wf;
                         }
                     }
                 }
             }
         }
-        if( NW && PACKED ) {
+        h_out = h_last;
+        f_out = f_last;
+
+        if( MULTI ) {  // the bottom lane's last row becomes the next pass' top boundary
+            const int cb = t - gmask;
+            const uint32_t vh = __shfl_sync( FULL, (uint32_t) h_out, gmask, G );
+            const uint32_t vf = __shfl_sync( FULL, (uint32_t) f_out, gmask, G );
+            if( bnd_h_out && cb >= 0 && cb < ncols ) {
+                if( gl == ( cb & gmask ) ) {
+                    wh = vh;
+                    wf = vf;
+                }
+                if( ( cb & gmask ) == gmask || cb == ncols - 1 ) {
+                    const int c = ( cb & ~gmask ) + gl;
+                    if( c <= cb ) {
+                        bnd_h_out[c] = wh;
+                        bnd_f_out[c] = wf;
+                    }
+                }
+            }
+        }
+        if( NW && PACKED && t == nsteps - 1 ) {
             const int hi = (int) (int16_t) ( (uint32_t) S >> 16 ), lo = (int) (int16_t) ( (uint32_t) S & 0xffffu );
             guard_max = max( guard_max, max( hi, lo ) );
         }
+        t++;
     }
     if( NW && PACKED && a.guard ) atomicMax( a.guard, guard_max );
 }

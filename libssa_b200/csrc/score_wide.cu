@@ -15,7 +15,8 @@ template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArg
     cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
     cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
     if( per_sm < 1 ) per_sm = 1;
-    long want = ( (long) args.nbatches + ( SCORE_THREADS / 32 ) - 1 ) / ( SCORE_THREADS / 32 );
+    const long groups_per_cta = ( SCORE_THREADS / 32 ) * ( 32 / args.group );
+    long want = ( (long) args.nbatches + groups_per_cta - 1 ) / groups_per_cta;
     int grid = sms * per_sm;
     if( want < grid ) grid = (int) ( want < 1 ? 1 : want );
     kernel<<<grid, SCORE_THREADS, smem_bytes, stream>>>( args );

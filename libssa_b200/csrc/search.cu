@@ -27,7 +27,6 @@ using namespace ssa;
 
 namespace {
 
-constexpr uint32_t BATCH_COLS = 4096;  // columns per work batch of the packed tier (fill/drain = 31 steps)
 
 template<typename T> struct DevBuf {  // grow-only device buffer
     T * p = nullptr;
@@ -74,15 +73,19 @@ struct PackedDb {
     // this shard, sorted by length (descending, provider index ascending)
     std::vector<uint32_t> sorted_all;  // provider index of GLOBAL sorted position g (all shards); shard r holds g = s*world + r
     std::vector<uint32_t> sorted_id;   // provider index of local sorted position s
+    std::vector<int32_t> sorted_pos_of_id;  // provider index -> GLOBAL sorted position (-1 = skipped record)
     std::vector<uint32_t> sorted_len;
     uint64_t local_residues = 0;
     size_t npairs = 0;
     uint64_t total_cols = 0;
     std::vector<uint64_t> pair_col;    // [npairs+1] first column of pair p in the stream
-    std::vector<Batch> batches;        // packed-tier work batches (whole pairs)
-    std::vector<uint32_t> batch_pair0; // first pair of each batch
+    struct BatchTable {                // packed-tier work batches (whole pairs) of at least `cols` columns
+        std::vector<Batch> batches;
+        std::vector<uint32_t> pair0;   // first pair of each batch
+        DevBuf<Batch> d_batches;
+    };
+    std::map<uint32_t, BatchTable> batch_tables;  // keyed by columns per batch
     DevBuf<uint16_t> d_stream;
-    DevBuf<Batch> d_batches;
     double pack_ms = 0, upload_ms = 0;
     // arrival order caches, keyed by (bit_width, chunk): provider indices in heap-arrival order
     struct Arrival {
@@ -99,16 +102,19 @@ struct Ctx {
     int rank = 0, world = 1;
     ssa_b200_allgather_fn allgather = nullptr;
     void * allgather_ctx = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+    cudaStream_t stream = nullptr, stream_aux = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     PackedDb db;
-    DevBuf<uint32_t> d_profile, d_out_packed, d_counter, d_bnd;
-    DevBuf<int32_t> d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
+    DevBuf<uint32_t> d_profile, d_profile_long, d_out_packed, d_counter, d_bnd;
+    DevBuf<Batch> d_long_batches;
+    PinBuf<Batch> h_long_batches;
+    PinBuf<uint32_t> h_profile_long;
+    DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
     std::vector<uint32_t> order_tmp;
     DevBuf<Batch> d_wide_batches;
     DevBuf<uint32_t> d_flag_list;
     PinBuf<uint32_t> h_profile, h_list;
-    PinBuf<int32_t> h_scores, h_first;
+    PinBuf<int32_t> h_scores, h_first, h_pos;
     PinBuf<Batch> h_wide_batches;
     ssa_b200_stats_t stats;
 };
@@ -131,6 +137,9 @@ void ensure_ctx() {
     CUDA_OK( cudaSetDevice( dev ) );
     ctx.device = dev;
     CUDA_OK( cudaStreamCreateWithFlags( &ctx.stream, cudaStreamNonBlocking ) );
+    CUDA_OK( cudaStreamCreateWithFlags( &ctx.stream_aux, cudaStreamNonBlocking ) );
+    CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_fork, cudaEventDisableTiming ) );
+    CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_join, cudaEventDisableTiming ) );
     CUDA_OK( cudaEventCreate( &ctx.ev_begin ) );
     CUDA_OK( cudaEventCreate( &ctx.ev_k0 ) );
     CUDA_OK( cudaEventCreate( &ctx.ev_k1 ) );
@@ -184,6 +193,8 @@ void build_db() {
 
     // shard: deal the length-sorted records round-robin
     db.sorted_all = sorted;
+    db.sorted_pos_of_id.assign( nall, -1 );
+    for( size_t g = 0; g < sorted.size(); g++ ) db.sorted_pos_of_id[sorted[g]] = (int32_t) g;
     db.sorted_id.clear();
     db.sorted_len.clear();
     db.local_residues = 0;
@@ -239,33 +250,14 @@ void build_db() {
     if( unknown > 0 ) print_warning( "%ld unknown symbols found and set to zero", (long) unknown );
     for( size_t i = db.total_cols; i < db.total_cols + 64; i++ ) h_stream.p[i] = 0;
 
-    // work batches of the packed tier: whole pairs, >= BATCH_COLS columns each
-    db.batches.clear();
-    db.batch_pair0.clear();
-    for( size_t p = 0; p < db.npairs; ) {
-        Batch b;
-        memset( &b, 0, sizeof( b ) );
-        b.col0 = db.pair_col[p];
-        b.bnd0 = db.pair_col[p];
-        b.out0 = (uint32_t) p;
-        size_t q = p;
-        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < BATCH_COLS ) q++;
-        if( db.pair_col[q] - db.pair_col[p] > 0x7fffffffull ) fatal( "libssa_b200: batch too long." );
-        b.ncols = (uint32_t) ( db.pair_col[q] - db.pair_col[p] );
-        db.batches.push_back( b );
-        db.batch_pair0.push_back( (uint32_t) p );
-        p = q;
-    }
+    for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
+    db.batch_tables.clear();
     db.pack_ms = wall_ms() - t0;
 
     const double t1 = wall_ms();
     db.d_stream.reserve( db.total_cols + 64 );
     CUDA_OK( cudaMemcpyAsync( db.d_stream.p, h_stream.p, ( db.total_cols + 64 ) * sizeof( uint16_t ), cudaMemcpyHostToDevice,
             ctx.stream ) );
-    db.d_batches.reserve( db.batches.size() + 1 );
-    if( !db.batches.empty() )
-        CUDA_OK( cudaMemcpyAsync( db.d_batches.p, db.batches.data(), db.batches.size() * sizeof( Batch ), cudaMemcpyHostToDevice,
-                ctx.stream ) );
     CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     h_stream.release();
     db.upload_ms = wall_ms() - t1;
@@ -281,7 +273,7 @@ void build_db() {
     ctx.stats.local_residues = db.local_residues;
     ctx.stats.pack_ms = db.pack_ms;
     ctx.stats.upload_ms = db.upload_ms;
-    ctx.stats.db_device_bytes = ( db.total_cols + 64 ) * sizeof( uint16_t ) + db.batches.size() * sizeof( Batch );
+    ctx.stats.db_device_bytes = ( db.total_cols + 64 ) * sizeof( uint16_t );
     print_info( "GPU database: %ld sequences, %ld residues, %ld columns in %ld pairs, packed in %.1f ms, uploaded in %.1f ms\n",
             (long) nloc, (long) db.local_residues, (long) db.total_cols, (long) db.npairs, db.pack_ms, db.upload_ms );
 }
@@ -305,6 +297,34 @@ void parallel_for( size_t n, size_t grain, const std::function<void( size_t, siz
             }
         } );
     for( auto & th : pool ) th.join();
+}
+
+// Work batches of the packed tier: runs of whole pairs with at least `cols` columns, built on demand and cached.
+// Small batches balance the persistent grid's work queue, large ones amortise the G-1 fill/drain steps.
+PackedDb::BatchTable & batch_table( uint32_t cols ) {
+    PackedDb & db = ctx.db;
+    auto it = db.batch_tables.find( cols );
+    if( it != db.batch_tables.end() ) return it->second;
+    PackedDb::BatchTable & bt = db.batch_tables[cols];
+    for( size_t p = 0; p < db.npairs; ) {
+        Batch b;
+        memset( &b, 0, sizeof( b ) );
+        b.col0 = db.pair_col[p];
+        b.bnd0 = db.pair_col[p];
+        b.out0 = (uint32_t) p;
+        size_t q = p;
+        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < cols ) q++;
+        if( db.pair_col[q] - db.pair_col[p] > 0x7fffffffull ) fatal( "libssa_b200: batch too long." );
+        b.ncols = (uint32_t) ( db.pair_col[q] - db.pair_col[p] );
+        bt.batches.push_back( b );
+        bt.pair0.push_back( (uint32_t) p );
+        p = q;
+    }
+    bt.d_batches.reserve( bt.batches.size() + 1 );
+    if( !bt.batches.empty() )
+        CUDA_OK( cudaMemcpyAsync( bt.d_batches.p, bt.batches.data(), bt.batches.size() * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    return bt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -348,6 +368,15 @@ __global__ void flag_overflow_kernel( const int32_t * gathered, uint32_t stride,
     }
 }
 
+// first-crossing columns of the flagged records only: out[k] = first8[idx], out[count + k] = first16[idx]
+__global__ void gather_first_kernel( const uint32_t * list, uint32_t count, const int32_t * first_all, uint32_t stride, int32_t * out ) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if( k >= count ) return;
+    const uint32_t i = list[k], r = i / stride, sl = i % stride;
+    out[k] = first_all[(size_t) r * 2 * stride + sl];
+    out[count + k] = first_all[(size_t) r * 2 * stride + stride + sl];
+}
+
 __global__ void fill_i32_kernel( int32_t * p, int32_t v, uint32_t n ) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if( i < n ) p[i] = v;
@@ -358,49 +387,65 @@ __global__ void fill_i32_kernel( int32_t * p, int32_t v, uint32_t n ) {
 // ------------------------------------------------------------------------------------------------
 
 struct Plan {
-    int npass = 1;
-    int R = 4;          // rows per lane of the packed tier
-    int wide_R = 8;
-    int wide_npass = 1;
-    int qpad = 0, wide_qpad = 0;
+    int G = 32, R = 4, npass = 1, qpad = 0;                      // packed tier: lanes per group, rows per lane, passes
+    int wide_G = 32, wide_R = 8, wide_npass = 1, wide_qpad = 0;   // wide tier
     int pad_score = 0;
-    int64_t lo = 0, hi = 0;  // matrix extremes over the symbols that can occur
+    int64_t lo = 0, hi = 0;  // matrix extremes
 };
 
-int pick_R( const int * options, int n, int rows_per_lane ) {
-    for( int i = 0; i < n; i++ )
-        if( options[i] >= rows_per_lane ) return options[i];
-    return options[n - 1];
+// Picks the systolic-array shape for a query: G lanes x R rows per pass.  Model of the instruction count per
+// packed word-row: ~7.5 instructions of DP + lookup, plus ~60 instructions of per-step work (shuffles, flags,
+// feed) shared by the R rows of a lane; rows beyond the query are wasted work, every pass re-streams the database.
+void pick_shape( size_t qlen, const int * r_options, int n_options, int * G_out, int * R_out, int * npass_out ) {
+    double best = 1e300;
+    for( int G = 4; G <= 32; G *= 2 )
+        for( int i = 0; i < n_options; i++ ) {
+            const int R = r_options[i];
+            const size_t rows = (size_t) G * R;
+            const size_t npass = ( qlen + rows - 1 ) / rows;
+            if( npass > 1 && G != 32 ) continue;  // several passes only with full-warp arrays
+            const double cost = (double) npass * rows * ( 7.5 + 60.0 / R ) + ( npass > 1 ? 0.03 * npass * rows * 7.5 : 0.0 );
+            if( cost < best ) {
+                best = cost;
+                *G_out = G;
+                *R_out = R;
+                *npass_out = (int) npass;
+            }
+        }
 }
 
 Plan make_plan( size_t qlen ) {
     Plan pl;
-    const int maxR = PACKED_R[sizeof( PACKED_R ) / sizeof( int ) - 1];
-    pl.npass = (int) ( ( qlen + 32 * maxR - 1 ) / ( 32 * maxR ) );
-    if( pl.npass < 1 ) pl.npass = 1;
-    int rows_per_pass = (int) ( ( qlen + pl.npass - 1 ) / pl.npass );
-    pl.R = pick_R( PACKED_R, sizeof( PACKED_R ) / sizeof( int ), ( rows_per_pass + 31 ) / 32 );
-    pl.qpad = pl.npass * 32 * pl.R;
-    const int wmaxR = WIDE_R[sizeof( WIDE_R ) / sizeof( int ) - 1];
-    pl.wide_npass = (int) ( ( qlen + 32 * wmaxR - 1 ) / ( 32 * wmaxR ) );
-    if( pl.wide_npass < 1 ) pl.wide_npass = 1;
-    rows_per_pass = (int) ( ( qlen + pl.wide_npass - 1 ) / pl.wide_npass );
-    pl.wide_R = pick_R( WIDE_R, sizeof( WIDE_R ) / sizeof( int ), ( rows_per_pass + 31 ) / 32 );
-    pl.wide_qpad = pl.wide_npass * 32 * pl.wide_R;
+    pick_shape( qlen, PACKED_R, sizeof( PACKED_R ) / sizeof( int ), &pl.G, &pl.R, &pl.npass );
+    if( const char * ov = getenv( "LIBSSA_B200_SHAPE" ) ) {  // development aid: "G,R" overrides the packed-tier shape
+        int g = 0, r = 0;
+        if( sscanf( ov, "%d,%d", &g, &r ) == 2 && ( g == 4 || g == 8 || g == 16 || g == 32 ) ) {
+            for( int opt : PACKED_R )
+                if( opt == r ) {
+                    pl.G = g;
+                    pl.R = r;
+                    pl.npass = (int) ( ( qlen + (size_t) g * r - 1 ) / ( (size_t) g * r ) );
+                }
+        }
+    }
+    pl.qpad = pl.npass * pl.G * pl.R;
+    pick_shape( qlen, WIDE_R, sizeof( WIDE_R ) / sizeof( int ), &pl.wide_G, &pl.wide_R, &pl.wide_npass );
+    pl.wide_qpad = pl.wide_npass * pl.wide_G * pl.wide_R;
     pl.lo = g_matrix.lo;
     pl.hi = g_matrix.hi;
     pl.pad_score = (int) std::min<int64_t>( pl.lo, 0 );
     return pl;
 }
 
-// Packed profile of pass `pass`: word [(k*32 + d)*32 + lane] = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as int16,
-// rows counted from rowbase + lane*R; rows beyond the query get pad_score for every residue.
+// Packed profile of pass `pass`: word [(k*32 + d)*32 + lane] = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as int16, the
+// rows counted from (pass*G + (lane mod G)) * R.  All 32 lanes have their own copy (groups repeat), so a warp-wide
+// lookup is bank-conflict free whatever residues the lanes hold.  Rows beyond the query get pad_score.
 void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
-    const int R = pl.R;
+    const int R = pl.R, G = pl.G;
     for( int k = 0; k < R / 2; k++ )
         for( int d = 0; d < 32; d++ )
             for( int lane = 0; lane < 32; lane++ ) {
-                size_t r0 = (size_t) pass * 32 * R + (size_t) lane * R + 2 * k;
+                size_t r0 = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R + 2 * k;
                 int v0 = r0 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0]] : pl.pad_score;
                 int v1 = r0 + 1 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0 + 1]] : pl.pad_score;
                 out[( k * 32 + d ) * 32 + lane] = ( (uint32_t) (uint16_t) (int16_t) v1 << 16 ) | (uint32_t) (uint16_t) (int16_t) v0;
@@ -408,11 +453,11 @@ void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const 
 }
 
 void fill_profile_wide( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
-    const int R = pl.wide_R;
+    const int R = pl.wide_R, G = pl.wide_G;
     for( int r = 0; r < R; r++ )
         for( int d = 0; d < 32; d++ )
             for( int lane = 0; lane < 32; lane++ ) {
-                size_t row = (size_t) pass * 32 * R + (size_t) lane * R + r;
+                size_t row = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R + r;
                 int v = row < qlen ? (int) g_matrix.m[( d << 5 ) + q[row]] : pl.pad_score;
                 out[( r * 32 + d ) * 32 + lane] = (uint32_t) v;
             }
@@ -497,7 +542,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     ctx.d_wide_batches.reserve( n );
     CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches.p, ctx.h_wide_batches.p, n * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
     ctx.stats.h2d_bytes += n * sizeof( Batch );
-    const int npass = pl.wide_npass, R = pl.wide_R;
+    const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
     ctx.h_profile.reserve( words * npass );
     for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile.p + p * words, q, qlen, pl, p );
@@ -515,14 +560,17 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         a.nbatches = (uint32_t) n;
         a.counter = ctx.d_counter.p;
         a.profile = ctx.d_profile.p + p * words;
+        a.group = (uint32_t) G;
+        a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
+        a.rg_word = (uint32_t) (int) g_gapE;
         a.gap_open_extend = (int) g_gapO + (int) g_gapE;
         a.gap_extend = g_gapE;
         a.gap_open = g_gapO;
         a.offset = 0;
-        a.rowbase = p * 32 * R;
+        a.rowbase = p * G * R;
         a.cap_lane = -1;
         a.cap_row = 0;
-        if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + 32 * R ) {
+        if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + (size_t) G * R ) {
             a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
             a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
         }
@@ -546,6 +594,70 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     ctx.stats.wide_tier_seqs += n;
 }
 
+// One launch (all passes) of the packed tier over `nbatches` batches with shape G x R.
+void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, int G, int R, int npass,
+        const Batch * d_batches, uint32_t nbatches, uint32_t * d_counter, uint32_t * d_profile, uint32_t * h_profile, int32_t offset ) {
+    PackedDb & db = ctx.db;
+    const size_t words = (size_t) ( R / 2 ) * 1024;
+    Plan shape = pl;
+    shape.G = G;
+    shape.R = R;
+    for( int p = 0; p < npass; p++ ) fill_profile_packed( h_profile + p * words, q, qlen, shape, p );
+    CUDA_OK( cudaMemcpyAsync( d_profile, h_profile, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
+    ctx.stats.h2d_bytes += words * npass * 4;
+    for( int p = 0; p < npass; p++ ) {
+        CUDA_OK( cudaMemsetAsync( d_counter, 0, 4, stream ) );
+        ScoreArgs a;
+        memset( &a, 0, sizeof( a ) );
+        a.stream = db.d_stream.p;
+        a.batches = d_batches;
+        a.nbatches = nbatches;
+        a.counter = d_counter;
+        a.profile = d_profile + p * words;
+        a.group = (uint32_t) G;
+        a.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
+        a.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
+        a.gap_open_extend = (int) g_gapO + (int) g_gapE;
+        a.gap_extend = g_gapE;
+        a.gap_open = g_gapO;
+        a.offset = offset;
+        a.rowbase = p * G * R;
+        a.cap_lane = -1;
+        if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + (size_t) G * R ) {
+            a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
+            a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
+        }
+        a.first_pass = ( p == 0 );
+        a.out = ctx.d_out_packed.p;
+        a.guard = nullptr;
+        if( npass > 1 ) {
+            uint32_t * base = ctx.d_bnd.p;
+            const uint64_t n = db.total_cols;
+            uint32_t * h0 = base, * f0 = base + n, * h1 = base + 2 * n, * f1 = base + 3 * n;
+            a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
+            a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
+            a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
+            a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
+        }
+        launch_score_packed( R, nw, npass > 1, a, stream );
+        ctx.stats.launches++;
+    }
+}
+
+// first pair (pairs are sorted by descending length of their longer sequence) whose length is <= len
+size_t first_pair_not_longer( int64_t len ) {
+    PackedDb & db = ctx.db;
+    size_t lo = 0, hi = db.npairs;
+    while( lo < hi ) {
+        size_t mid = ( lo + hi ) / 2;
+        if( (int64_t) db.sorted_len[2 * mid] > len )
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     PackedDb & db = ctx.db;
     const size_t nloc = db.sorted_id.size();
@@ -555,84 +667,113 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     if( qlen > ( 1u << 24 ) || ( qlen + db.sorted_len[0] ) > ( 1ull << 24 ) )
         fatal( "libssa_b200: query/database sequences beyond 2^24 symbols are not supported by the 32-bit tier." );
     Plan pl = make_plan( qlen );
+    int sms = 148;
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx.device );
 
-    // tier split: pairs whose longer sequence exceeds the packed tier's guaranteed range go to the wide tier
+    // ---- tier split: pairs whose longer sequence exceeds the packed tier's guaranteed range go to the wide tier ----
     int32_t offset = 0;
-    int64_t safe = packed_safe_len( pl, nw, pl.qpad, &offset );
+    const int qrows_max = std::max( pl.qpad, 32 * 32 * ( ( (int) qlen + 1023 ) / 1024 ) );
+    int64_t safe = packed_safe_len( pl, nw, qrows_max, &offset );
     if( (int) g_gapO + (int) g_gapE > 0 || g_gapE > 0 ) safe = 0;  // positive "penalties": only the wide tier is valid
-    size_t p0 = 0;  // first pair that is safe (pairs are sorted by descending length of A)
-    {
-        size_t lo = 0, hi = db.npairs;
-        while( lo < hi ) {
-            size_t mid = ( lo + hi ) / 2;
-            if( (int64_t) db.sorted_len[2 * mid] > safe )
-                lo = mid + 1;
-            else
-                hi = mid;
+    const size_t p_safe = first_pair_not_longer( safe );
+
+    // ---- shape of the packed tier ----
+    // The bulk of the database runs on groups of G lanes x R rows (few padded rows, per-step work amortised over many
+    // rows).  A pair is processed by ONE group from its first to its last column, so with narrow groups the longest
+    // pairs would outlast everything else; pairs longer than `long_len` columns therefore run on full-warp arrays
+    // (32 x long_R) in a second launch that overlaps the first on another stream.  Cost model in instructions:
+    // a warp-step costs 7.5 R + 60 and advances 32/G groups by one column.
+    int G = pl.G, R = pl.R, npass = pl.npass, long_R = 0;
+    size_t p_long_end = p_safe;
+    if( npass == 1 && qlen <= 1024 && !getenv( "LIBSSA_B200_SHAPE" ) ) {
+        const int * opts = PACKED_R;
+        const int nopt = sizeof( PACKED_R ) / sizeof( int );
+        int r32 = opts[nopt - 1];
+        for( int i = nopt - 1; i >= 0; i-- )
+            if( (size_t) 32 * opts[i] >= qlen ) r32 = opts[i];
+        double best = 1e300;
+        for( int g = 4; g <= 32; g *= 2 ) {
+            int r = 0;
+            for( int i = nopt - 1; i >= 0; i-- )
+                if( (size_t) g * opts[i] >= qlen ) r = opts[i];
+            if( r == 0 ) continue;
+            // pairs longer than this many columns would dominate the tail of a launch with groups of g lanes
+            const int64_t long_len = g == 32 ? INT64_MAX : std::max<int64_t>( 64, (int64_t) ( (double) db.total_cols * g / ( 1165.0 * sms ) ) );
+            const size_t pl_end = std::max( p_safe, first_pair_not_longer( long_len ) );
+            const double cols_long = (double) ( db.pair_col[pl_end] - db.pair_col[p_safe] );
+            const double cols_bulk = (double) ( db.total_cols - db.pair_col[pl_end] );
+            const double cost = cols_bulk * ( g / 32.0 ) * ( 7.5 * r + 60 ) + cols_long * ( 7.5 * r32 + 60 );
+            if( cost < best ) {
+                best = cost;
+                G = g;
+                R = r;
+                p_long_end = pl_end;
+                long_R = g == 32 ? 0 : r32;
+            }
         }
-        p0 = lo;
     }
-    size_t b0 = std::lower_bound( db.batch_pair0.begin(), db.batch_pair0.end(), (uint32_t) p0 ) - db.batch_pair0.begin();
-    size_t pair_start = b0 < db.batches.size() ? db.batch_pair0[b0] : db.npairs;
-    if( nw && pair_start < db.npairs ) offset = nw_offset_for( pl, pl.qpad, db.sorted_len[2 * pair_start] );
+
+    // batch size of the bulk class: ~6 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
+    const uint64_t groups = (uint64_t) sms * packed_blocks_per_sm( R, nw, npass > 1 ) * ( SCORE_THREADS / 32 ) * ( 32 / G );
+    uint32_t batch_cols = 4096;
+    while( batch_cols > 256 && db.total_cols / batch_cols < 6 * groups ) batch_cols /= 2;
+    PackedDb::BatchTable & bt = batch_table( batch_cols );
+    const size_t b0 = std::lower_bound( bt.pair0.begin(), bt.pair0.end(), (uint32_t) p_long_end ) - bt.pair0.begin();
+    const size_t bulk_pair0 = b0 < bt.batches.size() ? bt.pair0[b0] : db.npairs;   // bulk class = pairs [bulk_pair0, npairs)
+    size_t long_pair0 = p_safe;                                                  // long class = pairs [long_pair0, bulk_pair0)
+    if( long_R == 0 ) long_pair0 = bulk_pair0;                                  // no long class: those pairs go to the wide tier
+    const size_t wide_pairs = long_pair0;                                        // wide tier = pairs [0, long_pair0)
+    if( nw && wide_pairs < db.npairs ) offset = nw_offset_for( pl, qrows_max, db.sorted_len[2 * wide_pairs] );
 
     CUDA_OK( cudaEventRecord( ctx.ev_k0, ctx.stream ) );
-    // ---- packed tier ----
-    if( b0 < db.batches.size() ) {
-        const int npass = pl.npass, R = pl.R;
+    ctx.d_out_packed.reserve( db.npairs + 1 );
+    ctx.d_counter.reserve( 64 );
+    // ---- long class on the auxiliary stream ----
+    const size_t n_long = bulk_pair0 - long_pair0;
+    if( n_long > 0 ) {
+        ctx.h_long_batches.reserve( n_long );
+        for( size_t i = 0; i < n_long; i++ ) {
+            Batch b;
+            memset( &b, 0, sizeof( b ) );
+            const size_t p = long_pair0 + i;
+            b.col0 = db.pair_col[p];
+            b.bnd0 = db.pair_col[p];
+            b.ncols = db.sorted_len[2 * p];
+            b.out0 = (uint32_t) p;
+            ctx.h_long_batches.p[i] = b;
+        }
+        ctx.d_long_batches.reserve( n_long );
+        const size_t words = (size_t) ( long_R / 2 ) * 1024;
+        ctx.h_profile_long.reserve( words );
+        ctx.d_profile_long.reserve( words );
+        CUDA_OK( cudaEventRecord( ctx.ev_fork, ctx.stream ) );
+        CUDA_OK( cudaStreamWaitEvent( ctx.stream_aux, ctx.ev_fork, 0 ) );
+        CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches.p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
+        ctx.stats.h2d_bytes += n_long * sizeof( Batch );
+        launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, 32, long_R, 1, ctx.d_long_batches.p, (uint32_t) n_long, ctx.d_counter.p + 8,
+                ctx.d_profile_long.p, ctx.h_profile_long.p, offset );
+        CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
+    }
+    // ---- bulk class ----
+    if( b0 < bt.batches.size() ) {
         const size_t words = (size_t) ( R / 2 ) * 1024;
         ctx.h_profile.reserve( words * npass );
-        for( int p = 0; p < npass; p++ ) fill_profile_packed( ctx.h_profile.p + p * words, q, qlen, pl, p );
         ctx.d_profile.reserve( words * npass );
-        CUDA_OK( cudaMemcpyAsync( ctx.d_profile.p, ctx.h_profile.p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
-        ctx.stats.h2d_bytes += words * npass * 4;
-        ctx.d_out_packed.reserve( db.npairs + 1 );
-        ctx.d_counter.reserve( 64 );
-        ctx.d_guard.reserve( 4 );
         if( npass > 1 ) ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
-        for( int p = 0; p < npass; p++ ) {
-            CUDA_OK( cudaMemsetAsync( ctx.d_counter.p, 0, 4, ctx.stream ) );
-            ScoreArgs a;
-            memset( &a, 0, sizeof( a ) );
-            a.stream = db.d_stream.p;
-            a.batches = db.d_batches.p + b0;
-            a.nbatches = (uint32_t) ( db.batches.size() - b0 );
-            a.counter = ctx.d_counter.p;
-            a.profile = ctx.d_profile.p + p * words;
-            a.gap_open_extend = (int) g_gapO + (int) g_gapE;
-            a.gap_extend = g_gapE;
-            a.gap_open = g_gapO;
-            a.offset = offset;
-            a.rowbase = p * 32 * R;
-            a.cap_lane = -1;
-            if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + 32 * R ) {
-                a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
-                a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
-            }
-            a.first_pass = ( p == 0 );
-            a.out = ctx.d_out_packed.p;
-            a.guard = nullptr;
-            if( npass > 1 ) {
-                uint32_t * base = ctx.d_bnd.p;
-                const uint64_t n = db.total_cols;
-                uint32_t * h0 = base, * f0 = base + n, * h1 = base + 2 * n, * f1 = base + 3 * n;
-                a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
-                a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
-                a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
-                a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
-            }
-            launch_score_packed( R, nw, npass > 1, a, ctx.stream );
-            ctx.stats.launches++;
-        }
-        const uint32_t np = (uint32_t) ( db.npairs - pair_start );
-        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_out_packed.p, ctx.d_scores.p, (uint32_t) pair_start,
+        launch_packed_class( ctx.stream, q, qlen, nw, pl, G, R, npass, bt.d_batches.p + b0, (uint32_t) ( bt.batches.size() - b0 ), ctx.d_counter.p,
+                ctx.d_profile.p, ctx.h_profile.p, offset );
+    }
+    if( n_long > 0 ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
+    if( wide_pairs < db.npairs ) {
+        const uint32_t np = (uint32_t) ( db.npairs - wide_pairs );
+        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_out_packed.p, ctx.d_scores.p, (uint32_t) wide_pairs,
                 (uint32_t) db.npairs, (uint32_t) nloc, offset );
         ctx.stats.launches++;
     }
-    // ---- wide tier for the unsafe prefix ----
-    if( pair_start > 0 ) {
+    // ---- wide tier for the pairs beyond the packed tier's range ----
+    if( wide_pairs > 0 ) {
         std::vector<uint32_t> slots;
-        for( size_t s = 0; s < std::min( nloc, 2 * pair_start ); s++ ) slots.push_back( (uint32_t) s );
+        for( size_t s = 0; s < std::min( nloc, 2 * wide_pairs ); s++ ) slots.push_back( (uint32_t) s );
         run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr );
     }
     CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
@@ -651,12 +792,12 @@ PackedDb::Arrival & arrival_for( int bit_width, size_t chunk ) {
 void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_pos ) {
     PackedDb & db = ctx.db;
     const size_t nglob = db.sorted_all.size();
-    std::vector<int32_t> pos_of_id( db.lens_all.size(), -1 );
-    for( size_t a = 0; a < order.size(); a++ ) pos_of_id[order[a]] = (int32_t) a;
-    std::vector<int32_t> pos( nglob );
-    for( size_t g = 0; g < nglob; g++ ) pos[g] = pos_of_id[db.sorted_all[g]];
+    ctx.h_pos.reserve( nglob + 1 );
+    int32_t * pos = ctx.h_pos.p;
+    if( order.size() != nglob ) std::fill( pos, pos + nglob, -1 );  // records the reference never reaches
+    for( size_t a = 0; a < order.size(); a++ ) pos[db.sorted_pos_of_id[order[a]]] = (int32_t) a;
     d_pos.reserve( nglob + 1 );
-    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos.data(), nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
+    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos, nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
     CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     ctx.stats.h2d_bytes += nglob * sizeof( int32_t );
 }
@@ -686,7 +827,8 @@ void gpu_release() {
     if( !ctx.init ) return;
     cudaStreamSynchronize( ctx.stream );
     ctx.db.d_stream.release();
-    ctx.db.d_batches.release();
+    for( auto & kv : ctx.db.batch_tables ) kv.second.d_batches.release();
+    ctx.db.batch_tables.clear();
     for( auto & kv : ctx.db.arrival ) kv.second.d_pos_of_sorted.release();
     ctx.db.arrival.clear();
     ctx.db.valid = false;
@@ -697,6 +839,7 @@ void gpu_release() {
     ctx.d_scores.release();
     ctx.d_arrival_scores.release();
     ctx.d_first.release();
+    ctx.d_first_compact.release();
     ctx.d_gathered.release();
     ctx.d_pos_tmp.release();
     ctx.d_guard.release();
@@ -706,13 +849,21 @@ void gpu_release() {
     ctx.h_list.release();
     ctx.h_scores.release();
     ctx.h_first.release();
+    ctx.h_pos.release();
     ctx.h_wide_batches.release();
     traceback_release();
     cudaEventDestroy( ctx.ev_begin );
     cudaEventDestroy( ctx.ev_k0 );
     cudaEventDestroy( ctx.ev_k1 );
     cudaEventDestroy( ctx.ev_end );
+    cudaEventDestroy( ctx.ev_fork );
+    cudaEventDestroy( ctx.ev_join );
+    cudaStreamDestroy( ctx.stream_aux );
     cudaStreamDestroy( ctx.stream );
+    ctx.d_profile_long.release();
+    ctx.d_long_batches.release();
+    ctx.h_long_batches.release();
+    ctx.h_profile_long.release();
     ctx.init = false;
 }
 
@@ -818,16 +969,21 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
                 d_f_all = ctx.d_first.p + 2 * stride;
                 gather_i32( d_f, d_f_all, 2 * stride );
             }
-            ctx.h_first.reserve( 2 * stride * world + 2 );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_f_all, 2 * stride * world * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            ctx.d_first_compact.reserve( 2 * (size_t) count + 2 );
+            gather_first_kernel<<<( count + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_flag_list.p, count, d_f_all, (uint32_t) stride,
+                    ctx.d_first_compact.p );
+            ctx.stats.launches++;
+            ctx.h_first.reserve( 2 * (size_t) count + 2 );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, ctx.d_first_compact.p, 2 * (size_t) count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
             CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += 2 * stride * world * sizeof( int32_t );
+            ctx.stats.d2h_bytes += 2 * (size_t) count * sizeof( int32_t );
             ovf8.assign( db.lens_all.size(), -1 );
             ovf16.assign( db.lens_all.size(), -1 );
-            for( uint32_t i : flagged ) {
+            for( uint32_t k = 0; k < count; k++ ) {   // ctx.h_list still holds the (unsorted) device list order
+                const uint32_t i = ctx.h_list.p[k];
                 const size_t r = i / stride, sl = i % stride;
                 const uint32_t id = db.sorted_all[sl * world + r];
-                const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
+                const int32_t c8 = ctx.h_first.p[k], c16 = ctx.h_first.p[count + k];
                 if( req.bit_width == 8 && c8 != INT_MAX ) {
                     ovf8[id] = c8 / 4;
                     ctx.stats.overflow_8++;
