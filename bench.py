@@ -315,6 +315,10 @@ def run_ours(steps, warmup, n_gpus):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: park the real stdout and send any library chatter
+    # (e.g. NCCL's version banner) to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -326,7 +330,8 @@ def main():
     else:
         line = run_ours(args.steps, max(args.warmup, 0), args.gpus)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
