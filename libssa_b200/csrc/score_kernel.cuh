@@ -106,8 +106,11 @@ __device__ __forceinline__ uint32_t lds32( uint32_t addr ) {
 // words of shared memory the profile of one pass needs
 template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() { return PACKED ? ( R / 2 ) * 1024 : R * 1024; }
 
+// resident CTAs per SM the register allocator has to make room for (64K registers / 256 threads / blocks)
+template<bool PACKED, int R> __host__ __device__ constexpr int min_blocks() { return PACKED ? ( R <= 12 ? 4 : ( R <= 20 ? 3 : 2 ) ) : 2; }
+
 template<bool PACKED, int R, bool NW, bool MULTI, bool TRACK>
-__global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs a ) {
+__global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) score_kernel( const ScoreArgs a ) {
     typedef Arith<PACKED> A;
     typedef typename A::T T;
     constexpr unsigned FULL = 0xffffffffu;
@@ -131,19 +134,8 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
     const int row0 = a.rowbase + gl * R;
     const bool gen_top = is_top && ( a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
 
-    // per-lane constants of a sequence start (NW: reference needleman_wunsch_64.c:39-42,51-52)
-    T diag_init, h_init, e_init, top_h_init, top_f_init;
-    if( NW ) {
-        diag_init = A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset );
-        h_init = A::bcast( a.gap_open + ( row0 + 1 ) * a.gap_extend - a.offset );
-        e_init = A::bcast( 2 * a.gap_open + ( row0 + 2 ) * a.gap_extend - a.offset );
-        top_h_init = A::bcast( a.gap_open + a.gap_extend - a.offset );
-        top_f_init = A::bcast( 2 * a.gap_open + 2 * a.gap_extend - a.offset );
-    }
-    else {
-        diag_init = h_init = e_init = top_h_init = top_f_init = A::bcast( 0 );
-    }
-
+    // Values of a sequence start (NW: reference needleman_wunsch_64.c:39-42,51-52) are recomputed from row0 where a
+    // sequence starts (rare) instead of being held in registers.
     T Hp[R], E[R];
 #pragma unroll
     for( int r = 0; r < R; r++ ) {
@@ -152,7 +144,7 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
     }
     T S = A::bcast( NW ? -32768 : 0 );  // SW: running maximum of this lane's rows; NW: range guard
     T diag = A::bcast( 0 );             // H of (row0-1, previous column)
-    T top_h = top_h_init, top_f = top_f_init;
+    T top_h = A::bcast( 0 ), top_f = A::bcast( 0 );
     T h_out = A::bcast( 0 ), f_out = A::bcast( 0 ), s_out = A::bcast( 0 );
     T cap_b = A::bcast( 0 );            // NW PACKED: score of sequence B, kept until the pair ends
     int jcol = 0;                       // TRACK: column index within the sequence
@@ -230,9 +222,9 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
             f8_in = 0x7fffffff;
             f16_in = 0x7fffffff;
             if( gen_top ) {
-                if( ci & COL_FIRST ) {
-                    top_h = top_h_init;
-                    top_f = top_f_init;
+                if( NW && ( ci & COL_FIRST ) ) {
+                    top_h = A::bcast( a.gap_open + a.gap_extend - a.offset );
+                    top_f = A::bcast( 2 * a.gap_open + 2 * a.gap_extend - a.offset );
                 }
                 h_in = top_h;
                 f_in = top_f;
@@ -256,7 +248,14 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
         T h_last = A::bcast( 0 ), f_last = A::bcast( 0 );
         if( ci & COL_VALID ) {
             if( ci & COL_FIRST ) {  // a new sequence (pair) starts in this lane
-                T hv = h_init, ev = e_init;
+                T hv = A::bcast( 0 ), ev = A::bcast( 0 );
+                if( NW ) {
+                    hv = A::bcast( a.gap_open + ( row0 + 1 ) * a.gap_extend - a.offset );
+                    ev = A::bcast( 2 * a.gap_open + ( row0 + 2 ) * a.gap_extend - a.offset );
+                    // opaque to the optimiser: otherwise the 2R start values are hoisted out of the step loop as loop
+                    // invariants and occupy 2R registers for the whole kernel
+                    asm volatile( "" : "+r"( hv ), "+r"( ev ) );
+                }
 #pragma unroll
                 for( int r = 0; r < R; r++ ) {
                     Hp[r] = hv;
@@ -266,7 +265,7 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
                         ev = A::add( ev, RG );
                     }
                 }
-                diag = diag_init;
+                diag = NW ? A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset ) : A::bcast( 0 );
                 if( !NW ) S = A::bcast( 0 );
                 jcol = 0;
                 f8 = 0x7fffffff;
@@ -280,27 +279,28 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
             if( PACKED ) {
                 const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
                 const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
+                // The diagonal candidate of row r+1 (old H of row r + its substitution score) is formed BEFORE row r's
+                // H register is overwritten, so every H stays in one physical register across steps (no rotation moves).
+                uint32_t la = lds32( pa ), lb = lds32( pb );
+                T tc = A::add( hd, (T) __byte_perm( lb, la, 0x5410 ) );
 #pragma unroll
                 for( int k = 0; k < R / 2; k++ ) {
-                    const uint32_t la = lds32( pa + k * 4096 );
-                    const uint32_t lb = lds32( pb + k * 4096 );
-                    const T v0 = (T) __byte_perm( lb, la, 0x5410 );
-                    const T v1 = (T) __byte_perm( lb, la, 0x7632 );
-                    T h0, h1, hq;
-                    const T t0 = A::add( hd, v0 );
-                    hd = Hp[2 * k];
-                    h0 = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
-                    hq = A::add( h0, QR );
+                    const T t0 = tc;
+                    const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
+                    if( k + 1 < R / 2 ) {
+                        la = lds32( pa + ( k + 1 ) * 4096 );
+                        lb = lds32( pb + ( k + 1 ) * 4096 );
+                        tc = A::add( Hp[2 * k + 1], (T) __byte_perm( lb, la, 0x5410 ) );
+                    }
+                    T hq;
+                    Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                    hq = A::add( Hp[2 * k], QR );
                     E[2 * k] = A::addmax( E[2 * k], RG, hq );
                     f = A::addmax( f, RG, hq );
-                    Hp[2 * k] = h0;
-                    const T t1 = A::add( hd, v1 );
-                    hd = Hp[2 * k + 1];
-                    h1 = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
-                    hq = A::add( h1, QR );
+                    Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                    hq = A::add( Hp[2 * k + 1], QR );
                     E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
                     f = A::addmax( f, RG, hq );
-                    Hp[2 * k + 1] = h1;
                     // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over
                     // H: with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).
                     // Giving t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it
@@ -337,10 +337,16 @@ __global__ void __launch_bounds__( SCORE_THREADS ) score_kernel( const ScoreArgs
             // ---- results at sequence ends (rare, divergent) ----
             if( NW ) {
                 if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
+                    // pick H of the query's last row without turning Hp[] into an indexable (local-memory) array:
+                    // a chain of predicated moves, kept opaque to the optimiser
                     T sel = Hp[0];
 #pragma unroll
-                    for( int r = 1; r < R; r++ )
-                        if( r == a.cap_row ) sel = Hp[r];
+                    for( int r = 1; r < R; r++ ) {
+                        T cand = Hp[r];
+                        asm volatile( "" : "+r"( cand ) );
+                        if( r == a.cap_row ) sel = cand;
+                        asm volatile( "" : "+r"( sel ) );
+                    }
                     if( PACKED ) {
                         if( ci & COL_LAST_B ) cap_b = sel;
                         if( ci & COL_LAST_A ) {
