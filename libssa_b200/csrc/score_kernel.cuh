@@ -34,7 +34,7 @@ namespace ssa {
 constexpr uint32_t COL_FIRST = 1u << 10;   // first column of a sequence pair
 constexpr uint32_t COL_LAST_B = 1u << 11;  // last real column of sequence B (low half)
 constexpr uint32_t COL_LAST_A = 1u << 12;  // last column of sequence A = last column of the pair
-constexpr uint32_t COL_VALID = 1u << 15;   // set by lane 0 for real columns
+constexpr uint32_t COL_VALID = 1u << 15;   // real column (padding columns of odd-length pairs are 0)
 
 constexpr int SCORE_THREADS = 256;
 
@@ -121,6 +121,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
 
     // A warp is split into 32/G independent systolic arrays of G lanes (G = 4, 8, 16 or 32, chosen per query so
     // that G*R covers the query with few padded rows while R stays large enough to amortise the per-step work).
+    // Every step a lane advances by TWO database columns (A = even, B = odd column of the step): the two columns'
+    // F chains are independent, which doubles the instruction-level parallelism of the otherwise serial row loop,
+    // and the per-step work (shuffles, flags, loads) is shared by 2R cells.  Sequence pairs are padded to an even
+    // number of columns in the stream, so a sequence always starts in column A.
     const int lane = threadIdx.x & 31;
     const int G = (int) a.group;
     const int gmask = G - 1;
@@ -134,32 +138,111 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     const int row0 = a.rowbase + gl * R;
     const bool gen_top = is_top && ( a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
 
-    // Values of a sequence start (NW: reference needleman_wunsch_64.c:39-42,51-52) are recomputed from row0 where a
-    // sequence starts (rare) instead of being held in registers.
-    T Hp[R], E[R];
+    T Hp[R], E[R];   // H of the last processed column / E entering the next column, per row of this lane
 #pragma unroll
     for( int r = 0; r < R; r++ ) {
         Hp[r] = A::bcast( 0 );
         E[r] = A::bcast( 0 );
     }
     T S = A::bcast( NW ? -32768 : 0 );  // SW: running maximum of this lane's rows; NW: range guard
-    T diag = A::bcast( 0 );             // H of (row0-1, previous column)
+    T diag = A::bcast( 0 );             // H of (row0-1, last processed column)
     T top_h = A::bcast( 0 ), top_f = A::bcast( 0 );
-    T h_out = A::bcast( 0 ), f_out = A::bcast( 0 ), s_out = A::bcast( 0 );
+    T ha_out = A::bcast( 0 ), fa_out = A::bcast( 0 ), hb_out = A::bcast( 0 ), fb_out = A::bcast( 0 ), s_out = A::bcast( 0 );
     T cap_b = A::bcast( 0 );            // NW PACKED: score of sequence B, kept until the pair ends
     int jcol = 0;                       // TRACK: column index within the sequence
     int f8 = 0x7fffffff, f16 = 0x7fffffff, f8_out = 0x7fffffff, f16_out = 0x7fffffff;
     int guard_max = -0x7fffffff;
 
     // current work batch of this group
-    const uint16_t * st = a.stream;
-    const uint32_t * bnd_h_in = nullptr, * bnd_f_in = nullptr;
-    uint32_t * bnd_h_out = nullptr, * bnd_f_out = nullptr;
-    int ncols = 0, nsteps = 0, t = 0, out_idx = 0;
+    const uint32_t * st = (const uint32_t *) a.stream;   // two 16-bit column words per element
+    const uint2 * bnd_h_in = nullptr, * bnd_f_in = nullptr;
+    uint2 * bnd_h_out = nullptr, * bnd_f_out = nullptr;
+    int nsteps_cols = 0, nsteps = 0, t = 0, out_idx = 0;   // nsteps_cols = column pairs of the batch
     uint32_t half = 0;
     bool done = false;
-    uint32_t ci_n1 = 0, ci_n2 = 0;                  // column words of the next two steps (software prefetch)
-    uint32_t bh_n1 = 0, bf_n1 = 0, bh_n2 = 0, bf_n2 = 0, wh = 0, wf = 0;
+    uint32_t w_n1 = 0, w_n2 = 0;        // column words of the next two steps (software prefetch)
+    uint2 bh_n1 = make_uint2( 0, 0 ), bf_n1 = make_uint2( 0, 0 ), bh_n2 = make_uint2( 0, 0 ), bf_n2 = make_uint2( 0, 0 );
+
+    // one database column through this lane's R rows (used where the two-column loop does not apply)
+    auto single_column = [&]( const uint32_t ci, const T h_in, const T f_in, T & h_last, T & f_last ) {
+        T f = f_in;
+        T hd = diag;
+        diag = h_in;
+        if( PACKED ) {
+            const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
+            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
+            uint32_t la = lds32( pa ), lb = lds32( pb );
+            T tc = A::add( hd, (T) __byte_perm( lb, la, 0x5410 ) );
+#pragma unroll
+            for( int k = 0; k < R / 2; k++ ) {
+                const T t0 = tc;
+                const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
+                if( k + 1 < R / 2 ) {
+                    la = lds32( pa + ( k + 1 ) * 4096 );
+                    lb = lds32( pb + ( k + 1 ) * 4096 );
+                    tc = A::add( Hp[2 * k + 1], (T) __byte_perm( lb, la, 0x5410 ) );
+                }
+                T hq;
+                Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                hq = A::add( Hp[2 * k], QR );
+                E[2 * k] = A::addmax( E[2 * k], RG, hq );
+                f = A::addmax( f, RG, hq );
+                Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                hq = A::add( Hp[2 * k + 1], QR );
+                E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
+                f = A::addmax( f, RG, hq );
+                S = A::max3( S, t0, t1 );
+            }
+        }
+        else {
+            const uint32_t d = half ? ( ( ci >> 5 ) & 31u ) : ( ci & 31u );
+            const uint32_t pa = prof_base + ( d << 7 );
+            T colmax = A::bcast( 0 );
+#pragma unroll
+            for( int r = 0; r < R; r++ ) {
+                const T v = (T) lds32( pa + r * 4096 );
+                const T tt = A::add( hd, v );
+                hd = Hp[r];
+                const T h = NW ? A::max3( tt, E[r], f ) : A::max3_relu( tt, E[r], f );
+                const T hq = A::add( h, QR );
+                E[r] = A::addmax( E[r], RG, hq );
+                f = A::addmax( f, RG, hq );
+                Hp[r] = h;
+                if( !NW ) colmax = A::max2( colmax, h );
+            }
+            if( !NW ) S = A::max2( S, colmax );
+            if( TRACK ) {
+                if( (int) colmax >= a.thr8 && f8 == 0x7fffffff ) f8 = jcol;
+                if( (int) colmax >= a.thr16 && f16 == 0x7fffffff ) f16 = jcol;
+                jcol++;
+            }
+        }
+        h_last = Hp[R - 1];
+        f_last = f;
+    };
+
+    // NW: the lane that owns the query's last row records H at the last column of sequence A / B
+    auto nw_capture = [&]( const uint32_t ci ) {
+        if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
+            // pick H of the query's last row without turning Hp[] into an indexable (local-memory) array:
+            // a chain of predicated moves, kept opaque to the optimiser
+            T sel = Hp[0];
+#pragma unroll
+            for( int r = 1; r < R; r++ ) {
+                T cand = Hp[r];
+                asm volatile( "" : "+r"( cand ) );
+                if( r == a.cap_row ) sel = cand;
+                asm volatile( "" : "+r"( sel ) );
+            }
+            if( PACKED ) {
+                if( ci & COL_LAST_B ) cap_b = sel;
+                if( ci & COL_LAST_A ) ( (uint32_t *) a.out )[out_idx++] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
+            }
+            else {
+                if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
+            }
+        }
+    };
 
     while( true ) {
         if( t >= nsteps ) {  // group-uniform: this group's batch is finished, pull the next one from the queue
@@ -168,48 +251,54 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             b = __shfl_sync( group_mask, b, 0, G );
             if( b >= a.nbatches ) {
                 done = true;
-                ncols = 0;
+                nsteps_cols = 0;
                 nsteps = 0x7fffffff;
-                ci_n1 = 0;
-                ci_n2 = 0;
+                w_n1 = 0;
+                w_n2 = 0;
             }
             else {
                 const Batch bt = a.batches[b];
-                st = a.stream + bt.col0;
-                ncols = (int) bt.ncols;
-                nsteps = ncols + gmask;
+                st = (const uint32_t *) ( a.stream + bt.col0 );   // col0 is even: 4-byte aligned
+                nsteps_cols = (int) ( bt.ncols >> 1 );
+                nsteps = nsteps_cols + gmask;
                 out_idx = (int) bt.out0;
                 half = bt.half;
                 if( MULTI ) {
-                    bnd_h_in = a.bnd_h_in ? a.bnd_h_in + bt.bnd0 : nullptr;
-                    bnd_f_in = a.bnd_f_in ? a.bnd_f_in + bt.bnd0 : nullptr;
-                    bnd_h_out = a.bnd_h_out ? a.bnd_h_out + bt.bnd0 : nullptr;
-                    bnd_f_out = a.bnd_f_out ? a.bnd_f_out + bt.bnd0 : nullptr;
+                    bnd_h_in = a.bnd_h_in ? (const uint2 *) ( a.bnd_h_in + bt.bnd0 ) : nullptr;
+                    bnd_f_in = a.bnd_f_in ? (const uint2 *) ( a.bnd_f_in + bt.bnd0 ) : nullptr;
+                    bnd_h_out = a.bnd_h_out ? (uint2 *) ( a.bnd_h_out + bt.bnd0 ) : nullptr;
+                    bnd_f_out = a.bnd_f_out ? (uint2 *) ( a.bnd_f_out + bt.bnd0 ) : nullptr;
                 }
-                // lane gl works on column t - gl at step t: preload the columns of steps 0 and 1
-                ci_n1 = ( gl == 0 ) ? ( (uint32_t) st[0] | COL_VALID ) : 0;
-                ci_n2 = ( 1 - gl >= 0 && 1 - gl < ncols ) ? ( (uint32_t) st[1 - gl] | COL_VALID ) : 0;
+                // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
+                w_n1 = ( gl == 0 ) ? st[0] : 0;
+                w_n2 = ( 1 - gl >= 0 && 1 - gl < nsteps_cols ) ? st[1 - gl] : 0;
                 if( MULTI && bnd_h_in && is_top ) {
                     bh_n1 = bnd_h_in[0];
                     bf_n1 = bnd_f_in[0];
-                    bh_n2 = ncols > 1 ? bnd_h_in[1] : 0;
-                    bf_n2 = ncols > 1 ? bnd_f_in[1] : 0;
+                    if( nsteps_cols > 1 ) {
+                        bh_n2 = bnd_h_in[1];
+                        bf_n2 = bnd_f_in[1];
+                    }
                 }
             }
             t = 0;
         }
         if( __all_sync( FULL, done ) ) break;
 
-        // Every lane reads the column word of ITS column (t - gl) straight from the stream, two steps ahead of use:
-        // the G lanes of a group touch G consecutive 16-bit words, all groups run the same instruction stream.
-        const uint32_t ci = ci_n1;
-        ci_n1 = ci_n2;
+        // Every lane reads the column words of ITS column pair (t - gl) straight from the stream, two steps ahead
+        // of use: the G lanes of a group touch G consecutive 32-bit words, all groups run the same instructions.
+        const uint32_t w = w_n1;
+        w_n1 = w_n2;
         {
             const int c = t + 2 - gl;
-            ci_n2 = ( c >= 0 && c < ncols ) ? ( (uint32_t) st[c] | COL_VALID ) : 0;
+            w_n2 = ( c >= 0 && c < nsteps_cols ) ? st[c] : 0;
         }
-        T h_in = (T) __shfl_up_sync( FULL, h_out, 1, G );
-        T f_in = (T) __shfl_up_sync( FULL, f_out, 1, G );
+        const uint32_t cia = w & 0xffffu, cib = w >> 16;
+
+        T ha_in = (T) __shfl_up_sync( FULL, ha_out, 1, G );
+        T fa_in = (T) __shfl_up_sync( FULL, fa_out, 1, G );
+        T hb_in = (T) __shfl_up_sync( FULL, hb_out, 1, G );
+        T fb_in = (T) __shfl_up_sync( FULL, fb_out, 1, G );
         T s_in = A::bcast( 0 );
         int f8_in = 0x7fffffff, f16_in = 0x7fffffff;
         if( !NW ) s_in = (T) __shfl_up_sync( FULL, s_out, 1, G );
@@ -222,32 +311,40 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             f8_in = 0x7fffffff;
             f16_in = 0x7fffffff;
             if( gen_top ) {
-                if( NW && ( ci & COL_FIRST ) ) {
+                if( NW && ( cia & COL_FIRST ) ) {
                     top_h = A::bcast( a.gap_open + a.gap_extend - a.offset );
                     top_f = A::bcast( 2 * a.gap_open + 2 * a.gap_extend - a.offset );
                 }
-                h_in = top_h;
-                f_in = top_f;
+                ha_in = top_h;
+                fa_in = top_f;
+                if( NW ) {
+                    top_h = A::add( top_h, RG );
+                    top_f = A::add( top_f, RG );
+                }
+                hb_in = top_h;
+                fb_in = top_f;
                 if( NW ) {
                     top_h = A::add( top_h, RG );
                     top_f = A::add( top_f, RG );
                 }
             }
             else if( MULTI ) {
-                h_in = (T) bh_n1;
-                f_in = (T) bf_n1;
+                ha_in = (T) bh_n1.x;
+                hb_in = (T) bh_n1.y;
+                fa_in = (T) bf_n1.x;
+                fb_in = (T) bf_n1.y;
                 bh_n1 = bh_n2;
                 bf_n1 = bf_n2;
-                if( bnd_h_in && t + 2 < ncols ) {
+                if( bnd_h_in && t + 2 < nsteps_cols ) {
                     bh_n2 = bnd_h_in[t + 2];
                     bf_n2 = bnd_f_in[t + 2];
                 }
             }
         }
 
-        T h_last = A::bcast( 0 ), f_last = A::bcast( 0 );
-        if( ci & COL_VALID ) {
-            if( ci & COL_FIRST ) {  // a new sequence (pair) starts in this lane
+        T ha_last = A::bcast( 0 ), fa_last = A::bcast( 0 ), hb_last = A::bcast( 0 ), fb_last = A::bcast( 0 );
+        if( cia & COL_VALID ) {
+            if( cia & COL_FIRST ) {  // a new sequence (pair) starts in this lane (always in column A)
                 T hv = A::bcast( 0 ), ev = A::bcast( 0 );
                 if( NW ) {
                     hv = A::bcast( a.gap_open + ( row0 + 1 ) * a.gap_extend - a.offset );
@@ -272,98 +369,89 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 f16 = 0x7fffffff;
             }
 
-            T f = f_in;
-            T hd = diag;
-            diag = h_in;
-            T colmax = A::bcast( 0 );
-            if( PACKED ) {
-                const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
-                const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
-                // The diagonal candidate of row r+1 (old H of row r + its substitution score) is formed BEFORE row r's
-                // H register is overwritten, so every H stays in one physical register across steps (no rotation moves).
-                uint32_t la = lds32( pa ), lb = lds32( pb );
-                T tc = A::add( hd, (T) __byte_perm( lb, la, 0x5410 ) );
+            const bool b_valid = ( cib & COL_VALID ) != 0;
+            const bool slow = !PACKED || !b_valid || ( NW && ( cia & ( COL_LAST_A | COL_LAST_B ) ) );
+            if( slow ) {
+                // column by column: the wide tier, the padded last column of an odd-length pair, and NW results
+                // that must be read between the two columns
+                single_column( cia, ha_in, fa_in, ha_last, fa_last );
+                if( NW ) nw_capture( cia );
+                if( b_valid ) {
+                    single_column( cib, hb_in, fb_in, hb_last, fb_last );
+                    if( NW ) nw_capture( cib );
+                }
+            }
+            else {
+                // ---- two columns per step, packed tier ----
+                // Row r of column B needs row r of column A (E, H) and row r-1 of column B (F); row r+1 of column A
+                // needs neither, so the two F chains overlap.  The diagonal candidate of the NEXT row of column A
+                // (old H + substitution score) is formed before that row's H register is overwritten, so every H
+                // stays in one physical register across steps.
+                const uint32_t paa = prof_base + ( ( cia & 31u ) << 7 );
+                const uint32_t pba = prof_base + ( ( ( cia >> 5 ) & 31u ) << 7 );
+                const uint32_t pab = prof_base + ( ( cib & 31u ) << 7 );
+                const uint32_t pbb = prof_base + ( ( ( cib >> 5 ) & 31u ) << 7 );
+                T fa = fa_in, fb = fb_in;
+                T ha_prev = ha_in;                       // H of column A, previous row (diagonal of column B)
+                uint32_t laa = lds32( paa ), lba = lds32( pba );
+                T tca = A::add( diag, (T) __byte_perm( lba, laa, 0x5410 ) );
+                diag = hb_in;
 #pragma unroll
                 for( int k = 0; k < R / 2; k++ ) {
-                    const T t0 = tc;
-                    const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
+                    const uint32_t lab = lds32( pab + k * 4096 ), lbb = lds32( pbb + k * 4096 );
+                    const T ta0 = tca;
+                    const T ta1 = A::add( Hp[2 * k], (T) __byte_perm( lba, laa, 0x7632 ) );
                     if( k + 1 < R / 2 ) {
-                        la = lds32( pa + ( k + 1 ) * 4096 );
-                        lb = lds32( pb + ( k + 1 ) * 4096 );
-                        tc = A::add( Hp[2 * k + 1], (T) __byte_perm( lb, la, 0x5410 ) );
+                        laa = lds32( paa + ( k + 1 ) * 4096 );
+                        lba = lds32( pba + ( k + 1 ) * 4096 );
+                        tca = A::add( Hp[2 * k + 1], (T) __byte_perm( lba, laa, 0x5410 ) );
                     }
                     T hq;
-                    Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                    // column A, row 2k
+                    const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
+                    hq = A::add( ha0, QR );
+                    const T ea0 = A::addmax( E[2 * k], RG, hq );
+                    fa = A::addmax( fa, RG, hq );
+                    // column B, row 2k
+                    const T tb0 = A::add( ha_prev, (T) __byte_perm( lbb, lab, 0x5410 ) );
+                    Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
                     hq = A::add( Hp[2 * k], QR );
-                    E[2 * k] = A::addmax( E[2 * k], RG, hq );
-                    f = A::addmax( f, RG, hq );
-                    Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                    E[2 * k] = A::addmax( ea0, RG, hq );
+                    fb = A::addmax( fb, RG, hq );
+                    // column A, row 2k+1
+                    const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
+                    hq = A::add( ha1, QR );
+                    const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
+                    fa = A::addmax( fa, RG, hq );
+                    // column B, row 2k+1
+                    const T tb1 = A::add( ha0, (T) __byte_perm( lbb, lab, 0x7632 ) );
+                    Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
                     hq = A::add( Hp[2 * k + 1], QR );
-                    E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
-                    f = A::addmax( f, RG, hq );
-                    // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over
-                    // H: with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).
-                    // Giving t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it
-                    // stays a VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same
-                    // accumulator as an upper range guard.
-                    S = A::max3( S, t0, t1 );
+                    E[2 * k + 1] = A::addmax( ea1, RG, hq );
+                    fb = A::addmax( fb, RG, hq );
+                    ha_prev = ha1;
+                    // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
+                    // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
+                    // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
+                    // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
+                    // as an upper range guard.
+                    S = A::max3( S, ta0, ta1 );
+                    S = A::max3( S, tb0, tb1 );
                 }
+                ha_last = ha_prev;
+                fa_last = fa;
+                hb_last = Hp[R - 1];
+                fb_last = fb;
+                if( NW ) nw_capture( cib );
             }
-            else {
-                const uint32_t d = half ? ( ( ci >> 5 ) & 31u ) : ( ci & 31u );
-                const uint32_t pa = prof_base + ( d << 7 );
-#pragma unroll
-                for( int r = 0; r < R; r++ ) {
-                    const T v = (T) lds32( pa + r * 4096 );
-                    const T tt = A::add( hd, v );
-                    hd = Hp[r];
-                    const T h = NW ? A::max3( tt, E[r], f ) : A::max3_relu( tt, E[r], f );
-                    const T hq = A::add( h, QR );
-                    E[r] = A::addmax( E[r], RG, hq );
-                    f = A::addmax( f, RG, hq );
-                    Hp[r] = h;
-                    if( !NW ) colmax = A::max2( colmax, h );
-                }
-                if( !NW ) S = A::max2( S, colmax );
-                if( TRACK ) {
-                    if( (int) colmax >= a.thr8 && f8 == 0x7fffffff ) f8 = jcol;
-                    if( (int) colmax >= a.thr16 && f16 == 0x7fffffff ) f16 = jcol;
-                    jcol++;
-                }
-            }
-            h_last = Hp[R - 1];
-            f_last = f;
 
-            // ---- results at sequence ends (rare, divergent) ----
-            if( NW ) {
-                if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
-                    // pick H of the query's last row without turning Hp[] into an indexable (local-memory) array:
-                    // a chain of predicated moves, kept opaque to the optimiser
-                    T sel = Hp[0];
-#pragma unroll
-                    for( int r = 1; r < R; r++ ) {
-                        T cand = Hp[r];
-                        asm volatile( "" : "+r"( cand ) );
-                        if( r == a.cap_row ) sel = cand;
-                        asm volatile( "" : "+r"( sel ) );
-                    }
-                    if( PACKED ) {
-                        if( ci & COL_LAST_B ) cap_b = sel;
-                        if( ci & COL_LAST_A ) {
-                            ( (uint32_t *) a.out )[out_idx++] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
-                        }
-                    }
-                    else {
-                        if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
-                    }
-                }
-            }
-            else {
+            // ---- SW results at sequence ends (rare, divergent) ----
+            if( !NW ) {
                 const uint32_t last_mask = PACKED ? COL_LAST_A : ( half ? COL_LAST_B : COL_LAST_A );
                 s_out = A::bcast( 0 );
                 f8_out = 0x7fffffff;
                 f16_out = 0x7fffffff;
-                if( ci & last_mask ) {
+                if( ( cia | cib ) & last_mask ) {
                     s_out = A::max2( s_in, S );
                     if( TRACK ) {
                         f8_out = min( f8_in, f8 );
@@ -385,28 +473,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     }
                 }
             }
-        }
-        h_out = h_last;
-        f_out = f_last;
-
-        if( MULTI ) {  // the bottom lane's last row becomes the next pass' top boundary
-            const int cb = t - gmask;
-            const uint32_t vh = __shfl_sync( FULL, (uint32_t) h_out, gmask, G );
-            const uint32_t vf = __shfl_sync( FULL, (uint32_t) f_out, gmask, G );
-            if( bnd_h_out && cb >= 0 && cb < ncols ) {
-                if( gl == ( cb & gmask ) ) {
-                    wh = vh;
-                    wf = vf;
-                }
-                if( ( cb & gmask ) == gmask || cb == ncols - 1 ) {
-                    const int c = ( cb & ~gmask ) + gl;
-                    if( c <= cb ) {
-                        bnd_h_out[c] = wh;
-                        bnd_f_out[c] = wf;
-                    }
-                }
+            if( MULTI && is_bottom && bnd_h_out ) {  // this lane's last row becomes the next pass' top boundary
+                bnd_h_out[t - gmask] = make_uint2( (uint32_t) ha_last, (uint32_t) hb_last );
+                bnd_f_out[t - gmask] = make_uint2( (uint32_t) fa_last, (uint32_t) fb_last );
             }
         }
+        ha_out = ha_last;
+        fa_out = fa_last;
+        hb_out = hb_last;
+        fb_out = fb_last;
+
         if( NW && PACKED && t == nsteps - 1 ) {
             const int hi = (int) (int16_t) ( (uint32_t) S >> 16 ), lo = (int) (int16_t) ( (uint32_t) S & 0xffffu );
             guard_max = max( guard_max, max( hi, lo ) );

@@ -206,11 +206,12 @@ void build_db() {
     const size_t nloc = db.sorted_id.size();
     db.npairs = ( nloc + 1 ) / 2;
     db.pair_col.assign( db.npairs + 1, 0 );
-    for( size_t p = 0; p < db.npairs; p++ ) db.pair_col[p + 1] = db.pair_col[p] + db.sorted_len[2 * p];
+    // every pair occupies an even number of stream columns (the kernels advance two columns per step)
+    for( size_t p = 0; p < db.npairs; p++ ) db.pair_col[p + 1] = db.pair_col[p] + ( ( (uint64_t) db.sorted_len[2 * p] + 1 ) & ~1ull );
     db.total_cols = db.pair_col[db.npairs];
 
     // column stream: bits 0-4 residue of A, 5-9 residue of B (0 past its end, like the reference's padding,
-    // src/algo/8/search_8_util.h:60-74), 10 first column, 11 last column of B, 12 last column of A
+    // src/algo/8/search_8_util.h:60-74), 10 first column, 11 last column of B, 12 last column of A, 15 valid column
     PinBuf<uint16_t> h_stream;
     h_stream.reserve( db.total_cols + 64 );
     std::vector<size_t> unknown_per_chunk( ( db.npairs + 1023 ) / 1024 + 1, 0 );
@@ -237,12 +238,13 @@ void build_db() {
                         unknown++;
                     }
                 }
-                uint32_t v = (uint32_t) a | ( (uint32_t) b << 5 );
+                uint32_t v = (uint32_t) a | ( (uint32_t) b << 5 ) | COL_VALID;
                 if( c == 0 ) v |= COL_FIRST;
                 if( c + 1 == lb ) v |= COL_LAST_B;
                 if( c + 1 == la ) v |= COL_LAST_A;
                 out[c] = (uint16_t) v;
             }
+            if( la & 1 ) out[la] = 0;  // padding column of an odd-length pair: not VALID
         }
         unknown_per_chunk[p0 / 1024] = unknown;
     } );
@@ -533,7 +535,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         uint32_t s = slots[i];
         b.col0 = db.pair_col[s / 2];
         b.bnd0 = bnd;
-        b.ncols = db.sorted_len[s];
+        b.ncols = ( db.sorted_len[s] + 1u ) & ~1u;   // whole column pairs
         b.out0 = s;
         b.half = s & 1;
         bnd += b.ncols;
@@ -738,7 +740,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             const size_t p = long_pair0 + i;
             b.col0 = db.pair_col[p];
             b.bnd0 = db.pair_col[p];
-            b.ncols = db.sorted_len[2 * p];
+            b.ncols = (uint32_t) ( db.pair_col[p + 1] - db.pair_col[p] );
             b.out0 = (uint32_t) p;
             ctx.h_long_batches.p[i] = b;
         }
