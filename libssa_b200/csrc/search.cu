@@ -5,6 +5,7 @@
 #include "common.h"
 #include "score_launch.h"
 #include "traceback.h"
+#include "arrival.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -86,10 +87,18 @@ struct PackedDb {
     };
     std::map<uint32_t, BatchTable> batch_tables;  // keyed by columns per batch
     DevBuf<uint16_t> d_stream;
+    DevBuf<uint32_t> d_lens_all;           // record lengths, provider order (for the arrival-order kernel)
+    DevBuf<int32_t> d_sorted_pos_of_id;    // provider index -> global sorted position
+    struct ChunkInfo {                     // per chunk size: where each chunk's records start in arrival order
+        DevBuf<uint32_t> d_chunk_base;
+        uint32_t nchunks = 0;
+        size_t narr = 0;
+    };
+    std::map<size_t, ChunkInfo> chunk_info;
     double pack_ms = 0, upload_ms = 0;
     // arrival order caches, keyed by (bit_width, chunk): provider indices in heap-arrival order
     struct Arrival {
-        std::vector<uint32_t> order;       // arrival position -> provider index
+        std::vector<uint32_t> order;       // arrival position -> provider index (host copy)
         DevBuf<int32_t> d_pos_of_sorted;   // GLOBAL sorted position -> arrival position (-1 = never processed)
         bool uploaded = false;
     };
@@ -111,11 +120,15 @@ struct Ctx {
     PinBuf<uint32_t> h_profile_long;
     DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
     std::vector<uint32_t> order_tmp;
-    DevBuf<Batch> d_wide_batches;
+    DevBuf<Batch> d_wide_batches[2];
+    DevBuf<uint32_t> d_profile_wide[2];
+    PinBuf<uint32_t> h_profile_wide[2];
+    DevBuf<uint32_t> d_order;
+    PinBuf<uint32_t> h_order;
     DevBuf<uint32_t> d_flag_list;
     PinBuf<uint32_t> h_profile, h_list;
     PinBuf<int32_t> h_scores, h_first, h_pos;
-    PinBuf<Batch> h_wide_batches;
+    PinBuf<Batch> h_wide_batches[2];
     ssa_b200_stats_t stats;
 };
 
@@ -260,6 +273,18 @@ void build_db() {
     db.d_stream.reserve( db.total_cols + 64 );
     CUDA_OK( cudaMemcpyAsync( db.d_stream.p, h_stream.p, ( db.total_cols + 64 ) * sizeof( uint16_t ), cudaMemcpyHostToDevice,
             ctx.stream ) );
+    {
+        std::vector<uint32_t> lens32( nall );
+        for( size_t i = 0; i < nall; i++ ) lens32[i] = (uint32_t) db.lens_all[i];
+        db.d_lens_all.reserve( nall + 1 );
+        db.d_sorted_pos_of_id.reserve( nall + 1 );
+        if( nall ) {
+            CUDA_OK( cudaMemcpy( db.d_lens_all.p, lens32.data(), nall * 4, cudaMemcpyHostToDevice ) );
+            CUDA_OK( cudaMemcpy( db.d_sorted_pos_of_id.p, db.sorted_pos_of_id.data(), nall * 4, cudaMemcpyHostToDevice ) );
+        }
+        for( auto & kv : db.chunk_info ) kv.second.d_chunk_base.release();
+        db.chunk_info.clear();
+    }
     CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     h_stream.release();
     db.upload_ms = wall_ms() - t1;
@@ -522,12 +547,14 @@ void launch_fill( int32_t * p, int32_t v, size_t n ) {
 }
 
 // runs the wide tier over `items` (slots = sorted positions); optional first-crossing tracking
+// `slot` selects the staging buffers (0 = wide tier of a search, 1 = overflow tracking) so that a second use inside
+// one search never overwrites pinned memory an earlier asynchronous copy has not consumed yet
 void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t qlen, const Plan & pl, bool nw, bool track,
-        int32_t * d_first8, int32_t * d_first16 ) {
+        int32_t * d_first8, int32_t * d_first16, int slot ) {
     PackedDb & db = ctx.db;
     if( slots.empty() ) return;
     const size_t n = slots.size();
-    ctx.h_wide_batches.reserve( n );
+    ctx.h_wide_batches[slot].reserve( n );
     uint64_t bnd = 0;
     for( size_t i = 0; i < n; i++ ) {
         Batch b;
@@ -539,17 +566,17 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         b.out0 = s;
         b.half = s & 1;
         bnd += b.ncols;
-        ctx.h_wide_batches.p[i] = b;
+        ctx.h_wide_batches[slot].p[i] = b;
     }
-    ctx.d_wide_batches.reserve( n );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches.p, ctx.h_wide_batches.p, n * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
+    ctx.d_wide_batches[slot].reserve( n );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
     ctx.stats.h2d_bytes += n * sizeof( Batch );
     const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
-    ctx.h_profile.reserve( words * npass );
-    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile.p + p * words, q, qlen, pl, p );
-    ctx.d_profile.reserve( words * npass );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_profile.p, ctx.h_profile.p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
+    ctx.h_profile_wide[slot].reserve( words * npass );
+    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile_wide[slot].p + p * words, q, qlen, pl, p );
+    ctx.d_profile_wide[slot].reserve( words * npass );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[slot].p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
     ctx.stats.h2d_bytes += words * npass * 4;
     if( npass > 1 ) ctx.d_bnd.reserve( 4 * bnd + 256 );
     ctx.d_counter.reserve( 64 );
@@ -558,10 +585,10 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
         a.stream = db.d_stream.p;
-        a.batches = ctx.d_wide_batches.p;
+        a.batches = ctx.d_wide_batches[slot].p;
         a.nbatches = (uint32_t) n;
         a.counter = ctx.d_counter.p;
-        a.profile = ctx.d_profile.p + p * words;
+        a.profile = ctx.d_profile_wide[slot].p + p * words;
         a.group = (uint32_t) G;
         a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
         a.rg_word = (uint32_t) (int) g_gapE;
@@ -776,21 +803,69 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     if( wide_pairs > 0 ) {
         std::vector<uint32_t> slots;
         for( size_t s = 0; s < std::min( nloc, 2 * wide_pairs ); s++ ) slots.push_back( (uint32_t) s );
-        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr );
+        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0 );
     }
     CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
 }
 
-PackedDb::Arrival & arrival_for( int bit_width, size_t chunk ) {
+// where each chunk of `chunk` provider records starts in arrival order (the reference stops at the first chunk
+// without a non-empty record, src/algo/16/search_16.c:123)
+PackedDb::ChunkInfo & chunk_info_for( size_t chunk ) {
     PackedDb & db = ctx.db;
-    auto key = std::make_pair( bit_width, chunk );
-    auto it = db.arrival.find( key );
-    if( it != db.arrival.end() ) return it->second;
-    PackedDb::Arrival & ar = db.arrival[key];
-    arrival_order( db.lens_all, nullptr, nullptr, chunk, bit_width, ar.order );
-    return ar;
+    auto it = db.chunk_info.find( chunk );
+    if( it != db.chunk_info.end() ) return it->second;
+    PackedDb::ChunkInfo & ci = db.chunk_info[chunk];
+    std::vector<uint32_t> base;
+    size_t pos = 0;
+    const size_t n = db.lens_all.size();
+    for( size_t start = 0; start < n; start += chunk ) {
+        size_t cnt = 0;
+        for( size_t i = start; i < std::min( n, start + chunk ); i++ ) cnt += db.lens_all[i] > 0;
+        if( cnt == 0 ) break;
+        base.push_back( (uint32_t) pos );
+        pos += cnt;
+    }
+    ci.nchunks = (uint32_t) base.size();
+    ci.narr = pos;
+    ci.d_chunk_base.reserve( base.size() + 1 );
+    if( !base.empty() ) CUDA_OK( cudaMemcpy( ci.d_chunk_base.p, base.data(), base.size() * 4, cudaMemcpyHostToDevice ) );
+    return ci;
 }
 
+// Runs the scheduler emulation on the GPU (arrival.cuh): fills d_pos (global sorted position -> arrival position,
+// -1 = never reached) and d_order / h_order (arrival position -> provider index).  first_all = gathered overflow
+// columns of the tracking kernel or nullptr.  Returns the number of records in arrival order.
+size_t gpu_arrival_order( int bit_width, size_t chunk, const int32_t * d_first_all, size_t stride, DevBuf<int32_t> & d_pos,
+        uint32_t * h_order ) {
+    PackedDb & db = ctx.db;
+    PackedDb::ChunkInfo & ci = chunk_info_for( chunk );
+    const size_t nglob = db.sorted_all.size();
+    d_pos.reserve( nglob + 1 );
+    ctx.d_order.reserve( ci.narr + 1 );
+    CUDA_OK( cudaMemsetAsync( d_pos.p, 0xff, ( nglob + 1 ) * sizeof( int32_t ), ctx.stream ) );
+    if( ci.nchunks > 0 ) {
+        ArrivalArgs a;
+        a.lens = db.d_lens_all.p;
+        a.n_all = (uint32_t) db.lens_all.size();
+        a.chunk = (uint32_t) chunk;
+        a.nchunks = ci.nchunks;
+        a.chunk_base = ci.d_chunk_base.p;
+        a.bit_width = bit_width;
+        a.sorted_pos_of_id = db.d_sorted_pos_of_id.p;
+        a.first_all = d_first_all;
+        a.stride = (uint32_t) stride;
+        a.world = (uint32_t) ctx.world;
+        a.order = ctx.d_order.p;
+        a.pos_of_sorted = d_pos.p;
+        arrival_kernel<<<ci.nchunks, 32, 0, ctx.stream>>>( a );
+        ctx.stats.launches++;
+        CUDA_OK( cudaMemcpyAsync( h_order, ctx.d_order.p, ci.narr * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+        ctx.stats.d2h_bytes += ci.narr * sizeof( uint32_t );
+    }
+    return ci.narr;
+}
+
+PackedDb::Arrival & arrival_for( int bit_width, size_t chunk, bool on_gpu );
 void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_pos ) {
     PackedDb & db = ctx.db;
     const size_t nglob = db.sorted_all.size();
@@ -802,6 +877,26 @@ void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_
     CUDA_OK( cudaMemcpyAsync( d_pos.p, pos, nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
     CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     ctx.stats.h2d_bytes += nglob * sizeof( int32_t );
+}
+
+PackedDb::Arrival & arrival_for( int bit_width, size_t chunk, bool on_gpu ) {
+    PackedDb & db = ctx.db;
+    auto key = std::make_pair( bit_width, chunk );
+    auto it = db.arrival.find( key );
+    if( it != db.arrival.end() ) return it->second;
+    PackedDb::Arrival & ar = db.arrival[key];
+    if( on_gpu ) {
+        ctx.h_order.reserve( db.sorted_all.size() + 1 );
+        const size_t n = gpu_arrival_order( bit_width, chunk, nullptr, 1, ar.d_pos_of_sorted, ctx.h_order.p );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        ar.order.assign( ctx.h_order.p, ctx.h_order.p + n );
+    }
+    else {
+        arrival_order( db.lens_all, nullptr, nullptr, chunk, bit_width, ar.order );
+        upload_positions( ar.order, ar.d_pos_of_sorted );
+    }
+    ar.uploaded = true;
+    return ar;
 }
 
 // all-gather `count` int32 per rank from d_send into d_recv (rank-major); world = 1: plain copy
@@ -829,6 +924,10 @@ void gpu_release() {
     if( !ctx.init ) return;
     cudaStreamSynchronize( ctx.stream );
     ctx.db.d_stream.release();
+    ctx.db.d_lens_all.release();
+    ctx.db.d_sorted_pos_of_id.release();
+    for( auto & kv : ctx.db.chunk_info ) kv.second.d_chunk_base.release();
+    ctx.db.chunk_info.clear();
     for( auto & kv : ctx.db.batch_tables ) kv.second.d_batches.release();
     ctx.db.batch_tables.clear();
     for( auto & kv : ctx.db.arrival ) kv.second.d_pos_of_sorted.release();
@@ -845,14 +944,20 @@ void gpu_release() {
     ctx.d_gathered.release();
     ctx.d_pos_tmp.release();
     ctx.d_guard.release();
-    ctx.d_wide_batches.release();
+    for( int i = 0; i < 2; i++ ) {
+        ctx.d_wide_batches[i].release();
+        ctx.h_wide_batches[i].release();
+        ctx.d_profile_wide[i].release();
+        ctx.h_profile_wide[i].release();
+    }
+    ctx.d_order.release();
+    ctx.h_order.release();
     ctx.d_flag_list.release();
     ctx.h_profile.release();
     ctx.h_list.release();
     ctx.h_scores.release();
     ctx.h_first.release();
     ctx.h_pos.release();
-    ctx.h_wide_batches.release();
     traceback_release();
     cudaEventDestroy( ctx.ev_begin );
     cudaEventDestroy( ctx.ev_k0 );
@@ -936,6 +1041,9 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     // block in which the running maximum got there, which changes the order in which scores reach the heap.
     std::vector<int64_t> ovf8, ovf16;
     bool have_overflow = false;
+    const bool use_gpu_arrival = g_chunk_size <= (size_t) ARRIVAL_MAX_CHUNK;
+    const int32_t * d_first_gathered = nullptr;
+    uint32_t n_flagged = 0;
     if( !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const int32_t thr = req.bit_width == 8 ? 255 : 65535;
         const uint32_t total = (uint32_t) ( stride * world );
@@ -965,58 +1073,61 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
             int32_t * d_f = ctx.d_first.p;  // [stride] first8 | [stride] first16
             launch_fill( d_f, INT_MAX, 2 * stride );
             Plan pl = make_plan( req.qlen );
-            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride );  // rewrites the same exact scores
+            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride, 1 );  // rewrites the same exact scores
             int32_t * d_f_all = d_f;
             if( world > 1 ) {
                 d_f_all = ctx.d_first.p + 2 * stride;
                 gather_i32( d_f, d_f_all, 2 * stride );
             }
+            d_first_gathered = d_f_all;
+            // overflow counters (the reference prints them at OUTPUT_INFO) and, for the host fallback, the columns
             ctx.d_first_compact.reserve( 2 * (size_t) count + 2 );
             gather_first_kernel<<<( count + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_flag_list.p, count, d_f_all, (uint32_t) stride,
                     ctx.d_first_compact.p );
             ctx.stats.launches++;
             ctx.h_first.reserve( 2 * (size_t) count + 2 );
             CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, ctx.d_first_compact.p, 2 * (size_t) count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += 2 * (size_t) count * sizeof( int32_t );
-            ovf8.assign( db.lens_all.size(), -1 );
-            ovf16.assign( db.lens_all.size(), -1 );
-            for( uint32_t k = 0; k < count; k++ ) {   // ctx.h_list still holds the (unsorted) device list order
-                const uint32_t i = ctx.h_list.p[k];
-                const size_t r = i / stride, sl = i % stride;
-                const uint32_t id = db.sorted_all[sl * world + r];
-                const int32_t c8 = ctx.h_first.p[k], c16 = ctx.h_first.p[count + k];
-                if( req.bit_width == 8 && c8 != INT_MAX ) {
-                    ovf8[id] = c8 / 4;
-                    ctx.stats.overflow_8++;
-                }
-                if( c16 != INT_MAX ) {
-                    ovf16[id] = c16 / 4;
-                    ctx.stats.overflow_16++;
+            if( !use_gpu_arrival ) {
+                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+                ovf8.assign( db.lens_all.size(), -1 );
+                ovf16.assign( db.lens_all.size(), -1 );
+                for( uint32_t k = 0; k < count; k++ ) {   // ctx.h_list still holds the (unsorted) device list order
+                    const uint32_t i = ctx.h_list.p[k];
+                    const size_t r = i / stride, sl = i % stride;
+                    const uint32_t id = db.sorted_all[sl * world + r];
+                    const int32_t c8 = ctx.h_first.p[k], c16 = ctx.h_first.p[count + k];
+                    if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[id] = c8 / 4;
+                    if( c16 != INT_MAX ) ovf16[id] = c16 / 4;
                 }
             }
+            ctx.stats.d2h_bytes += 2 * (size_t) count * sizeof( int32_t );
+            n_flagged = count;
         }
     }
 
     // ---- heap-arrival order of the emulated one-thread reference run ----
-    const std::vector<uint32_t> * order = nullptr;
+    const uint32_t * order = nullptr;
+    size_t narr = 0;
     DevBuf<int32_t> * d_pos = nullptr;
-    if( !have_overflow ) {
-        PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size );
-        if( !ar.uploaded ) {
-            upload_positions( ar.order, ar.d_pos_of_sorted );
-            ar.uploaded = true;
-        }
-        order = &ar.order;
+    if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
+        PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size, use_gpu_arrival );
+        order = ar.order.data();
+        narr = ar.order.size();
         d_pos = &ar.d_pos_of_sorted;
+    }
+    else if( use_gpu_arrival ) {
+        ctx.h_order.reserve( nglob + 1 );
+        narr = gpu_arrival_order( req.bit_width, g_chunk_size, d_first_gathered, stride, ctx.d_pos_tmp, ctx.h_order.p );
+        order = ctx.h_order.p;   // complete once the stream is synchronised below
+        d_pos = &ctx.d_pos_tmp;
     }
     else {
         arrival_order( db.lens_all, ovf8.data(), ovf16.data(), g_chunk_size, req.bit_width, ctx.order_tmp );
         upload_positions( ctx.order_tmp, ctx.d_pos_tmp );
-        order = &ctx.order_tmp;
+        order = ctx.order_tmp.data();
+        narr = ctx.order_tmp.size();
         d_pos = &ctx.d_pos_tmp;
     }
-    const size_t narr = order->size();
     std::vector<Hit> hits;
     if( narr > 0 && nglob > 0 ) {
         ctx.d_arrival_scores.reserve( narr + 1 );
@@ -1029,13 +1140,17 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
         CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
         ctx.stats.d2h_bytes += narr * sizeof( int32_t );
-        replay_topk( ctx.h_scores.p, order->data(), narr, req.hitcount, hits );
+        replay_topk( ctx.h_scores.p, order, narr, req.hitcount, hits );
     }
     else {
         CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
         CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     }
 
+    for( uint32_t k = 0; k < n_flagged; k++ ) {  // valid after the synchronisation above
+        if( req.bit_width == 8 && ctx.h_first.p[k] != INT_MAX ) ctx.stats.overflow_8++;
+        if( ctx.h_first.p[n_flagged + k] != INT_MAX ) ctx.stats.overflow_16++;
+    }
     if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
         print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
                 (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );

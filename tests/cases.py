@@ -132,6 +132,8 @@ CASES = [
      "db": ["protein", 2000, 11, "P07327"], "query": "P07327", "runs": _runs(k=40) + [["sw", 8, 12, A], ["nw", 16, 12, A]]},
     {"name": "synth_protein_2000_chunk100", "symtype": AMINOACID, "scoring": "blosum62", "gaps": [-11, -1], "chunk": 100,
      "db": ["protein", 2000, 11, "P07327"], "query": "P07327", "runs": _runs(k=40)},
+    {"name": "synth_protein_2000_chunk5000", "symtype": AMINOACID, "scoring": "blosum62", "gaps": [-11, -1], "chunk": 5000,
+     "db": ["protein", 2000, 11, "P07327"], "query": "P07327", "runs": _runs(k=40)},   # > 2048: host scheduler emulation
     {"name": "synth_protein_edge_O74807", "symtype": AMINOACID, "scoring": "blosum50", "gaps": [-3, -1],
      "db": ["protein_edge", 1500, 5, "O74807"], "query": "O74807", "runs": _runs(k=30) + [["sw", 16, 2000, S], ["sw", 16, 8, A]]},
     {"name": "synth_protein_long_query", "symtype": AMINOACID, "scoring": "blosum62", "gaps": [-11, -1],
