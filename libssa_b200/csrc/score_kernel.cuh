@@ -155,13 +155,12 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
 
     // current work batch of this group
     const uint32_t * st = (const uint32_t *) a.stream;   // two 16-bit column words per element
-    const uint2 * bnd_h_in = nullptr, * bnd_f_in = nullptr;
-    uint2 * bnd_h_out = nullptr, * bnd_f_out = nullptr;
+    uint32_t bnd_base = 0;              // MULTI: this batch's first column pair in the pass-boundary buffers
     int nsteps_cols = 0, nsteps = 0, t = 0, out_idx = 0;   // nsteps_cols = column pairs of the batch
     uint32_t half = 0;
     bool done = false;
     uint32_t w_n1 = 0, w_n2 = 0;        // column words of the next two steps (software prefetch)
-    uint2 bh_n1 = make_uint2( 0, 0 ), bf_n1 = make_uint2( 0, 0 ), bh_n2 = make_uint2( 0, 0 ), bf_n2 = make_uint2( 0, 0 );
+    uint2 bh_n1 = make_uint2( 0, 0 ), bf_n1 = make_uint2( 0, 0 );   // MULTI: boundary row of the next step (top lane)
 
     // one database column through this lane's R rows (used where the two-column loop does not apply)
     auto single_column = [&]( const uint32_t ci, const T h_in, const T f_in, T & h_last, T & f_last ) {
@@ -263,22 +262,13 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 nsteps = nsteps_cols + gmask;
                 out_idx = (int) bt.out0;
                 half = bt.half;
-                if( MULTI ) {
-                    bnd_h_in = a.bnd_h_in ? (const uint2 *) ( a.bnd_h_in + bt.bnd0 ) : nullptr;
-                    bnd_f_in = a.bnd_f_in ? (const uint2 *) ( a.bnd_f_in + bt.bnd0 ) : nullptr;
-                    bnd_h_out = a.bnd_h_out ? (uint2 *) ( a.bnd_h_out + bt.bnd0 ) : nullptr;
-                    bnd_f_out = a.bnd_f_out ? (uint2 *) ( a.bnd_f_out + bt.bnd0 ) : nullptr;
-                }
+                if( MULTI ) bnd_base = (uint32_t) ( bt.bnd0 >> 1 );
                 // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
                 w_n1 = ( gl == 0 ) ? st[0] : 0;
                 w_n2 = ( 1 - gl >= 0 && 1 - gl < nsteps_cols ) ? st[1 - gl] : 0;
-                if( MULTI && bnd_h_in && is_top ) {
-                    bh_n1 = bnd_h_in[0];
-                    bf_n1 = bnd_f_in[0];
-                    if( nsteps_cols > 1 ) {
-                        bh_n2 = bnd_h_in[1];
-                        bf_n2 = bnd_f_in[1];
-                    }
+                if( MULTI && a.bnd_h_in && is_top ) {
+                    bh_n1 = ( (const uint2 *) a.bnd_h_in )[bnd_base];
+                    bf_n1 = ( (const uint2 *) a.bnd_f_in )[bnd_base];
                 }
             }
             t = 0;
@@ -333,11 +323,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 hb_in = (T) bh_n1.y;
                 fa_in = (T) bf_n1.x;
                 fb_in = (T) bf_n1.y;
-                bh_n1 = bh_n2;
-                bf_n1 = bf_n2;
-                if( bnd_h_in && t + 2 < nsteps_cols ) {
-                    bh_n2 = bnd_h_in[t + 2];
-                    bf_n2 = bnd_f_in[t + 2];
+                if( a.bnd_h_in && t + 1 < nsteps_cols ) {  // next step's boundary row, one step ahead of use
+                    bh_n1 = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 1];
+                    bf_n1 = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 1];
                 }
             }
         }
@@ -473,9 +461,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     }
                 }
             }
-            if( MULTI && is_bottom && bnd_h_out ) {  // this lane's last row becomes the next pass' top boundary
-                bnd_h_out[t - gmask] = make_uint2( (uint32_t) ha_last, (uint32_t) hb_last );
-                bnd_f_out[t - gmask] = make_uint2( (uint32_t) fa_last, (uint32_t) fb_last );
+            if( MULTI && is_bottom && a.bnd_h_out ) {  // this lane's last row becomes the next pass' top boundary
+                ( (uint2 *) a.bnd_h_out )[bnd_base + t - gmask] = make_uint2( (uint32_t) ha_last, (uint32_t) hb_last );
+                ( (uint2 *) a.bnd_f_out )[bnd_base + t - gmask] = make_uint2( (uint32_t) fa_last, (uint32_t) fb_last );
             }
         }
         ha_out = ha_last;

@@ -114,7 +114,7 @@ struct Ctx {
     cudaStream_t stream = nullptr, stream_aux = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     PackedDb db;
-    DevBuf<uint32_t> d_profile, d_profile_long, d_out_packed, d_counter, d_bnd;
+    DevBuf<uint32_t> d_profile, d_profile_long, d_out_packed, d_counter, d_bnd, d_bnd_wide;
     DevBuf<Batch> d_long_batches;
     PinBuf<Batch> h_long_batches;
     PinBuf<uint32_t> h_profile_long;
@@ -550,7 +550,7 @@ void launch_fill( int32_t * p, int32_t v, size_t n ) {
 // `slot` selects the staging buffers (0 = wide tier of a search, 1 = overflow tracking) so that a second use inside
 // one search never overwrites pinned memory an earlier asynchronous copy has not consumed yet
 void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t qlen, const Plan & pl, bool nw, bool track,
-        int32_t * d_first8, int32_t * d_first16, int slot ) {
+        int32_t * d_first8, int32_t * d_first16, int slot, cudaStream_t stream ) {
     PackedDb & db = ctx.db;
     if( slots.empty() ) return;
     const size_t n = slots.size();
@@ -569,25 +569,25 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         ctx.h_wide_batches[slot].p[i] = b;
     }
     ctx.d_wide_batches[slot].reserve( n );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
     ctx.stats.h2d_bytes += n * sizeof( Batch );
     const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
     ctx.h_profile_wide[slot].reserve( words * npass );
     for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile_wide[slot].p + p * words, q, qlen, pl, p );
     ctx.d_profile_wide[slot].reserve( words * npass );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[slot].p, words * npass * 4, cudaMemcpyHostToDevice, ctx.stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
     ctx.stats.h2d_bytes += words * npass * 4;
-    if( npass > 1 ) ctx.d_bnd.reserve( 4 * bnd + 256 );
+    if( npass > 1 ) ctx.d_bnd_wide.reserve( 4 * bnd + 256 );
     ctx.d_counter.reserve( 64 );
     for( int p = 0; p < npass; p++ ) {
-        CUDA_OK( cudaMemsetAsync( ctx.d_counter.p, 0, 4, ctx.stream ) );
+        CUDA_OK( cudaMemsetAsync( ( ctx.d_counter.p + 16 + 8 * slot ), 0, 4, stream ) );
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
         a.stream = db.d_stream.p;
         a.batches = ctx.d_wide_batches[slot].p;
         a.nbatches = (uint32_t) n;
-        a.counter = ctx.d_counter.p;
+        a.counter = ( ctx.d_counter.p + 16 + 8 * slot );
         a.profile = ctx.d_profile_wide[slot].p + p * words;
         a.group = (uint32_t) G;
         a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
@@ -610,14 +610,14 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         a.thr8 = 255;
         a.thr16 = 65535;
         if( npass > 1 ) {
-            uint32_t * base = ctx.d_bnd.p;
+            uint32_t * base = ctx.d_bnd_wide.p;
             uint32_t * h0 = base, * f0 = base + bnd, * h1 = base + 2 * bnd, * f1 = base + 3 * bnd;
             a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
             a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
             a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
-        launch_score_wide( R, nw, npass > 1, track, a, ctx.stream );
+        launch_score_wide( R, nw, npass > 1, track, a, stream );
         ctx.stats.launches++;
     }
     ctx.stats.wide_tier_seqs += n;
@@ -668,7 +668,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
             a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
-        launch_score_packed( R, nw, npass > 1, a, stream );
+        launch_score_packed( R, nw, npass > 1 || getenv( "LIBSSA_B200_FORCE_MULTI" ) != nullptr, a, stream );
         ctx.stats.launches++;
     }
 }
@@ -757,8 +757,18 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     CUDA_OK( cudaEventRecord( ctx.ev_k0, ctx.stream ) );
     ctx.d_out_packed.reserve( db.npairs + 1 );
     ctx.d_counter.reserve( 64 );
-    // ---- long class on the auxiliary stream ----
+    // ---- auxiliary stream: the few sequences of the wide tier and the long class overlap the bulk launch ----
     const size_t n_long = bulk_pair0 - long_pair0;
+    const bool use_aux = n_long > 0 || wide_pairs > 0;
+    if( use_aux ) {
+        CUDA_OK( cudaEventRecord( ctx.ev_fork, ctx.stream ) );
+        CUDA_OK( cudaStreamWaitEvent( ctx.stream_aux, ctx.ev_fork, 0 ) );
+    }
+    if( wide_pairs > 0 ) {  // pairs beyond the packed tier's guaranteed range: exact int32 tier
+        std::vector<uint32_t> slots;
+        for( size_t s = 0; s < std::min( nloc, 2 * wide_pairs ); s++ ) slots.push_back( (uint32_t) s );
+        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0, ctx.stream_aux );
+    }
     if( n_long > 0 ) {
         ctx.h_long_batches.reserve( n_long );
         for( size_t i = 0; i < n_long; i++ ) {
@@ -775,14 +785,12 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
         const size_t words = (size_t) ( long_R / 2 ) * 1024;
         ctx.h_profile_long.reserve( words );
         ctx.d_profile_long.reserve( words );
-        CUDA_OK( cudaEventRecord( ctx.ev_fork, ctx.stream ) );
-        CUDA_OK( cudaStreamWaitEvent( ctx.stream_aux, ctx.ev_fork, 0 ) );
         CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches.p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
         ctx.stats.h2d_bytes += n_long * sizeof( Batch );
         launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, 32, long_R, 1, ctx.d_long_batches.p, (uint32_t) n_long, ctx.d_counter.p + 8,
                 ctx.d_profile_long.p, ctx.h_profile_long.p, offset );
-        CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
     }
+    if( use_aux ) CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
     // ---- bulk class ----
     if( b0 < bt.batches.size() ) {
         const size_t words = (size_t) ( R / 2 ) * 1024;
@@ -792,18 +800,12 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
         launch_packed_class( ctx.stream, q, qlen, nw, pl, G, R, npass, bt.d_batches.p + b0, (uint32_t) ( bt.batches.size() - b0 ), ctx.d_counter.p,
                 ctx.d_profile.p, ctx.h_profile.p, offset );
     }
-    if( n_long > 0 ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
+    if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
     if( wide_pairs < db.npairs ) {
         const uint32_t np = (uint32_t) ( db.npairs - wide_pairs );
         unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_out_packed.p, ctx.d_scores.p, (uint32_t) wide_pairs,
                 (uint32_t) db.npairs, (uint32_t) nloc, offset );
         ctx.stats.launches++;
-    }
-    // ---- wide tier for the pairs beyond the packed tier's range ----
-    if( wide_pairs > 0 ) {
-        std::vector<uint32_t> slots;
-        for( size_t s = 0; s < std::min( nloc, 2 * wide_pairs ); s++ ) slots.push_back( (uint32_t) s );
-        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0 );
     }
     CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
 }
@@ -937,6 +939,7 @@ void gpu_release() {
     ctx.d_out_packed.release();
     ctx.d_counter.release();
     ctx.d_bnd.release();
+    ctx.d_bnd_wide.release();
     ctx.d_scores.release();
     ctx.d_arrival_scores.release();
     ctx.d_first.release();
@@ -1073,7 +1076,7 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
             int32_t * d_f = ctx.d_first.p;  // [stride] first8 | [stride] first16
             launch_fill( d_f, INT_MAX, 2 * stride );
             Plan pl = make_plan( req.qlen );
-            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride, 1 );  // rewrites the same exact scores
+            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride, 1, ctx.stream );  // rewrites the same exact scores
             int32_t * d_f_all = d_f;
             if( world > 1 ) {
                 d_f_all = ctx.d_first.p + 2 * stride;
