@@ -9,9 +9,10 @@ D = os.path.join(ROOT, "tests/golden/data")
 qname = sys.argv[1] if len(sys.argv) > 1 else "P07327"
 mode = sys.argv[2] if len(sys.argv) > 2 else "sw"
 q0 = open(D + "/P07327").read().split("\n", 1)[1].replace("\n", "")
-path = os.path.join(tempfile.gettempdir(), "prof_S100k.fas")
+nseq = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
+path = os.path.join(tempfile.gettempdir(), "prof_S%d.fas" % nseq)
 if not os.path.exists(path):
-    synth.write_protein_db(path, 100000, 20150402, query=q0, workers=1)
+    synth.write_protein_db(path, nseq, 20150402, query=q0)
 lib = L.load()
 lib.set_output_mode(L.OUTPUT_SILENT)
 lib.init_symbol_translation(L.AMINOACID); lib.init_score_matrix(L.MATRIX_BUILDIN, "blosum62"); lib.init_gap_penalties(-11, -1)

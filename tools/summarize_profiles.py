@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""Turns the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/."""
+import collections, csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+def launches():
+    rows = [r for r in csv.reader(open(os.path.join(G, "launches_%s.csv" % tag))) if len(r) > 10]
+    hdr, data = None, []
+    for r in rows:
+        if r[0] == "ID": hdr = r; continue
+        if hdr: data.append(dict(zip(hdr, r)))
+    agg = collections.OrderedDict()
+    for d in data:
+        v = float(d["Metric Value"].replace(",", "")); u = d["Metric Unit"]
+        us = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
+        k = d["Kernel Name"]
+        a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += us
+    tot = sum(a[1] for a in agg.values())
+    out = ["# ncu launch list of `python bench.py --steps 2 --warmup 1` (%s)" % tag, "",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` on one B200; raw CSV: `profiles/launches_%s.csv`." % tag,
+           "Times under ncu are cold-cache and serialised: compare SHARES.  %d launches, %.1f ms in total." % (len(data), tot / 1e3), "",
+           "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        out.append("| `%s` | %d | %.2f | %.2f %% |" % (k.replace("|", "/"), a[0], a[1] / 1e3, 100 * a[1] / tot))
+    share = sum(a[1] for k, a in agg.items() if "score_kernel<1" in k) / tot
+    out += ["", "Packed scoring kernels (`score_kernel<1, R, ...>`): **%.1f %%** of the GPU time of a step; the wide tier (`score_kernel<0, ...>`), "
+            "arrival-order, unpack, flag, scatter and fill kernels share the rest." % (100 * share)]
+    open(os.path.join(P, "launches_%s.md" % tag), "w").write("\n".join(out) + "\n")
+    import shutil; shutil.copy(os.path.join(G, "launches_%s.csv" % tag), os.path.join(P, "launches_%s.csv" % tag))
+    return share
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio"]
+
+def kernel_report(rep, title, cells_per_launch, note):
+    raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    out = ["# %s" % title, "", note, ""]
+    res = []
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
+        out += ["## launch %s: `%s`" % (d.get("ID"), d.get("Kernel Name")), "", "| metric | value | unit |", "|---|---|---|"]
+        for w in WANT:
+            if w in d: out.append("| %s | %s | %s |" % (w, d[w], u[w]))
+        def num(k):
+            v = float(d[k].replace(",", "")); un = u[k]
+            return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}.get(un, 1)
+        t = num("gpu__time_duration.sum"); dram = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        inst = float(d["smsp__inst_executed.sum"].replace(",", ""))
+        out += ["", "derived: %.1f GCUPS under ncu (padded rows not counted), DRAM traffic %.1f MB per launch, %.2f warp instructions per packed word-row"
+                % (cells_per_launch / t / 1e9, dram / 1e6, inst / (cells_per_launch / 64.0)), ""]
+        res.append({"kernel": d.get("Kernel Name"), "seconds": t, "dram_bytes": dram, "instructions": inst})
+    open(os.path.join(P, rep.replace(".ncu-rep", ".md")), "w").write("\n".join(out) + "\n")
+    return res
+
+if __name__ == "__main__":
+    share = launches()
+    meta = json.load(open(os.path.join(G, "bench_%s.json" % tag)))
+    res_per_gpu = meta["config"]["db_residues"] / meta["n_gpus"]
+    # prof_<tag>_top: P33450 (5147 aa) vs the 500k database: one pass = 896 query rows
+    top = kernel_report("prof_%s_top.ncu-rep" % tag, "ncu --set full: dominant kernel of the benchmark step (P33450, 5147 aa, one of 6 passes of 896 rows)",
+                        res_per_gpu * 5147 / 6.0,
+                        "`ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_kernel<1, 28 -s 13 -c 2 python tools/profile_target.py P33450 sw 500000` "
+                        "(same 500 000-record database shape as bench.py; the capture follows a plain run of the same command that exited 0).")
+    json.dump({"kernel": top[-1]["kernel"], "dram_bytes_per_launch": top[-1]["dram_bytes"], "seconds_under_ncu": top[-1]["seconds"],
+               "algorithmic_cells_per_launch": res_per_gpu * 5147 / 6.0, "algorithmic_bytes_per_launch": res_per_gpu * 1.0 + 4.0 * meta["config"]["db_records"] / meta["n_gpus"],
+               "score_kernel_share_of_step": share, "source": "profiles/prof_%s_top.md" % tag}, open(os.path.join(P, "roofline_%s.json" % tag), "w"), indent=1)
+    q375 = kernel_report("prof_%s_q375.ncu-rep" % tag, "ncu --set full: bulk kernel of a 375-aa query (P07327, groups of 16 lanes x 24 rows, two columns per step)",
+                         res_per_gpu * 375, "`ncu --set full ... -k regex:score_kernel<1, 24 ... python tools/profile_target.py P07327 sw 500000`; pairs longer than the "
+                         "long-class threshold run in a separate (32 x 12) launch and are not part of this launch, so the derived GCUPS slightly overstates.")
+    print("share", share, top[-1], q375[-1])
