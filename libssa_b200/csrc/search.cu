@@ -6,6 +6,7 @@
 #include "score_launch.h"
 #include "traceback.h"
 #include "arrival.cuh"
+#include "nw_sat.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -88,6 +89,8 @@ struct PackedDb {
     std::map<uint32_t, BatchTable> batch_tables;  // keyed by columns per batch
     DevBuf<uint16_t> d_stream;
     DevBuf<uint32_t> d_lens_all;           // record lengths, provider order (for the arrival-order kernel)
+    DevBuf<uint64_t> d_pair_col;           // first stream column of every pair
+    DevBuf<uint32_t> d_sorted_len;         // record length by local sorted position
     DevBuf<int32_t> d_sorted_pos_of_id;    // provider index -> global sorted position
     struct ChunkInfo {                     // per chunk size: where each chunk's records start in arrival order
         DevBuf<uint32_t> d_chunk_base;
@@ -123,7 +126,11 @@ struct Ctx {
     DevBuf<Batch> d_wide_batches[2];
     DevBuf<uint32_t> d_profile_wide[2];
     PinBuf<uint32_t> h_profile_wide[2];
-    DevBuf<uint32_t> d_order;
+    DevBuf<uint32_t> d_order, d_wave_list;
+    DevBuf<int16_t> d_nw_scratch;
+    DevBuf<uint8_t> d_query;
+    DevBuf<int32_t> d_matrix32;
+    uint64_t matrix32_version = ~0ull;
     PinBuf<uint32_t> h_order;
     DevBuf<uint32_t> d_flag_list;
     PinBuf<uint32_t> h_profile, h_list;
@@ -282,6 +289,10 @@ void build_db() {
             CUDA_OK( cudaMemcpy( db.d_lens_all.p, lens32.data(), nall * 4, cudaMemcpyHostToDevice ) );
             CUDA_OK( cudaMemcpy( db.d_sorted_pos_of_id.p, db.sorted_pos_of_id.data(), nall * 4, cudaMemcpyHostToDevice ) );
         }
+        db.d_pair_col.reserve( db.npairs + 2 );
+        db.d_sorted_len.reserve( nloc + 2 );
+        CUDA_OK( cudaMemcpy( db.d_pair_col.p, db.pair_col.data(), ( db.npairs + 1 ) * sizeof( uint64_t ), cudaMemcpyHostToDevice ) );
+        if( nloc ) CUDA_OK( cudaMemcpy( db.d_sorted_len.p, db.sorted_len.data(), nloc * sizeof( uint32_t ), cudaMemcpyHostToDevice ) );
         for( auto & kv : db.chunk_info ) kv.second.d_chunk_base.release();
         db.chunk_info.clear();
     }
@@ -402,6 +413,17 @@ __global__ void gather_first_kernel( const uint32_t * list, uint32_t count, cons
     const uint32_t i = list[k], r = i / stride, sl = i % stride;
     out[k] = first_all[(size_t) r * 2 * stride + sl];
     out[count + k] = first_all[(size_t) r * 2 * stride + stride + sl];
+}
+
+__global__ void iota_kernel( uint32_t * p, uint32_t first, uint32_t n ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n ) p[i] = first + i;
+}
+
+// counts the entries that are not INT_MAX (records that overflow a tier)
+__global__ void count_set_kernel( const int32_t * p, uint32_t n, uint32_t * out ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n && p[i] != 0x7fffffff ) atomicAdd( out, 1u );
 }
 
 __global__ void fill_i32_kernel( int32_t * p, int32_t v, uint32_t n ) {
@@ -810,6 +832,91 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
 }
 
+// ---- order emulation of the reference's narrow NW tiers (nw_sat.cuh) ----
+
+// Longest database sequence for which the saturating `bits`-wide NW kernel of the reference provably never
+// saturates nor trips its overflow test (all of H - padded columns included -, E, F and the injected boundaries
+// stay strictly inside the tier's range), so that no emulation is needed.  -1 = none.
+int64_t nw_tier_safe_len( size_t qlen, int bits ) {
+    const int64_t LO = bits == 8 ? -128 : -32768, HI = bits == 8 ? 127 : 32767;
+    const int64_t gO = g_gapO, gE = g_gapE, QR = gO + gE;
+    if( gO > 0 || gE > 0 || QR <= LO + 2 ) return -1;
+    for( int i = 0; i < 1024; i++ )
+        if( g_matrix.m[i] < LO || g_matrix.m[i] > HI ) return -1;   // the typed copies of the matrix would wrap
+    const int64_t hip = std::max<int64_t>( g_matrix.hi, 0 ), lom = std::min<int64_t>( g_matrix.lo, 0 );
+    auto safe = [&]( int64_t d ) {
+        const int64_t d4 = ( d + 3 ) / 4 * 4;
+        const int64_t hi = hip * ( std::min<int64_t>( (int64_t) qlen, d4 ) + 1 );
+        const int64_t lo = 2 * gO + ( (int64_t) qlen + d4 + 2 ) * gE + lom + QR;
+        return hi < HI - 1 && lo > LO - QR + 2;
+    };
+    if( !safe( 1 ) ) return -1;
+    int64_t a = 1, b = 1 << 26;
+    while( a + 1 < b ) {
+        int64_t mid = ( a + b ) / 2;
+        if( safe( mid ) )
+            a = mid;
+        else
+            b = mid;
+    }
+    return a;
+}
+
+// number of leading local sorted positions (longest sequences first) whose length exceeds `len`
+size_t sorted_prefix_longer_than( int64_t len ) {
+    PackedDb & db = ctx.db;
+    size_t lo = 0, hi = db.sorted_len.size();
+    while( lo < hi ) {
+        size_t mid = ( lo + hi ) / 2;
+        if( (int64_t) db.sorted_len[mid] > len )
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// emulates the `bits`-wide saturating NW kernel for the first `count` local sorted positions; first_col[s] receives
+// 4 * (overflow block) for the records that overflow
+void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t * d_first_col ) {
+    PackedDb & db = ctx.db;
+    if( count == 0 ) return;
+    if( ctx.matrix32_version != g_matrix.version ) {
+        int32_t m32[1024];
+        for( int i = 0; i < 1024; i++ ) m32[i] = (int32_t) g_matrix.m[i];
+        ctx.d_matrix32.reserve( 1024 );
+        CUDA_OK( cudaMemcpy( ctx.d_matrix32.p, m32, sizeof( m32 ), cudaMemcpyHostToDevice ) );
+        ctx.matrix32_version = g_matrix.version;
+    }
+    ctx.d_query.reserve( qlen + 1 );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_query.p, q, qlen, cudaMemcpyHostToDevice, ctx.stream ) );
+    ctx.stats.h2d_bytes += qlen;
+    const size_t wave = std::max<size_t>( 4096, ( 256u << 20 ) / ( 4 * qlen ) );
+    ctx.d_nw_scratch.reserve( 2 * qlen * std::min( wave, count ) + 16 );
+    ctx.d_wave_list.reserve( std::min( wave, count ) + 1 );
+    for( size_t first = 0; first < count; first += wave ) {
+        const size_t n = std::min( wave, count - first );
+        iota_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_wave_list.p, (uint32_t) first, (uint32_t) n );
+        NwSatArgs a;
+        a.stream = db.d_stream.p;
+        a.pair_col = db.d_pair_col.p;
+        a.sorted_len = db.d_sorted_len.p;
+        a.list = ctx.d_wave_list.p;
+        a.count = (uint32_t) n;
+        a.query = ctx.d_query.p;
+        a.qlen = (uint32_t) qlen;
+        a.matrix = ctx.d_matrix32.p;
+        a.gap_open = g_gapO;
+        a.gap_extend = g_gapE;
+        a.bits = bits;
+        a.scratch_h = ctx.d_nw_scratch.p;
+        a.scratch_e = ctx.d_nw_scratch.p + qlen * n;
+        a.first_col = d_first_col;
+        nw_sat_kernel<<<(unsigned) ( ( n + 127 ) / 128 ), 128, 0, ctx.stream>>>( a );
+        ctx.stats.launches += 2;
+    }
+}
+
 // where each chunk of `chunk` provider records starts in arrival order (the reference stops at the first chunk
 // without a non-empty record, src/algo/16/search_16.c:123)
 PackedDb::ChunkInfo & chunk_info_for( size_t chunk ) {
@@ -927,6 +1034,8 @@ void gpu_release() {
     cudaStreamSynchronize( ctx.stream );
     ctx.db.d_stream.release();
     ctx.db.d_lens_all.release();
+    ctx.db.d_pair_col.release();
+    ctx.db.d_sorted_len.release();
     ctx.db.d_sorted_pos_of_id.release();
     for( auto & kv : ctx.db.chunk_info ) kv.second.d_chunk_base.release();
     ctx.db.chunk_info.clear();
@@ -954,6 +1063,11 @@ void gpu_release() {
         ctx.h_profile_wide[i].release();
     }
     ctx.d_order.release();
+    ctx.d_wave_list.release();
+    ctx.d_nw_scratch.release();
+    ctx.d_query.release();
+    ctx.d_matrix32.release();
+    ctx.matrix32_version = ~0ull;
     ctx.h_order.release();
     ctx.d_flag_list.release();
     ctx.h_profile.release();
@@ -1108,6 +1222,52 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         }
     }
 
+    // ---- NW entered at 8 or 16 bit: which records overflow the reference's saturating tiers, and where ----
+    // (only for the records static bounds cannot clear: usually none at 16 bit, everything at 8 bit)
+    uint32_t * d_nw_counts = nullptr;
+    if( nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+        const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 8 ) ) : 0;
+        const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 16 ) );
+        // every rank takes the same branch: whether any shard needs the emulation follows from the GLOBAL longest record
+        const int64_t longest = nglob ? (int64_t) db.lens_all[db.sorted_all[0]] : 0;
+        const bool need8 = req.bit_width == 8 && longest > nw_tier_safe_len( req.qlen, 8 );
+        const bool need16 = longest > nw_tier_safe_len( req.qlen, 16 );
+        if( need8 || need16 ) {
+            have_overflow = true;
+            ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+            int32_t * d_f = ctx.d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier
+            launch_fill( d_f, INT_MAX, 2 * stride );
+            if( n8 ) run_nw_sat( req.query, req.qlen, 8, n8, d_f );
+            if( n16 ) run_nw_sat( req.query, req.qlen, 16, n16, d_f + stride );
+            ctx.d_counter.reserve( 64 );
+            d_nw_counts = ctx.d_counter.p + 32;
+            CUDA_OK( cudaMemsetAsync( d_nw_counts, 0, 8, ctx.stream ) );
+            count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx.stream>>>( d_f, (uint32_t) stride, d_nw_counts );
+            count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx.stream>>>( d_f + stride, (uint32_t) stride, d_nw_counts + 1 );
+            ctx.stats.launches += 2;
+            d_first_gathered = d_f;
+            if( world > 1 ) {
+                int32_t * d_f_all = ctx.d_first.p + 2 * stride;
+                gather_i32( d_f, d_f_all, 2 * stride );
+                d_first_gathered = d_f_all;
+            }
+            if( !use_gpu_arrival ) {  // chunk sizes the arrival kernel does not cover: overflow blocks to the host emulation
+                ctx.h_first.reserve( 2 * stride * world + 2 );
+                CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_first_gathered, 2 * stride * world * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+                ctx.stats.d2h_bytes += 2 * stride * world * sizeof( int32_t );
+                ovf8.assign( db.lens_all.size(), -1 );
+                ovf16.assign( db.lens_all.size(), -1 );
+                for( size_t g = 0; g < nglob; g++ ) {
+                    const size_t r = g % world, sl = g / world;
+                    const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
+                    if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[db.sorted_all[g]] = c8 / 4;
+                    if( c16 != INT_MAX ) ovf16[db.sorted_all[g]] = c16 / 4;
+                }
+            }
+        }
+    }
+
     // ---- heap-arrival order of the emulated one-thread reference run ----
     const uint32_t * order = nullptr;
     size_t narr = 0;
@@ -1150,6 +1310,12 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
     }
 
+    if( d_nw_counts ) {  // records of this shard the reference would have re-aligned (NW tiers)
+        uint32_t c[2] = { 0, 0 };
+        CUDA_OK( cudaMemcpy( c, d_nw_counts, 8, cudaMemcpyDeviceToHost ) );
+        if( req.bit_width == 8 ) ctx.stats.overflow_8 = c[0];
+        ctx.stats.overflow_16 = c[1];
+    }
     for( uint32_t k = 0; k < n_flagged; k++ ) {  // valid after the synchronisation above
         if( req.bit_width == 8 && ctx.h_first.p[k] != INT_MAX ) ctx.stats.overflow_8++;
         if( ctx.h_first.p[n_flagged + k] != INT_MAX ) ctx.stats.overflow_16++;

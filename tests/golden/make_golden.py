@@ -39,7 +39,7 @@ def main():
     for name in ("blosum45", "blosum50", "blosum62", "blosum80", "blosum90", "pam30", "pam70", "pam250"):
         ref.init_score_matrix(MATRIX_BUILDIN, name)
         mats[name] = dump_matrix(ref)
-    for match, mismatch in ((1, -1), (2, -2), (5, -4), (127, -1), (30, -1)):
+    for match, mismatch in ((1, -1), (2, -2), (5, -4), (127, -1), (30, -1), (12, -4)):
         ref.init_constant_scores(match, mismatch)
         mats["const_%d_%d" % (match, mismatch)] = dump_matrix(ref)
     json.dump(mats, open(os.path.join(HERE, "matrices.json"), "w"))

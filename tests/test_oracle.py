@@ -23,7 +23,10 @@ def load_case(port, case):
     nuc = case["symtype"] == cases.NUCLEOTIDE
     recs = port.read_fasta(cases.db_path(case["db"]))
     seqs = [port.map_db(s, nuc) for _, s in recs]
-    if "query_string" in case:
+    if "query_string_fn" in case:
+        from libssa_b200 import synth
+        q = port.map_query(synth.random_nucleotide(5, 3000, iupac_rate=0.02), nuc)
+    elif "query_string" in case:
         q = port.map_query(case["query_string"], nuc)
     else:
         q = port.map_query(port.read_fasta(os.path.join(cases.DATA, case["query"]))[0][1], nuc)
