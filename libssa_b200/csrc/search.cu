@@ -7,6 +7,7 @@
 #include "traceback.h"
 #include "arrival.cuh"
 #include "nw_sat.cuh"
+#include "topk.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -90,6 +91,7 @@ struct PackedDb {
     DevBuf<uint16_t> d_stream;
     DevBuf<uint32_t> d_lens_all;           // record lengths, provider order (for the arrival-order kernel)
     DevBuf<uint64_t> d_pair_col;           // first stream column of every pair
+    DevBuf<uint32_t> d_sorted_all;         // global sorted position -> provider index
     DevBuf<uint32_t> d_sorted_len;         // record length by local sorted position
     DevBuf<int32_t> d_sorted_pos_of_id;    // provider index -> global sorted position
     struct ChunkInfo {                     // per chunk size: where each chunk's records start in arrival order
@@ -126,7 +128,12 @@ struct Ctx {
     DevBuf<Batch> d_wide_batches[2];
     DevBuf<uint32_t> d_profile_wide[2];
     PinBuf<uint32_t> h_profile_wide[2];
-    DevBuf<uint32_t> d_order, d_wave_list;
+    DevBuf<uint32_t> d_order, d_wave_list, d_topk_ids;
+    DevBuf<int32_t> d_topk_scores;
+    DevBuf<SelectState> d_select;
+    PinBuf<SelectState> h_select;
+    PinBuf<uint32_t> h_topk_ids;
+    PinBuf<int32_t> h_topk_scores;
     DevBuf<int16_t> d_nw_scratch;
     DevBuf<uint8_t> d_query;
     DevBuf<int32_t> d_matrix32;
@@ -289,6 +296,8 @@ void build_db() {
             CUDA_OK( cudaMemcpy( db.d_lens_all.p, lens32.data(), nall * 4, cudaMemcpyHostToDevice ) );
             CUDA_OK( cudaMemcpy( db.d_sorted_pos_of_id.p, db.sorted_pos_of_id.data(), nall * 4, cudaMemcpyHostToDevice ) );
         }
+        db.d_sorted_all.reserve( sorted.size() + 1 );
+        if( !sorted.empty() ) CUDA_OK( cudaMemcpy( db.d_sorted_all.p, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice ) );
         db.d_pair_col.reserve( db.npairs + 2 );
         db.d_sorted_len.reserve( nloc + 2 );
         CUDA_OK( cudaMemcpy( db.d_pair_col.p, db.pair_col.data(), ( db.npairs + 1 ) * sizeof( uint64_t ), cudaMemcpyHostToDevice ) );
@@ -418,6 +427,16 @@ __global__ void gather_first_kernel( const uint32_t * list, uint32_t count, cons
 __global__ void iota_kernel( uint32_t * p, uint32_t first, uint32_t n ) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if( i < n ) p[i] = first + i;
+}
+
+// records scoring >= thr8 / >= thr16 over the gathered score vector (the reference's overflow counters)
+__global__ void count_ge_kernel( const int32_t * gathered, uint32_t stride, uint32_t world, uint32_t nglobal, int32_t thr8, int32_t thr16, uint32_t * out ) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= stride * world ) return;
+    uint32_t r = i / stride, sl = i % stride;
+    if( (uint64_t) sl * world + r >= nglobal ) return;
+    if( gathered[i] >= thr8 ) atomicAdd( out, 1u );
+    if( gathered[i] >= thr16 ) atomicAdd( out + 1, 1u );
 }
 
 // counts the entries that are not INT_MAX (records that overflow a tier)
@@ -1035,6 +1054,7 @@ void gpu_release() {
     ctx.db.d_stream.release();
     ctx.db.d_lens_all.release();
     ctx.db.d_pair_col.release();
+    ctx.db.d_sorted_all.release();
     ctx.db.d_sorted_len.release();
     ctx.db.d_sorted_pos_of_id.release();
     for( auto & kv : ctx.db.chunk_info ) kv.second.d_chunk_base.release();
@@ -1063,6 +1083,12 @@ void gpu_release() {
         ctx.h_profile_wide[i].release();
     }
     ctx.d_order.release();
+    ctx.d_topk_ids.release();
+    ctx.d_topk_scores.release();
+    ctx.d_select.release();
+    ctx.h_select.release();
+    ctx.h_topk_ids.release();
+    ctx.h_topk_scores.release();
     ctx.d_wave_list.release();
     ctx.d_nw_scratch.release();
     ctx.d_query.release();
@@ -1152,16 +1178,73 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         d_all = ctx.d_gathered.p;
     }
 
+    const bool use_gpu_arrival = g_chunk_size <= (size_t) ARRIVAL_MAX_CHUNK;
+
+    // ---- top-k on the device ----
+    // Radix-select the k-th largest score T and count the ties at T (topk.cuh).  If no more than k records score
+    // >= T the reported set is {score >= T} whatever the arrival order, so the k hits are compacted on the device
+    // and nothing else crosses PCIe.  Only when the tie at T straddles the cut-off does the reference's tie
+    // behaviour matter; then the arrival-order replay below runs.
+    bool fast_done = false;
+    std::vector<Hit> hits;
+    {
+        PackedDb::Arrival & base = arrival_for( req.bit_width, g_chunk_size, use_gpu_arrival );  // validity: records the reference reaches
+        const size_t n_valid = base.order.size();
+        const size_t k = req.hitcount;
+        if( k > 0 && k < n_valid && nglob > 0 ) {
+            ctx.d_select.reserve( 1 );
+            ctx.h_select.reserve( 1 );
+            SelectArgs sa;
+            sa.scores = d_all;
+            sa.pos = base.d_pos_of_sorted.p;
+            sa.stride = (uint32_t) stride;
+            sa.world = (uint32_t) world;
+            sa.nglobal = (uint32_t) nglob;
+            sa.state = ctx.d_select.p;
+            const uint32_t total = (uint32_t) ( stride * world );
+            const unsigned grid = std::min<unsigned>( ( total + 255 ) / 256, 148 * 8 );
+            select_init_kernel<<<1, 256, 0, ctx.stream>>>( ctx.d_select.p, (uint32_t) k );
+            const int shifts[3] = { 21, 10, 0 };
+            const uint32_t masks[3] = { 0x7ff, 0x7ff, 0x3ff };
+            for( int p = 0; p < 3; p++ ) {
+                select_hist_kernel<<<grid, 256, 0, ctx.stream>>>( sa, shifts[p], masks[p] );
+                select_pick_kernel<<<1, 1024, 0, ctx.stream>>>( ctx.d_select.p, shifts[p], masks[p], p == 2 );
+            }
+            ctx.d_topk_scores.reserve( k + 1 );
+            ctx.d_topk_ids.reserve( k + 1 );
+            select_compact_kernel<<<grid, 256, 0, ctx.stream>>>( sa, db.d_sorted_all.p, ctx.d_topk_scores.p, ctx.d_topk_ids.p, (uint32_t) k );
+            ctx.stats.launches += 8;
+            ctx.h_topk_scores.reserve( k + 1 );
+            ctx.h_topk_ids.reserve( k + 1 );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_select.p, ctx.d_select.p, 32, cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_topk_scores.p, ctx.d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaMemcpyAsync( ctx.h_topk_ids.p, ctx.d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            ctx.stats.d2h_bytes += 32 + k * 8;
+            const SelectState & st = *ctx.h_select.p;
+            if( (size_t) st.count_gt + st.count_eq <= k ) {  // no tie straddles the cut-off: the set is order-independent
+                const size_t n = (size_t) st.count_gt + st.count_eq;
+                hits.resize( n );
+                for( size_t i = 0; i < n; i++ ) hits[i] = Hit{ ctx.h_topk_ids.p[i], ctx.h_topk_scores.p[i] };
+                std::sort( hits.begin(), hits.end(), []( const Hit & x, const Hit & y ) {
+                    if( x.score != y.score ) return x.score > y.score;
+                    return x.db_id > y.db_id;
+                } );
+                fast_done = true;
+            }
+        }
+    }
+
     // ---- which records would the reference have pushed through its overflow cascade? (SW only) ----
     // A record overflows the 8-bit tier when its score reaches 255 and the 16-bit tier at 65535
     // (reference src/algo/simd/search_simd_sw.c:372-379,422-423); it then leaves its SIMD channel after the 4-column
     // block in which the running maximum got there, which changes the order in which scores reach the heap.
     std::vector<int64_t> ovf8, ovf16;
     bool have_overflow = false;
-    const bool use_gpu_arrival = g_chunk_size <= (size_t) ARRIVAL_MAX_CHUNK;
     const int32_t * d_first_gathered = nullptr;
     uint32_t n_flagged = 0;
-    if( !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+    if( !fast_done && !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const int32_t thr = req.bit_width == 8 ? 255 : 65535;
         const uint32_t total = (uint32_t) ( stride * world );
         ctx.d_flag_list.reserve( total + 2 );
@@ -1225,7 +1308,7 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     // ---- NW entered at 8 or 16 bit: which records overflow the reference's saturating tiers, and where ----
     // (only for the records static bounds cannot clear: usually none at 16 bit, everything at 8 bit)
     uint32_t * d_nw_counts = nullptr;
-    if( nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+    if( !fast_done && nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 8 ) ) : 0;
         const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 16 ) );
         // every rank takes the same branch: whether any shard needs the emulation follows from the GLOBAL longest record
@@ -1272,7 +1355,10 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     const uint32_t * order = nullptr;
     size_t narr = 0;
     DevBuf<int32_t> * d_pos = nullptr;
-    if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
+    if( fast_done ) {
+        // nothing to replay
+    }
+    else if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
         PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size, use_gpu_arrival );
         order = ar.order.data();
         narr = ar.order.size();
@@ -1291,8 +1377,22 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         narr = ctx.order_tmp.size();
         d_pos = &ctx.d_pos_tmp;
     }
-    std::vector<Hit> hits;
-    if( narr > 0 && nglob > 0 ) {
+    if( fast_done ) {
+        if( !nw && ( req.bit_width == 8 || req.bit_width == 16 ) ) {  // the reference's overflow counters (informational)
+            ctx.d_counter.reserve( 64 );
+            uint32_t * d_c = ctx.d_counter.p + 40;
+            CUDA_OK( cudaMemsetAsync( d_c, 0, 8, ctx.stream ) );
+            const uint32_t total = (uint32_t) ( stride * world );
+            count_ge_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world, (uint32_t) nglob, 255, 65535, d_c );
+            ctx.stats.launches++;
+            uint32_t c[2];
+            CUDA_OK( cudaMemcpyAsync( c, d_c, 8, cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            if( req.bit_width == 8 ) ctx.stats.overflow_8 = c[0];
+            ctx.stats.overflow_16 = c[1];
+        }
+    }
+    else if( narr > 0 && nglob > 0 ) {
         ctx.d_arrival_scores.reserve( narr + 1 );
         const uint32_t total = (uint32_t) ( stride * world );
         scatter_arrival_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, d_pos->p, ctx.d_arrival_scores.p,
