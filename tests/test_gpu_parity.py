@@ -198,3 +198,13 @@ def test_full_size_properties(prod, port, big_db, tmp_path):
     _, sw2 = prod.score_all(q, False)
     assert (sw2 == sw[perm]).all()
     prod.free_sequence(q)
+
+
+def test_zz_exit_and_reinitialise(prod):
+    """ssa_exit() releases matrices, database and all device state (reference src/libssa.c:266-271); a later search must
+    rebuild everything from scratch and give the same result"""
+    case = SEARCHES[0]["case"]
+    before = cases.run_case(prod, case)
+    prod.ssa_exit()
+    after = cases.run_case(prod, case)
+    assert before == after == SEARCHES[0]["result"]
