@@ -208,3 +208,23 @@ def test_zz_exit_and_reinitialise(prod):
     prod.ssa_exit()
     after = cases.run_case(prod, case)
     assert before == after == SEARCHES[0]["result"]
+
+
+def test_c_host_program_drop_in(prod, tmp_path):
+    """A C program that includes only libssa.h, linked against libssa_b200.so, prints the hit list the Python mirror returns"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    db = cases.db_path(["protein", 2000, 11, "P07327"])
+    qf = os.path.join(cases.DATA, "P07327")
+    for mode, bw, align in (("sw", 16, "align"), ("nw", 8, "score")):
+        out = subprocess.run([os.path.join(root, "examples", "search_example"), db, qf, mode, str(bw), "7", align],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        got = [l.split("\t") for l in out.stdout.strip().split("\n") if l and not l.startswith("libssa")]
+        case = {"symtype": cases.AMINOACID, "scoring": "blosum62", "gaps": [-11, -1], "db": ["protein", 2000, 11, "P07327"], "query": "P07327",
+                "runs": [[mode, bw, 7, 1 if align == "align" else 0]]}
+        exp = cases.run_case(prod, case)[0]
+        assert [(int(g[0]), int(g[1])) for g in got] == [(e[0], e[1]) for e in exp]
+        if align == "align":
+            assert [g[4] for g in got] == [e[2] for e in exp]
