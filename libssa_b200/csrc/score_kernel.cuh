@@ -103,6 +103,12 @@ __device__ __forceinline__ uint32_t lds32( uint32_t addr ) {
     return v;
 }
 
+__device__ __forceinline__ uint2 lds64( uint32_t addr ) {
+    uint2 v;
+    asm volatile( "ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"( v.x ), "=r"( v.y ) : "r"( addr ) );
+    return v;
+}
+
 // words of shared memory the profile of one pass needs
 template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() { return PACKED ? ( R / 2 ) * 1024 : R * 1024; }
 
@@ -132,7 +138,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     const unsigned group_mask = ( G == 32 ? FULL : ( ( 1u << G ) - 1u ) << ( lane & ~gmask ) );
     const bool is_top = gl == 0;
     const bool is_bottom = gl == gmask;
-    const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * 4;
+    // packed tier: 64-bit entries [row quad][residue][lane] = two (row pair) words; wide tier: 32-bit entries [row][residue][lane]
+    const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * ( PACKED ? 8 : 4 );
     const T QR = (T) a.qr_word;   // gapO + gapE, replicated per half for the packed tier
     const T RG = (T) a.rg_word;   // gapE
     const int row0 = a.rowbase + gl * R;
@@ -168,29 +175,30 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         T hd = diag;
         diag = h_in;
         if( PACKED ) {
-            const uint32_t pa = prof_base + ( ( ci & 31u ) << 7 );
-            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 7 );
-            uint32_t la = lds32( pa ), lb = lds32( pb );
-            T tc = A::add( hd, (T) __byte_perm( lb, la, 0x5410 ) );
+            const uint32_t pa = prof_base + ( ( ci & 31u ) << 8 );
+            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 8 );
+            T hd2 = hd;
 #pragma unroll
-            for( int k = 0; k < R / 2; k++ ) {
-                const T t0 = tc;
-                const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
-                if( k + 1 < R / 2 ) {
-                    la = lds32( pa + ( k + 1 ) * 4096 );
-                    lb = lds32( pb + ( k + 1 ) * 4096 );
-                    tc = A::add( Hp[2 * k + 1], (T) __byte_perm( lb, la, 0x5410 ) );
+            for( int k2 = 0; k2 < R / 4; k2++ ) {
+                const uint2 la2 = lds64( pa + k2 * 8192 ), lb2 = lds64( pb + k2 * 8192 );
+#pragma unroll
+                for( int j = 0; j < 2; j++ ) {
+                    const int k = 2 * k2 + j;
+                    const uint32_t la = j ? la2.y : la2.x, lb = j ? lb2.y : lb2.x;
+                    const T t0 = A::add( hd2, (T) __byte_perm( lb, la, 0x5410 ) );
+                    const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
+                    hd2 = Hp[2 * k + 1];
+                    T hq;
+                    Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                    hq = A::add( Hp[2 * k], QR );
+                    E[2 * k] = A::addmax( E[2 * k], RG, hq );
+                    f = A::addmax( f, RG, hq );
+                    Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                    hq = A::add( Hp[2 * k + 1], QR );
+                    E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
+                    f = A::addmax( f, RG, hq );
+                    S = A::max3( S, t0, t1 );
                 }
-                T hq;
-                Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
-                hq = A::add( Hp[2 * k], QR );
-                E[2 * k] = A::addmax( E[2 * k], RG, hq );
-                f = A::addmax( f, RG, hq );
-                Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
-                hq = A::add( Hp[2 * k + 1], QR );
-                E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
-                f = A::addmax( f, RG, hq );
-                S = A::max3( S, t0, t1 );
             }
         }
         else {
@@ -375,56 +383,60 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // needs neither, so the two F chains overlap.  The diagonal candidate of the NEXT row of column A
                 // (old H + substitution score) is formed before that row's H register is overwritten, so every H
                 // stays in one physical register across steps.
-                const uint32_t paa = prof_base + ( ( cia & 31u ) << 7 );
-                const uint32_t pba = prof_base + ( ( ( cia >> 5 ) & 31u ) << 7 );
-                const uint32_t pab = prof_base + ( ( cib & 31u ) << 7 );
-                const uint32_t pbb = prof_base + ( ( ( cib >> 5 ) & 31u ) << 7 );
+                const uint32_t paa = prof_base + ( ( cia & 31u ) << 8 );
+                const uint32_t pba = prof_base + ( ( ( cia >> 5 ) & 31u ) << 8 );
+                const uint32_t pab = prof_base + ( ( cib & 31u ) << 8 );
+                const uint32_t pbb = prof_base + ( ( ( cib >> 5 ) & 31u ) << 8 );
                 T fa = fa_in, fb = fb_in;
                 T ha_prev = ha_in;                       // H of column A, previous row (diagonal of column B)
-                uint32_t laa = lds32( paa ), lba = lds32( pba );
-                T tca = A::add( diag, (T) __byte_perm( lba, laa, 0x5410 ) );
+                T hda = diag;                            // H of column A-1, previous row (diagonal of column A)
                 diag = hb_in;
 #pragma unroll
-                for( int k = 0; k < R / 2; k++ ) {
-                    const uint32_t lab = lds32( pab + k * 4096 ), lbb = lds32( pbb + k * 4096 );
-                    const T ta0 = tca;
-                    const T ta1 = A::add( Hp[2 * k], (T) __byte_perm( lba, laa, 0x7632 ) );
-                    if( k + 1 < R / 2 ) {
-                        laa = lds32( paa + ( k + 1 ) * 4096 );
-                        lba = lds32( pba + ( k + 1 ) * 4096 );
-                        tca = A::add( Hp[2 * k + 1], (T) __byte_perm( lba, laa, 0x5410 ) );
+                for( int k2 = 0; k2 < R / 4; k2++ ) {
+                    // one 64-bit shared load per sequence and column fetches the scores of four query rows
+                    const uint2 laa2 = lds64( paa + k2 * 8192 ), lba2 = lds64( pba + k2 * 8192 );
+                    const uint2 lab2 = lds64( pab + k2 * 8192 ), lbb2 = lds64( pbb + k2 * 8192 );
+#pragma unroll
+                    for( int j = 0; j < 2; j++ ) {
+                        const int k = 2 * k2 + j;
+                        const uint32_t laa = j ? laa2.y : laa2.x, lba = j ? lba2.y : lba2.x;
+                        const uint32_t lab = j ? lab2.y : lab2.x, lbb = j ? lbb2.y : lbb2.x;
+                        // diagonal candidates of column A are formed from the OLD H registers before they are overwritten
+                        const T ta0 = A::add( hda, (T) __byte_perm( lba, laa, 0x5410 ) );
+                        const T ta1 = A::add( Hp[2 * k], (T) __byte_perm( lba, laa, 0x7632 ) );
+                        hda = Hp[2 * k + 1];
+                        T hq;
+                        // column A, row 2k
+                        const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
+                        hq = A::add( ha0, QR );
+                        const T ea0 = A::addmax( E[2 * k], RG, hq );
+                        fa = A::addmax( fa, RG, hq );
+                        // column B, row 2k
+                        const T tb0 = A::add( ha_prev, (T) __byte_perm( lbb, lab, 0x5410 ) );
+                        Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
+                        hq = A::add( Hp[2 * k], QR );
+                        E[2 * k] = A::addmax( ea0, RG, hq );
+                        fb = A::addmax( fb, RG, hq );
+                        // column A, row 2k+1
+                        const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
+                        hq = A::add( ha1, QR );
+                        const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
+                        fa = A::addmax( fa, RG, hq );
+                        // column B, row 2k+1
+                        const T tb1 = A::add( ha0, (T) __byte_perm( lbb, lab, 0x7632 ) );
+                        Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
+                        hq = A::add( Hp[2 * k + 1], QR );
+                        E[2 * k + 1] = A::addmax( ea1, RG, hq );
+                        fb = A::addmax( fb, RG, hq );
+                        ha_prev = ha1;
+                        // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
+                        // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
+                        // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
+                        // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
+                        // as an upper range guard.
+                        S = A::max3( S, ta0, ta1 );
+                        S = A::max3( S, tb0, tb1 );
                     }
-                    T hq;
-                    // column A, row 2k
-                    const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
-                    hq = A::add( ha0, QR );
-                    const T ea0 = A::addmax( E[2 * k], RG, hq );
-                    fa = A::addmax( fa, RG, hq );
-                    // column B, row 2k
-                    const T tb0 = A::add( ha_prev, (T) __byte_perm( lbb, lab, 0x5410 ) );
-                    Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
-                    hq = A::add( Hp[2 * k], QR );
-                    E[2 * k] = A::addmax( ea0, RG, hq );
-                    fb = A::addmax( fb, RG, hq );
-                    // column A, row 2k+1
-                    const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
-                    hq = A::add( ha1, QR );
-                    const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
-                    fa = A::addmax( fa, RG, hq );
-                    // column B, row 2k+1
-                    const T tb1 = A::add( ha0, (T) __byte_perm( lbb, lab, 0x7632 ) );
-                    Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
-                    hq = A::add( Hp[2 * k + 1], QR );
-                    E[2 * k + 1] = A::addmax( ea1, RG, hq );
-                    fb = A::addmax( fb, RG, hq );
-                    ha_prev = ha1;
-                    // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
-                    // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
-                    // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
-                    // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
-                    // as an upper range guard.
-                    S = A::max3( S, ta0, ta1 );
-                    S = A::max3( S, tb0, tb1 );
                 }
                 ha_last = ha_prev;
                 fa_last = fa;

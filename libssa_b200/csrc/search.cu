@@ -505,8 +505,8 @@ Plan make_plan( size_t qlen ) {
     return pl;
 }
 
-// Packed profile of pass `pass`: word [(k*32 + d)*32 + lane] = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as int16, the
-// rows counted from (pass*G + (lane mod G)) * R.  All 32 lanes have their own copy (groups repeat), so a warp-wide
+// Packed profile of pass `pass`: one word per (row pair k, residue d, lane) = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as
+// int16, two consecutive row pairs forming one 64-bit shared-memory entry; rows counted from (pass*G + (lane mod G)) * R.  All 32 lanes have their own copy (groups repeat), so a warp-wide
 // lookup is bank-conflict free whatever residues the lanes hold.  Rows beyond the query get pad_score.
 void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
     const int R = pl.R, G = pl.G;
@@ -516,7 +516,9 @@ void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const 
                 size_t r0 = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R + 2 * k;
                 int v0 = r0 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0]] : pl.pad_score;
                 int v1 = r0 + 1 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0 + 1]] : pl.pad_score;
-                out[( k * 32 + d ) * 32 + lane] = ( (uint32_t) (uint16_t) (int16_t) v1 << 16 ) | (uint32_t) (uint16_t) (int16_t) v0;
+                // 64-bit entries [row quad k/2][residue][lane]; word k%2 of an entry = rows 2k (low half), 2k+1 (high half)
+                out[( ( ( k / 2 ) * 32 + d ) * 32 + lane ) * 2 + ( k & 1 )] =
+                        ( (uint32_t) (uint16_t) (int16_t) v1 << 16 ) | (uint32_t) (uint16_t) (int16_t) v0;
             }
 }
 
