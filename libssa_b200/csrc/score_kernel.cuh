@@ -3,26 +3,29 @@
 // (src/algo/simd/search_simd_{sw,nw}.c), its profile transposition (src/algo/{8,16}/search_*_util.c),
 // the scalar 64-bit tier (src/algo/64/*.c) and the chunk loop around them.
 //
-// Decomposition (one warp = one systolic array):
-//   * lane l of a warp owns R consecutive query rows [rowbase + l*R, rowbase + (l+1)*R); their H (previous
-//     column) and E state live in registers for the whole launch;
-//   * database columns stream through the lanes: at step t lane l works on column t-l and hands the H and F
-//     of its last row (plus the column's residues) to lane l+1 with __shfl_up_sync - the anti-diagonal
-//     wavefront, one shuffle hop per step;
+// Decomposition:
+//   * a warp is split into 32/G independent systolic arrays of G lanes (G = 4..32, chosen per query); lane l of an
+//     array owns R consecutive query rows [rowbase + l*R, rowbase + (l+1)*R) whose H (previous column) and E state
+//     live in registers for the whole launch;
+//   * database columns stream through the lanes, TWO per step: at step t lane l works on column pair t-l and hands
+//     the H and F of its last row (both columns) to lane l+1 with __shfl_up_sync - the anti-diagonal wavefront, one
+//     shuffle hop per step; the two columns' F chains are independent, which doubles the instruction-level
+//     parallelism of the otherwise serial row loop;
 //   * the columns of MANY database sequences are concatenated into one stream per work batch; flag bits in the
 //     stream mark first/last columns, where a lane resets its state / reports its result.  The wavefront
-//     therefore fills and drains once per batch (31 steps per >= 4096 columns), not once per sequence;
-//   * PACKED tier: every 32-bit register holds the same DP cell of TWO database sequences (A in the high, B in
-//     the low 16 bits): inter-sequence SIMD-in-word.  All arithmetic is one SASS instruction per packed word:
+//     therefore fills and drains once per batch (G-1 steps per >= 256 columns), not once per sequence.  Every lane
+//     reads the 32-bit word of ITS column pair straight from the stream, prefetched two steps ahead;
+//   * PACKED tier: every 32-bit register holds the same DP cell of TWO database sequences (A in the high, B in the
+//     low 16 bits): inter-sequence SIMD-in-word.  All arithmetic is one SASS instruction per packed word:
 //     VIADD.16x2 (FMA-side pipe), VIMNMX3.S16x2[.RELU] and VIADDMNMX.S16x2 (ALU pipe, DPX);
-//   * substitution scores come from a query profile in shared memory laid out [row pair][residue][lane], so a
-//     warp-wide lookup is bank-conflict free whatever residues the lanes hold: two LDS fetch the scores of two
-//     query rows for sequence A resp. B, two PRMT interleave them into the (A:B) words of the two rows;
+//   * substitution scores come from a query profile in shared memory laid out [row quad][residue][lane] (64-bit
+//     entries), so a warp-wide lookup is bank-conflict free whatever residues the lanes hold: one LDS.64 fetches the
+//     scores of four query rows for sequence A resp. B, PRMT interleaves them into the (A:B) words of the rows;
 //   * WIDE tier (PACKED=false): the same systolic array on plain int32 for the (rare) sequences whose scores
 //     cannot be guaranteed to fit 16 bits - the counterpart of the reference's 16->64 bit overflow cascade.
 //     Optionally tracks the first column whose running maximum reaches 255 / 65535, which is what the
 //     reference's 8/16-bit tiers would have overflowed at (needed to reproduce its hit order, replay.cpp);
-//   * queries longer than 32*R rows are processed in passes; the H/F of the last row of a pass is written to a
+//   * queries longer than G*R rows are processed in passes; the H/F of the last row of a pass is written to a
 //     boundary buffer in global memory and read back by lane 0 of the next pass.
 #pragma once
 
