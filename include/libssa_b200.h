@@ -83,6 +83,17 @@ size_t ssa_b200_host_arrival_order( const uint64_t * lens, size_t n, size_t chun
 size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
         uint64_t * ids_out, int64_t * scores_out );
 size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out );
+/*
+ * Hit selection of a search over several query frames and/or several database entries per record (both strands,
+ * translated searches): the reference's per-chunk schedule  frames x entries -> overflow lists re-run under every
+ * frame  (src/algo/8/search_8.c:94-124, src/algo/16/search_16.c:92-113, src/algo/64/search_64.c:44-56), the bounded
+ * heaps and both final sorts.  slot_lens[nslots]: entry lengths in provider order, buffer_max entries per record
+ * (0 = skipped); scores / ovf8 / ovf16 are [q_count][nslots] (ovf: overflow block of the entry under that frame in
+ * the 8- resp. 16-bit tier, -1 = none; may be NULL).  Returns the number of hits written.
+ */
+size_t ssa_b200_host_frames_replay( const uint64_t * slot_lens, size_t nslots, size_t chunk_slots, int bit_width, int q_count,
+        int buffer_max, const int32_t * scores, const int32_t * ovf8, const int32_t * ovf16, size_t hitcount,
+        uint32_t * slots_out, uint8_t * frames_out, int64_t * scores_out );
 
 /* copies the current 32x32 score table (index (db_symbol << 5) + query_symbol); 0 if scoring is not initialised */
 int ssa_b200_get_score_matrix( int64_t * out_1024 );

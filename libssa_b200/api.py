@@ -68,7 +68,7 @@ class Stats(C.Structure):
 class Hit:
     """Python copy of one alignment_t of the result list."""
     __slots__ = ("score", "db_id", "db_len", "db_seq", "q_len", "cigar", "cigar_len",
-                 "q_start", "q_end", "d_start", "d_end")
+                 "q_start", "q_end", "d_start", "d_end", "db_strand", "db_frame", "q_strand", "q_frame")
 
     def __repr__(self):
         return "Hit(score=%d, id=%d, cigar=%r, q=%d-%d, d=%d-%d)" % (
@@ -151,6 +151,8 @@ class LibSSA:
             h.cigar_len = a.alignment_len
             h.q_start, h.q_end = a.align_q_start, a.align_q_end
             h.d_start, h.d_end = a.align_d_start, a.align_d_end
+            h.db_strand, h.db_frame = a.db_seq.strand, a.db_seq.frame
+            h.q_strand, h.q_frame = a.query.strand, a.query.frame
             hits.append(h)
         self.lib.free_alignment(plist)
         return hits
@@ -219,6 +221,26 @@ class LibSSA:
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
         n = f(sc.ctypes.data, order.ctypes.data, len(order), hitcount, ids.ctypes.data, out.ctypes.data)
         return [(int(out[i]), int(ids[i])) for i in range(n)]
+
+    def host_frames_replay(self, slot_lens, chunk_slots, bit_width, buffer_max, scores, hitcount, ovf8=None, ovf16=None):
+        """Hit list [(score, slot, frame)] of a multi-frame search; scores/ovf8/ovf16 are [q_count][nslots]."""
+        import numpy as np
+        lens = np.ascontiguousarray(slot_lens, dtype=np.uint64)
+        sc = np.ascontiguousarray(scores, dtype=np.int32)
+        q_count, nslots = sc.shape
+        o8 = None if ovf8 is None else np.ascontiguousarray(ovf8, dtype=np.int32)
+        o16 = None if ovf16 is None else np.ascontiguousarray(ovf16, dtype=np.int32)
+        slots = np.zeros(max(hitcount, 1), dtype=np.uint32)
+        frames = np.zeros(max(hitcount, 1), dtype=np.uint8)
+        out = np.zeros(max(hitcount, 1), dtype=np.int64)
+        f = self.lib.ssa_b200_host_frames_replay
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                      C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = f(lens.ctypes.data, nslots, chunk_slots, bit_width, q_count, buffer_max, sc.ctypes.data,
+              None if o8 is None else o8.ctypes.data, None if o16 is None else o16.ctypes.data, hitcount,
+              slots.ctypes.data, frames.ctypes.data, out.ctypes.data)
+        return [(int(out[i]), int(slots[i]), int(frames[i])) for i in range(n)]
 
     def host_sorted_order(self, lens):
         import numpy as np

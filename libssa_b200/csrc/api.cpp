@@ -66,6 +66,7 @@ API void init_symbol_translation( int type, int strands, int d_gencode, int q_ge
     if( strands < 1 || strands > 3 ) fatal( "Illegal strands specified." );
     g_symtype = type;
     g_query_strands = strands;
+    init_translation_tables( q_gencode, d_gencode );  // reference src/libssa.c:156
     g_db_epoch++;
 }
 
@@ -86,18 +87,27 @@ static void test_configuration( p_query query ) {  // reference src/libssa.c:196
         fatal( "Nucleotide sequences can only be aligned using constant scores." );
 }
 
-// The query frames a search runs over (reference src/algo/searcher.c:42-90).  Only the un-translated
-// modes are served by the GPU path so far, i.e. exactly one frame.
-static sequence_t query_frame( p_query query, int * strand, int * frame ) {
-    *strand = 0;
-    *frame = 0;
+// The query frames a search runs over (reference src/algo/searcher.c:42-90).
+static std::vector<QueryFrame> query_frames( p_query query ) {
+    std::vector<QueryFrame> frames;
+    auto add = [&]( const sequence_t & s, int strand, int frame ) {
+        frames.push_back( QueryFrame{ (const uint8_t *) s.seq, s.len, strand, frame } );
+    };
     if( g_symtype == NUCLEOTIDE ) {
-        if( g_query_strands != FORWARD_STRAND )
-            fatal( "Nucleotide searches on the complementary strand are not available in the GPU library yet." );
-        return query->nt[0];
+        for( int s = 0; s < 2; s++ )
+            if( ( s + 1 ) & g_query_strands ) add( query->nt[s], s, 0 );
     }
-    if( g_symtype == AMINOACID ) return query->aa[0];
-    fatal( "Translated searches (TRANS_QUERY/TRANS_DB/TRANS_BOTH) are not available in the GPU library yet." );
+    else if( g_symtype == AMINOACID || g_symtype == TRANS_DB ) {
+        add( query->aa[0], 0, 0 );
+    }
+    else {
+        for( int s = 0; s < 2; s++ )
+            if( ( s + 1 ) & g_query_strands )
+                for( int f = 0; f < 3; f++ ) add( query->aa[3 * s + f], s, f );
+    }
+    for( const QueryFrame & f : frames )
+        if( !f.seq ) fatal( "Query was not read with the current symbol type / strands (re-read it after init_symbol_translation)." );
+    return frames;
 }
 
 static p_alignment_list run_search( p_query query, size_t hitcount, int bit_width, int align_type, int search_type ) {
@@ -106,9 +116,7 @@ static p_alignment_list run_search( p_query query, size_t hitcount, int bit_widt
         fatal( "\nunknown bit width provided: %d\n\n", bit_width );  // reference src/algo/searcher.c:115-117
 
     SearchRequest req;
-    sequence_t q = query_frame( query, &req.q_strand, &req.q_frame );
-    req.query = (const uint8_t *) q.seq;
-    req.qlen = q.len;
+    req.frames = query_frames( query );
     req.search_type = search_type;
     req.bit_width = bit_width;
     req.hitcount = hitcount;
@@ -123,18 +131,19 @@ static p_alignment_list run_search( p_query query, size_t hitcount, int bit_widt
     alist->alignments = (p_alignment *) xmalloc( ( hits.size() ? hits.size() : 1 ) * sizeof( p_alignment ) );
     for( size_t i = 0; i < hits.size(); i++ ) {
         const HitAlignment & h = hits[i];
+        const QueryFrame & qf = req.frames[h.query_id];
         p_alignment a = (p_alignment) xmalloc( sizeof( alignment_t ) );
         a->db_seq.seq = (char *) xmalloc( h.db_codes.size() + 1 );
         memcpy( a->db_seq.seq, h.db_codes.data(), h.db_codes.size() );
         a->db_seq.seq[h.db_codes.size()] = 0;
         a->db_seq.len = h.db_codes.size();
         a->db_seq.ID = h.hit.db_id;
-        a->db_seq.strand = 0;
-        a->db_seq.frame = 0;
-        a->query.seq = q.seq;  // borrowed, not freed by free_alignment (aligner.c:80,118)
-        a->query.len = q.len;
-        a->query.strand = req.q_strand;
-        a->query.frame = req.q_frame;
+        a->db_seq.strand = h.db_frame;   // the reference fills these two swapped (src/algo/aligner.c:76-77)
+        a->db_seq.frame = h.db_strand;
+        a->query.seq = (char *) qf.seq;  // borrowed, not freed by free_alignment (aligner.c:80,118)
+        a->query.len = qf.len;
+        a->query.strand = qf.strand;
+        a->query.frame = qf.frame;
         a->score = (long) h.hit.score;
         a->alignment = nullptr;
         a->alignment_len = 0;  // left uninitialised by the reference for COMPUTE_SCORE; we define it as 0
@@ -185,9 +194,8 @@ API void ssa_exit( void ) {  // reference src/libssa.c:266-271
 
 API size_t ssa_b200_score_all( p_query query, int nw, int64_t * scores, uint64_t * ids ) {
     test_configuration( query );
-    int strand, frame;
-    sequence_t q = query_frame( query, &strand, &frame );
-    return gpu_score_all( (const uint8_t *) q.seq, q.len, nw ? NEEDLEMAN_WUNSCH : SMITH_WATERMAN, scores, ids );
+    std::vector<QueryFrame> frames = query_frames( query );
+    return gpu_score_all( frames[0].seq, frames[0].len, nw ? NEEDLEMAN_WUNSCH : SMITH_WATERMAN, scores, ids );
 }
 
 // ---- host-only helpers of the hit selection (no GPU needed): used by the multi-process merge and its CPU tests ----
@@ -206,6 +214,26 @@ API size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const 
     replay_topk( scores_in_arrival_order, order, n, hitcount, hits );
     for( size_t i = 0; i < hits.size(); i++ ) {
         ids_out[i] = hits[i].db_id;
+        scores_out[i] = hits[i].score;
+    }
+    return hits.size();
+}
+
+API size_t ssa_b200_host_frames_replay( const uint64_t * slot_lens, size_t nslots, size_t chunk_slots, int bit_width, int q_count,
+        int buffer_max, const int32_t * scores, const int32_t * ovf8, const int32_t * ovf16, size_t hitcount,
+        uint32_t * slots_out, uint8_t * frames_out, int64_t * scores_out ) {
+    std::vector<uint64_t> lens( slot_lens, slot_lens + nslots );
+    std::vector<std::vector<int32_t>> sc( q_count ), o8( q_count ), o16( q_count );
+    for( int q = 0; q < q_count; q++ ) {
+        sc[q].assign( scores + (size_t) q * nslots, scores + (size_t) ( q + 1 ) * nslots );
+        if( ovf8 ) o8[q].assign( ovf8 + (size_t) q * nslots, ovf8 + (size_t) ( q + 1 ) * nslots );
+        if( ovf16 ) o16[q].assign( ovf16 + (size_t) q * nslots, ovf16 + (size_t) ( q + 1 ) * nslots );
+    }
+    std::vector<FrameHit> hits;
+    general_search_order( lens, chunk_slots, bit_width, q_count, buffer_max, sc, o8, o16, hitcount, hits );
+    for( size_t i = 0; i < hits.size(); i++ ) {
+        slots_out[i] = hits[i].slot;
+        frames_out[i] = hits[i].query_id;
         scores_out[i] = hits[i].score;
     }
     return hits.size();

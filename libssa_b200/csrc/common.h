@@ -52,10 +52,13 @@ extern const char * sym_ncbi_aa;
 extern const char * sym_ncbi_nt16;
 extern int g_symtype;
 extern int g_query_strands;
+extern int g_db_gencode;  // genetic code the database translation table was built with
 bool gencode_is_valid( int code );
 // DB-side mapping: unknown symbols -> 0 (+ warning); returns number of unknown symbols
 size_t map_db_sequence( const char * ascii, size_t len, uint8_t * out, const signed char * map );
 void revcompl_codes( const uint8_t * in, size_t len, uint8_t * out );
+void init_translation_tables( int q_gencode, int d_gencode );
+void translate_codes( bool db_side, const uint8_t * nt, size_t len, int strand, int frame, std::vector<uint8_t> & out );
 
 // ---- matrices.cpp (reference src/matrices.c)
 struct ScoreMatrix {
@@ -95,24 +98,42 @@ void arrival_order( const std::vector<uint64_t> & lens, const int64_t * ovf8, co
 // replays thread heap + merge heap + final sort (reference minheap.c, manager.c:141-172)
 void replay_topk( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t k,
         std::vector<Hit> & out );
+// General form for searches with several query frames and/or several database entries per record (strands, 6-frame
+// translation).  `slots` = database entries in provider order (buffer_max per record, length 0 = absent);
+// scores/ovf8/ovf16 are indexed [frame][slot].  Produces the reference's final, sorted hit list.
+struct FrameHit {
+    uint32_t slot;
+    uint8_t query_id;
+    int64_t score;
+};
+void general_search_order( const std::vector<uint64_t> & slot_lens, size_t chunk_slots, int bit_width, int q_count, int buffer_max,
+        const std::vector<std::vector<int32_t>> & scores, const std::vector<std::vector<int32_t>> & ovf8,
+        const std::vector<std::vector<int32_t>> & ovf16, size_t hitcount, std::vector<FrameHit> & out,
+        size_t * n_ovf8 = nullptr, size_t * n_ovf16 = nullptr );
 
 // ---- search.cu: the device side
+struct QueryFrame {          // one entry of the reference's search_data_t::queries[] (src/libssa_datatypes.h:49-61)
+    const uint8_t * seq;     // code string
+    size_t len;
+    int strand, frame;
+};
 struct SearchRequest {
-    const uint8_t * query;  // code string
-    size_t qlen;
+    std::vector<QueryFrame> frames;  // 1 frame for AMINOACID / NUCLEOTIDE forward / TRANS_DB, up to 6 otherwise
     int search_type;   // SMITH_WATERMAN / NEEDLEMAN_WUNSCH
     int bit_width;     // 8 / 16 / 64: entry tier of the emulated reference scheduler
     size_t hitcount;
     int align_type;
-    int q_strand, q_frame;
 };
 struct HitAlignment {
-    Hit hit;
-    std::vector<uint8_t> db_codes;  // mapped database sequence of the hit
+    Hit hit;                        // db_id = provider record index
+    int query_id = 0;               // index into SearchRequest::frames
+    int db_strand = 0, db_frame = 0; // as stored by the reference's db_adapter for the scored database entry
+    std::vector<uint8_t> db_codes;  // database sequence of the result record (reference us_prepare_sequence semantics)
     std::string cigar;              // empty for COMPUTE_SCORE
     size_t q_start = 0, q_end = 0, d_start = 0, d_end = 0;
 };
 void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out );
 size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64_t * scores, uint64_t * ids );
+int db_buffer_max();  // database entries per provider record for the current symbol type / strands (reference adp_init)
 void gpu_prepare_db();
 void gpu_release();

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 static p_query new_query() {
     p_query q = (p_query) xmalloc( sizeof( struct _query ) );
@@ -54,8 +55,20 @@ static void fill_and_map( p_query q, const char * text, size_t len ) {
         }
     }
     else if( g_symtype == TRANS_QUERY || g_symtype == TRANS_BOTH ) {
+        // reading frames of the selected strands (reference src/query.c:146-159); the nucleotide string itself is dropped
+        std::vector<uint8_t> prot;
+        for( int s = 0; s < 2; s++ ) {
+            if( !( ( s + 1 ) & g_query_strands ) ) continue;
+            for( int f = 0; f < 3; f++ ) {
+                translate_codes( false, (const uint8_t *) mapped.seq, mapped.len, s, f, prot );
+                sequence_t & dst = q->aa[3 * s + f];
+                dst.seq = (char *) xmalloc( prot.size() + 1 );
+                memcpy( dst.seq, prot.data(), prot.size() );
+                dst.seq[prot.size()] = 0;
+                dst.len = prot.size();
+            }
+        }
         free( mapped.seq );
-        fatal( "Translated searches (TRANS_QUERY/TRANS_DB/TRANS_BOTH) are not available in the GPU library yet." );
     }
     else {
         q->aa[0] = mapped;

@@ -52,11 +52,12 @@ void simd_emission( const std::vector<uint64_t> & blocks, int channels, std::vec
     }
 }
 
-struct Heap {  // reference src/util/minheap.c:30-91, comparisons on the score only
+template<typename Elem>
+struct HeapT {  // reference src/util/minheap.c:30-91, comparisons on the score only
     size_t cap;
-    std::vector<Hit> a;
-    explicit Heap( size_t k ) : cap( k ) { a.reserve( k ); }
-    void add( const Hit & e ) {
+    std::vector<Elem> a;
+    explicit HeapT( size_t k ) : cap( k ) { a.reserve( k ); }
+    void add( const Elem & e ) {
         if( a.size() < cap ) {
             size_t i = a.size();
             a.push_back( e );
@@ -81,6 +82,17 @@ struct Heap {  // reference src/util/minheap.c:30-91, comparisons on the score o
         }
     }
 };
+typedef HeapT<Hit> Heap;
+
+int buffer_max_for_sort = 1;
+int frame_hit_compare( const void * a, const void * b ) {  // minheap.c:93-102 / manager.c:68-77 on (score, record id), descending
+    const FrameHit * x = (const FrameHit *) a;
+    const FrameHit * y = (const FrameHit *) b;
+    if( x->score != y->score ) return x->score < y->score ? 1 : -1;
+    const uint32_t rx = x->slot / (uint32_t) buffer_max_for_sort, ry = y->slot / (uint32_t) buffer_max_for_sort;
+    if( rx != ry ) return rx < ry ? 1 : -1;
+    return 0;
+}
 
 }  // namespace
 
@@ -159,4 +171,77 @@ void replay_topk( const int32_t * scores, const uint32_t * order, size_t n, size
         if( x.score != y.score ) return x.score > y.score;  // minheap.c:93-102, manager.c:68-77
         return x.db_id > y.db_id;
     } );
+}
+
+// Searches with several query frames and/or several database entries per record.  Per chunk the reference runs every
+// query frame over the chunk (src/algo/8/search_8.c:94-99), collects the entries that overflowed under ANY frame in
+// detection order (an entry can be listed more than once) and re-runs that list under EVERY frame through the next
+// tier (search_8.c:101-121, src/algo/16/search_16.c:92-113, src/algo/64/search_64.c:44-56), so a (frame, entry) pair
+// can reach the heap more than once.  Entries of one record tie on (score, db_id) in both final sorts; the order among
+// them is whatever the C library's qsort leaves, so the same qsort is applied here to the same array.
+void general_search_order( const std::vector<uint64_t> & lens, size_t chunk_slots, int bit_width, int q_count, int buffer_max,
+        const std::vector<std::vector<int32_t>> & scores, const std::vector<std::vector<int32_t>> & ovf8,
+        const std::vector<std::vector<int32_t>> & ovf16, size_t hitcount, std::vector<FrameHit> & out, size_t * n_ovf8,
+        size_t * n_ovf16 ) {
+    size_t count8 = 0, count16 = 0;
+    const size_t n = lens.size();
+    HeapT<FrameHit> thread_heap( hitcount );
+    auto add = [&]( int q, uint32_t slot ) { thread_heap.add( FrameHit{ slot, (uint8_t) q, (int64_t) scores[q][slot] } ); };
+    auto overflows = []( const std::vector<std::vector<int32_t>> & o, int q, uint32_t slot ) {
+        return !o.empty() && !o[q].empty() && o[q][slot] >= 0;
+    };
+    std::vector<uint32_t> idx, emit, l16, l64;
+    std::vector<uint64_t> blocks;
+    // one SIMD tier over `list` for every frame: non-overflowing entries reach the heap, the others are appended to `next`
+    auto simd_tier = [&]( const std::vector<uint32_t> & list, int channels, const std::vector<std::vector<int32_t>> & ovf,
+                          std::vector<uint32_t> & next ) {
+        for( int q = 0; q < q_count; q++ ) {
+            blocks.resize( list.size() );
+            for( size_t i = 0; i < list.size(); i++ ) {
+                uint64_t b = ( lens[list[i]] + 3 ) / 4;
+                if( overflows( ovf, q, list[i] ) ) b = std::min<uint64_t>( b, (uint64_t) ovf[q][list[i]] + 1 );
+                blocks[i] = b;
+            }
+            simd_emission( blocks, channels, emit );
+            for( uint32_t e : emit ) {
+                const uint32_t s = list[e];
+                if( overflows( ovf, q, s ) )
+                    next.push_back( s );
+                else
+                    add( q, s );
+            }
+        }
+    };
+    for( size_t start = 0; start < n; start += chunk_slots ) {
+        idx.clear();
+        for( size_t i = start; i < std::min( n, start + chunk_slots ); i++ )
+            if( lens[i] > 0 ) idx.push_back( (uint32_t) i );
+        if( idx.empty() ) break;
+        l16.clear();
+        l64.clear();
+        if( bit_width == 64 ) {
+            l64 = idx;
+        }
+        else {
+            if( bit_width == 8 )
+                simd_tier( idx, 32, ovf8, l16 );
+            else
+                l16 = idx;
+            if( bit_width == 8 ) count8 += l16.size();  // search_8.c:119
+            if( !l16.empty() ) simd_tier( l16, 16, ovf16, l64 );
+            count16 += l64.size();  // search_16.c:106
+        }
+        for( int q = 0; q < q_count && !l64.empty(); q++ )
+            for( uint32_t s : l64 ) add( q, s );
+    }
+    if( n_ovf8 ) *n_ovf8 = count8;
+    if( n_ovf16 ) *n_ovf16 = count16;
+    HeapT<FrameHit> result( hitcount );  // manager.c:141-146
+    for( const FrameHit & h : thread_heap.a ) result.add( h );
+    out = result.a;
+    buffer_max_for_sort = buffer_max;
+    if( !out.empty() ) {
+        qsort( out.data(), out.size(), sizeof( FrameHit ), frame_hit_compare );  // minheap_sort, manager.c:176
+        qsort( out.data(), out.size(), sizeof( FrameHit ), frame_hit_compare );  // sort_alignment_list, manager.c:113
+    }
 }

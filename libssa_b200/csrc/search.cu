@@ -68,9 +68,12 @@ template<typename T> struct PinBuf {  // grow-only pinned host buffer
 struct PackedDb {
     bool valid = false;
     uint64_t epoch = 0;
-    int symtype = -1;
+    int symtype = -1, strands = -1, db_gencode = -1;
     int rank = 0, world = 1;
-    // provider order (all shards): lengths, 0 = skipped record
+    // Database entries in provider order (all shards): lengths, 0 = skipped.  One entry per record, or buffer_max
+    // entries per record (index record * buffer_max + b) when strands / translation frames multiply the database
+    // (reference src/db_adapter.c:46-107,118-139).
+    int buffer_max = 1;
     std::vector<uint64_t> lens_all;
     uint64_t n_seqs = 0, n_residues = 0;
     // this shard, sorted by length (descending, provider index ascending)
@@ -184,23 +187,81 @@ void parallel_for( size_t n, size_t grain, const std::function<void( size_t, siz
 void build_db() {
     ensure_ctx();
     PackedDb & db = ctx.db;
-    if( db.valid && db.epoch == g_db_epoch && db.symtype == g_symtype && db.rank == ctx.rank && db.world == ctx.world ) return;
+    const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
+    const int gencode_key = translate_db ? g_db_gencode : 0;
+    const int strands_key = ( g_symtype == NUCLEOTIDE || translate_db ) ? g_query_strands : 0;
+    if( db.valid && db.epoch == g_db_epoch && db.symtype == g_symtype && db.rank == ctx.rank && db.world == ctx.world &&
+            db.strands == strands_key && db.db_gencode == gencode_key )
+        return;
 
     const double t0 = wall_ms();
-    if( g_symtype != NUCLEOTIDE && g_symtype != AMINOACID )
-        fatal( "Translated searches (TRANS_QUERY/TRANS_DB/TRANS_BOTH) are not available in the GPU library yet." );
-    if( g_symtype == NUCLEOTIDE && g_query_strands != FORWARD_STRAND )
-        fatal( "Nucleotide searches on the complementary strand are not available in the GPU library yet." );
-    const signed char * map = ( g_symtype == NUCLEOTIDE ) ? map_ncbi_nt16 : map_ncbi_aa;
+    const signed char * map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
+    int bm = 1;  // reference adp_init, src/db_adapter.c:118-139
+    if( g_symtype == NUCLEOTIDE )
+        bm = ( g_query_strands & COMPLEMENTARY_STRAND ) ? 2 : 1;
+    else if( translate_db )
+        bm = ( g_query_strands ^ BOTH_STRANDS ) ? 3 : 6;
+    const bool general = bm > 1 || translate_db;  // entries are materialised as code strings first
+    db.buffer_max = bm;
 
     db.arrival.clear();
     db.lens_all.clear();
     std::vector<const char *> text;
+    std::vector<uint64_t> rec_len;
     for( size_t i = 0;; i++ ) {  // the reference walks ids until the provider returns NULL (db_adapter.c:224-229)
         p_seqinfo rec = ssa_db_get_sequence( i );
         if( !rec ) break;
-        db.lens_all.push_back( rec->seqlen );
+        rec_len.push_back( rec->seqlen );
         text.push_back( rec->seq );
+    }
+    std::vector<uint8_t> entry_codes;
+    std::vector<uint64_t> entry_off;
+    size_t unknown_mapped = 0;
+    if( !general ) {
+        db.lens_all = rec_len;
+    }
+    else {
+        // entries of record r: nucleotide = forward, reverse complement; translated = frames 0-2 of one strand or of
+        // both (db_adapter.c:46-107).  Entries that come out empty are skipped like empty records.
+        const size_t nrec = rec_len.size();
+        if( nrec * (size_t) bm > 0xfffffff0ull ) fatal( "libssa_b200: more than 2^32 database entries are not supported." );
+        db.lens_all.assign( nrec * bm, 0 );
+        entry_off.assign( nrec * bm + 1, 0 );
+        for( size_t r = 0; r < nrec; r++ )
+            for( int b = 0; b < bm; b++ ) {
+                uint64_t len = rec_len[r];
+                if( translate_db ) len = len >= (uint64_t) ( b % 3 ) ? ( len - ( b % 3 ) ) / 3 : 0;
+                db.lens_all[r * bm + b] = len;
+                entry_off[r * bm + b + 1] = entry_off[r * bm + b] + len;
+            }
+        entry_codes.resize( entry_off.back() + 1 );
+        std::vector<size_t> unknown_per( ( nrec + 255 ) / 256 + 1, 0 );
+        parallel_for( nrec, 256, [&]( size_t r0, size_t r1 ) {
+            std::vector<uint8_t> nt, tmp;
+            size_t unknown = 0;
+            for( size_t r = r0; r < r1; r++ ) {
+                if( rec_len[r] == 0 ) continue;
+                nt.resize( rec_len[r] + 1 );
+                unknown += map_db_sequence( text[r], rec_len[r], nt.data(), map );
+                for( int b = 0; b < bm; b++ ) {
+                    uint8_t * dst = entry_codes.data() + entry_off[r * bm + b];
+                    if( !translate_db ) {
+                        if( b == 0 )
+                            memcpy( dst, nt.data(), rec_len[r] );
+                        else
+                            revcompl_codes( nt.data(), rec_len[r], dst );
+                    }
+                    else {
+                        const int strand = ( bm == 6 ) ? b / 3 : g_query_strands - 1;
+                        translate_codes( true, nt.data(), rec_len[r], strand, b % 3, tmp );
+                        if( tmp.size() != db.lens_all[r * bm + b] ) fatal( "libssa_b200: internal error: translated length." );
+                        if( !tmp.empty() ) memcpy( dst, tmp.data(), tmp.size() );
+                    }
+                }
+            }
+            unknown_per[r0 / 256] = unknown;
+        } );
+        unknown_mapped = std::accumulate( unknown_per.begin(), unknown_per.end(), (size_t) 0 );
     }
     const size_t nall = db.lens_all.size();
     if( nall > 0xfffffff0ull ) fatal( "libssa_b200: more than 2^32 database records are not supported." );
@@ -248,18 +309,21 @@ void build_db() {
             const uint32_t la = db.sorted_len[2 * p];
             const bool has_b = 2 * p + 1 < nloc;
             const uint32_t lb = has_b ? db.sorted_len[2 * p + 1] : 0;
-            const unsigned char * ta = (const unsigned char *) text[db.sorted_id[2 * p]];
-            const unsigned char * tb = has_b ? (const unsigned char *) text[db.sorted_id[2 * p + 1]] : nullptr;
+            const unsigned char * ta = general ? entry_codes.data() + entry_off[db.sorted_id[2 * p]]
+                                               : (const unsigned char *) text[db.sorted_id[2 * p]];
+            const unsigned char * tb = !has_b ? nullptr
+                    : general ? entry_codes.data() + entry_off[db.sorted_id[2 * p + 1]]
+                              : (const unsigned char *) text[db.sorted_id[2 * p + 1]];
             uint16_t * out = h_stream.p + db.pair_col[p];
             for( uint32_t c = 0; c < la; c++ ) {
-                int a = map[ta[c]];
+                int a = general ? (int) ta[c] : map[ta[c]];
                 if( a < 0 ) {
                     a = 0;
                     unknown++;
                 }
                 int b = 0;
                 if( c < lb ) {
-                    b = map[tb[c]];
+                    b = general ? (int) tb[c] : map[tb[c]];
                     if( b < 0 ) {
                         b = 0;
                         unknown++;
@@ -275,7 +339,7 @@ void build_db() {
         }
         unknown_per_chunk[p0 / 1024] = unknown;
     } );
-    size_t unknown = std::accumulate( unknown_per_chunk.begin(), unknown_per_chunk.end(), (size_t) 0 );
+    size_t unknown = unknown_mapped + std::accumulate( unknown_per_chunk.begin(), unknown_per_chunk.end(), (size_t) 0 );
     if( unknown > 0 ) print_warning( "%ld unknown symbols found and set to zero", (long) unknown );
     for( size_t i = db.total_cols; i < db.total_cols + 64; i++ ) h_stream.p[i] = 0;
 
@@ -311,6 +375,8 @@ void build_db() {
 
     db.epoch = g_db_epoch;
     db.symtype = g_symtype;
+    db.strands = strands_key;
+    db.db_gencode = gencode_key;
     db.rank = ctx.rank;
     db.world = ctx.world;
     db.valid = true;
@@ -1152,25 +1218,18 @@ size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64
     return nloc;
 }
 
-void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
-    const double t_call = wall_ms();
-    build_db();
+// One query frame against the entry stream: top-k with the reference's one-thread tie behaviour.  Hit ids are entry
+// (slot) indices.  Every key (score, id) is distinct, so the final order does not depend on the sort algorithm.
+static void search_single( const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
     PackedDb & db = ctx.db;
     const size_t nloc = db.sorted_id.size();
     const size_t nglob = db.sorted_all.size();
     const size_t world = (size_t) ctx.world;
     const size_t stride = ( nglob + world - 1 ) / world;  // local positions per rank, padded
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
-    out.clear();
-    ctx.stats.launches = 0;
-    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
-    ctx.stats.wide_tier_seqs = 0;
-    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
-    ctx.stats.cells = (uint64_t) req.qlen * db.local_residues;
-
-    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
     ctx.d_scores.reserve( stride + 2 );
-    score_shard( req.query, req.qlen, nw );
+    score_shard( query, qlen, nw );
 
     // ---- shard results -> every rank (NCCL all-gather over NVLink, supplied by the host language) ----
     int32_t * d_all = ctx.d_scores.p;
@@ -1180,17 +1239,18 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         d_all = ctx.d_gathered.p;
     }
 
-    const bool use_gpu_arrival = g_chunk_size <= (size_t) ARRIVAL_MAX_CHUNK;
 
     // ---- top-k on the device ----
     // Radix-select the k-th largest score T and count the ties at T (topk.cuh).  If no more than k records score
     // >= T the reported set is {score >= T} whatever the arrival order, so the k hits are compacted on the device
     // and nothing else crosses PCIe.  Only when the tie at T straddles the cut-off does the reference's tie
     // behaviour matter; then the arrival-order replay below runs.
+    const size_t chunk = g_chunk_size * (size_t) db.buffer_max;  // entries per reference chunk (db_adapter.c:196)
+    const bool use_gpu_arrival = chunk <= (size_t) ARRIVAL_MAX_CHUNK;
     bool fast_done = false;
-    std::vector<Hit> hits;
+    hits.clear();
     {
-        PackedDb::Arrival & base = arrival_for( req.bit_width, g_chunk_size, use_gpu_arrival );  // validity: records the reference reaches
+        PackedDb::Arrival & base = arrival_for( req.bit_width, chunk, use_gpu_arrival );  // validity: records the reference reaches
         const size_t n_valid = base.order.size();
         const size_t k = req.hitcount;
         if( k > 0 && k < n_valid && nglob > 0 ) {
@@ -1274,8 +1334,8 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
             ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
             int32_t * d_f = ctx.d_first.p;  // [stride] first8 | [stride] first16
             launch_fill( d_f, INT_MAX, 2 * stride );
-            Plan pl = make_plan( req.qlen );
-            run_wide( slots, req.query, req.qlen, pl, false, true, d_f, d_f + stride, 1, ctx.stream );  // rewrites the same exact scores
+            Plan pl = make_plan( qlen );
+            run_wide( slots, query, qlen, pl, false, true, d_f, d_f + stride, 1, ctx.stream );  // rewrites the same exact scores
             int32_t * d_f_all = d_f;
             if( world > 1 ) {
                 d_f_all = ctx.d_first.p + 2 * stride;
@@ -1311,19 +1371,19 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     // (only for the records static bounds cannot clear: usually none at 16 bit, everything at 8 bit)
     uint32_t * d_nw_counts = nullptr;
     if( !fast_done && nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
-        const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 8 ) ) : 0;
-        const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( req.qlen, 16 ) );
+        const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( qlen, 8 ) ) : 0;
+        const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( qlen, 16 ) );
         // every rank takes the same branch: whether any shard needs the emulation follows from the GLOBAL longest record
         const int64_t longest = nglob ? (int64_t) db.lens_all[db.sorted_all[0]] : 0;
-        const bool need8 = req.bit_width == 8 && longest > nw_tier_safe_len( req.qlen, 8 );
-        const bool need16 = longest > nw_tier_safe_len( req.qlen, 16 );
+        const bool need8 = req.bit_width == 8 && longest > nw_tier_safe_len( qlen, 8 );
+        const bool need16 = longest > nw_tier_safe_len( qlen, 16 );
         if( need8 || need16 ) {
             have_overflow = true;
             ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
             int32_t * d_f = ctx.d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier
             launch_fill( d_f, INT_MAX, 2 * stride );
-            if( n8 ) run_nw_sat( req.query, req.qlen, 8, n8, d_f );
-            if( n16 ) run_nw_sat( req.query, req.qlen, 16, n16, d_f + stride );
+            if( n8 ) run_nw_sat( query, qlen, 8, n8, d_f );
+            if( n16 ) run_nw_sat( query, qlen, 16, n16, d_f + stride );
             ctx.d_counter.reserve( 64 );
             d_nw_counts = ctx.d_counter.p + 32;
             CUDA_OK( cudaMemsetAsync( d_nw_counts, 0, 8, ctx.stream ) );
@@ -1361,19 +1421,19 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         // nothing to replay
     }
     else if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
-        PackedDb::Arrival & ar = arrival_for( req.bit_width, g_chunk_size, use_gpu_arrival );
+        PackedDb::Arrival & ar = arrival_for( req.bit_width, chunk, use_gpu_arrival );
         order = ar.order.data();
         narr = ar.order.size();
         d_pos = &ar.d_pos_of_sorted;
     }
     else if( use_gpu_arrival ) {
         ctx.h_order.reserve( nglob + 1 );
-        narr = gpu_arrival_order( req.bit_width, g_chunk_size, d_first_gathered, stride, ctx.d_pos_tmp, ctx.h_order.p );
+        narr = gpu_arrival_order( req.bit_width, chunk, d_first_gathered, stride, ctx.d_pos_tmp, ctx.h_order.p );
         order = ctx.h_order.p;   // complete once the stream is synchronised below
         d_pos = &ctx.d_pos_tmp;
     }
     else {
-        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), g_chunk_size, req.bit_width, ctx.order_tmp );
+        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), chunk, req.bit_width, ctx.order_tmp );
         upload_positions( ctx.order_tmp, ctx.d_pos_tmp );
         order = ctx.order_tmp.data();
         narr = ctx.order_tmp.size();
@@ -1422,22 +1482,184 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
         if( req.bit_width == 8 && ctx.h_first.p[k] != INT_MAX ) ctx.stats.overflow_8++;
         if( ctx.h_first.p[n_flagged + k] != INT_MAX ) ctx.stats.overflow_16++;
     }
+}
+
+// Searches over several query frames, or whose hit list holds tied entries of one record: every frame is scored on the
+// GPU, the scores (and, for 8/16-bit entry, the overflow blocks) come back to the host, and the reference's chunk /
+// frame / overflow-list schedule is replayed there (replay.cpp: general_search_order).
+static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh ) {
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    const size_t nglob = db.sorted_all.size();
+    const size_t world = (size_t) ctx.world;
+    const size_t stride = ( nglob + world - 1 ) / world;
+    const size_t total = stride * world;
+    const size_t nslots = db.lens_all.size();
+    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
+    const int Q = (int) req.frames.size();
+    const bool tiers = req.bit_width == 8 || req.bit_width == 16;
+    std::vector<std::vector<int32_t>> scores( Q ), ovf8( Q ), ovf16( Q );
+    ctx.stats.cells = 0;
+    for( int q = 0; q < Q; q++ ) {
+        const QueryFrame & f = req.frames[q];
+        scores[q].assign( nslots, 0 );
+        ctx.stats.cells += (uint64_t) f.len * db.local_residues;
+        if( nglob == 0 ) continue;
+        ctx.d_scores.reserve( stride + 2 );
+        score_shard( f.seq, f.len, nw );
+        int32_t * d_all = ctx.d_scores.p;
+        if( world > 1 ) {
+            ctx.d_gathered.reserve( total + 2 );
+            gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
+            d_all = ctx.d_gathered.p;
+        }
+        ctx.h_scores.reserve( total + 1 );
+        CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, d_all, total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        ctx.stats.d2h_bytes += total * sizeof( int32_t );
+        for( size_t g = 0; g < nglob; g++ ) scores[q][db.sorted_all[g]] = ctx.h_scores.p[( g % world ) * stride + g / world];
+        if( !tiers ) continue;
+
+        bool have = false;
+        ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+        int32_t * d_f = ctx.d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier: first overflowing column
+        if( !nw ) {  // SW: score >= 255 / 65535 (src/algo/simd/search_simd_sw.c:372-379)
+            const int32_t thr = req.bit_width == 8 ? 255 : 65535;
+            for( size_t g = 0; g < nglob && !have; g++ ) have = scores[q][db.sorted_all[g]] >= thr;
+            if( have ) {
+                std::vector<uint32_t> slots;
+                for( size_t sl = 0; sl < nloc; sl++ )
+                    if( ctx.h_scores.p[(size_t) ctx.rank * stride + sl] >= thr ) slots.push_back( (uint32_t) sl );
+                launch_fill( d_f, INT_MAX, 2 * stride );
+                Plan pl = make_plan( f.len );
+                run_wide( slots, f.seq, f.len, pl, false, true, d_f, d_f + stride, 1, ctx.stream );
+            }
+        }
+        else {  // NW: the saturating tiers, only for the entries static bounds cannot clear (nw_sat.cuh)
+            const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( f.len, 8 ) ) : 0;
+            const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( f.len, 16 ) );
+            const int64_t longest = (int64_t) db.lens_all[db.sorted_all[0]];
+            have = ( req.bit_width == 8 && longest > nw_tier_safe_len( f.len, 8 ) ) || longest > nw_tier_safe_len( f.len, 16 );
+            if( have ) {
+                launch_fill( d_f, INT_MAX, 2 * stride );
+                if( n8 ) run_nw_sat( f.seq, f.len, 8, n8, d_f );
+                if( n16 ) run_nw_sat( f.seq, f.len, 16, n16, d_f + stride );
+            }
+        }
+        if( !have ) continue;
+        int32_t * d_f_all = d_f;
+        if( world > 1 ) {
+            d_f_all = ctx.d_first.p + 2 * stride;
+            gather_i32( d_f, d_f_all, 2 * stride );
+        }
+        ctx.h_first.reserve( 2 * total + 2 );
+        CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_f_all, 2 * total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        ctx.stats.d2h_bytes += 2 * total * sizeof( int32_t );
+        ovf8[q].assign( nslots, -1 );
+        ovf16[q].assign( nslots, -1 );
+        for( size_t g = 0; g < nglob; g++ ) {
+            const size_t r = g % world, sl = g / world;
+            const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
+            if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[q][db.sorted_all[g]] = c8 / 4;
+            if( c16 != INT_MAX ) ovf16[q][db.sorted_all[g]] = c16 / 4;
+        }
+    }
+    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    size_t n8 = 0, n16 = 0;
+    general_search_order( db.lens_all, g_chunk_size * (size_t) db.buffer_max, req.bit_width, Q, db.buffer_max, scores, ovf8, ovf16,
+            req.hitcount, fh, &n8, &n16 );
+    ctx.stats.overflow_8 = n8;
+    ctx.stats.overflow_16 = n16;
+}
+void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
+    const double t_call = wall_ms();
+    build_db();
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
+    const uint32_t bm = (uint32_t) db.buffer_max;
+    out.clear();
+    ctx.stats.launches = 0;
+    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
+    ctx.stats.wide_tier_seqs = 0;
+    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
+    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+
+    std::vector<FrameHit> fh;
+    bool done = false;
+    if( req.frames.size() == 1 ) {
+        std::vector<Hit> hits;
+        search_single( req.frames[0].seq, req.frames[0].len, req, hits );
+        // entries of one record that tie on the score are ordered by the C library's sort in the reference: replay then
+        done = true;
+        for( size_t i = 1; i < hits.size() && bm > 1; i++ )
+            if( hits[i].score == hits[i - 1].score && hits[i].db_id / bm == hits[i - 1].db_id / bm ) done = false;
+        if( done ) {
+            fh.resize( hits.size() );
+            for( size_t i = 0; i < hits.size(); i++ ) fh[i] = FrameHit{ (uint32_t) hits[i].db_id, 0, hits[i].score };
+        }
+    }
+    if( !done ) search_frames( req, fh );
+
     if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
         print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
                 (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
 
-    // ---- result records ----
-    const signed char * map = ( g_symtype == NUCLEOTIDE ) ? map_ncbi_nt16 : map_ncbi_aa;
-    out.resize( hits.size() );
-    for( size_t i = 0; i < hits.size(); i++ ) {
-        out[i].hit = hits[i];
-        p_seqinfo rec = ssa_db_get_sequence( hits[i].db_id );
-        if( !rec ) fatal( "Could not get sequence from DB: %ld", (long) hits[i].db_id );  // aligner.c:66-68
-        out[i].db_codes.resize( rec->seqlen );
-        map_db_sequence( rec->seq, rec->seqlen, out[i].db_codes.data(), map );
+    // ---- result records: reference src/algo/aligner.c:62-93 ----
+    // The reference rebuilds the database side from the record with us_prepare_sequence( seq, len, frame, strand )
+    // (src/util/util_sequence.c:384-417): nucleotide records always come back as the forward strand, and a translated
+    // record of a one-strand search is translated from the complementary strand whichever strand was scored.  The
+    // alignment is computed on that sequence; reproduced as is.
+    const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
+    const signed char * map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
+    out.resize( fh.size() );
+    bool scored_sequence = true;  // the alignment runs on the very sequence that was scored
+    for( size_t i = 0; i < fh.size(); i++ ) {
+        const uint32_t rec_id = fh[i].slot / bm, b = fh[i].slot % bm;
+        out[i].hit = Hit{ rec_id, fh[i].score };
+        out[i].query_id = fh[i].query_id;
+        if( g_symtype == NUCLEOTIDE ) {
+            out[i].db_strand = (int) b;
+            out[i].db_frame = 0;
+            if( b ) scored_sequence = false;
+        }
+        else if( translate_db ) {
+            out[i].db_strand = bm == 6 ? (int) ( b / 3 ) : g_query_strands;  // db_adapter.c:80,92
+            out[i].db_frame = (int) ( b % 3 );
+            if( bm == 3 && g_query_strands == FORWARD_STRAND ) scored_sequence = false;
+        }
+        p_seqinfo rec = ssa_db_get_sequence( rec_id );
+        if( !rec ) fatal( "Could not get sequence from DB: %ld", (long) rec_id );  // aligner.c:66-68
+        if( translate_db ) {
+            std::vector<uint8_t> nt( rec->seqlen + 1 );
+            map_db_sequence( rec->seq, rec->seqlen, nt.data(), map );
+            translate_codes( true, nt.data(), rec->seqlen, out[i].db_strand, out[i].db_frame, out[i].db_codes );
+        }
+        else {
+            out[i].db_codes.resize( rec->seqlen );
+            map_db_sequence( rec->seq, rec->seqlen, out[i].db_codes.data(), map );
+        }
     }
     if( req.align_type == COMPUTE_ALIGNMENT && !out.empty() ) {
-        traceback_hits( ctx.stream, req.query, req.qlen, nw, out, &ctx.stats );
+        if( req.frames.size() == 1 ) {
+            traceback_hits( ctx.stream, req.frames[0].seq, req.frames[0].len, nw, out, &ctx.stats, scored_sequence );
+        }
+        else {
+            for( size_t q = 0; q < req.frames.size(); q++ ) {
+                std::vector<HitAlignment> group;
+                std::vector<size_t> where;
+                for( size_t i = 0; i < out.size(); i++ )
+                    if( (size_t) out[i].query_id == q ) {
+                        where.push_back( i );
+                        group.push_back( std::move( out[i] ) );
+                    }
+                if( group.empty() ) continue;
+                traceback_hits( ctx.stream, req.frames[q].seq, req.frames[q].len, nw, group, &ctx.stats, scored_sequence );
+                for( size_t j = 0; j < where.size(); j++ ) out[where[j]] = std::move( group[j] );
+            }
+        }
     }
 
     float ms = 0;

@@ -342,7 +342,7 @@ void traceback_release() {
 }
 
 void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bool nw, std::vector<HitAlignment> & hits,
-        ssa_b200_stats_t * stats ) {
+        ssa_b200_stats_t * stats, bool scored_sequence ) {
     const int n = (int) hits.size();
     if( n == 0 ) return;
     if( !tb.d_matrix ) CUDA_OK( cudaMalloc( &tb.d_matrix, 1024 * sizeof( int32_t ) ) );
@@ -439,7 +439,7 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
     std::vector<uint32_t> runs;
     for( int k = 0; k < n; k++ ) {
         const int32_t * r = &res[8 * k];
-        if( !nw && r[0] != (int32_t) hits[k].hit.score )
+        if( scored_sequence && !nw && r[0] != (int32_t) hits[k].hit.score )
             fatal( "libssa_b200: internal error: alignment score %d differs from search score %ld for sequence %ld", r[0],
                     (long) hits[k].hit.score, (long) hits[k].hit.db_id );
         if( !r[5] ) fatal( "Internal error in align function." );  // align.c:131

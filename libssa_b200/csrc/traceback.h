@@ -4,5 +4,5 @@
 #include <cuda_runtime.h>
 
 void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bool nw, std::vector<HitAlignment> & hits,
-        ssa_b200_stats_t * stats );
+        ssa_b200_stats_t * stats, bool scored_sequence );
 void traceback_release();

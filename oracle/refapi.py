@@ -129,6 +129,55 @@ class LibSSA:
         return self._collect(self.lib.nw_align(q, hitcount, bit_width, align_type))
 
 
+class _Elem(C.Structure):  # elem_t, src/util/minheap.h:26-32
+    _fields_ = [("db_id", C.c_size_t), ("db_frame", C.c_uint8), ("db_strand", C.c_uint8), ("query_id", C.c_uint8),
+                ("score", C.c_long)]
+
+
+class _MinHeap(C.Structure):  # minheap_t, src/util/minheap.h:34-38
+    _fields_ = [("alloc", C.c_size_t), ("count", C.c_size_t), ("array", C.POINTER(_Elem))]
+
+
+class _SearchResult(C.Structure):  # search_result_t, src/libssa_datatypes.h:40-46
+    _fields_ = [("heap", C.POINTER(_MinHeap)), ("chunk_count", C.c_size_t), ("seq_count", C.c_size_t),
+                ("overflow_8_bit_count", C.c_size_t), ("overflow_16_bit_count", C.c_size_t)]
+
+
+def search_phase(ref, q, hitcount, bit_width, nw):
+    """The reference's search phase alone, through its internal entry points: one searcher pass (s_search,
+    src/algo/searcher.c:158-181), the merge into the result heap and minheap_sort exactly as m_run does
+    (src/algo/manager.c:141-176), WITHOUT the result-record creation - which crashes for TRANS_DB / TRANS_BOTH
+    (us_prepare_sequence reallocs an uninitialised pointer, src/util/util_sequence.c:385,408).
+    -> ([(score, db_id, db_frame, db_strand, query_id)], overflow_8, overflow_16)"""
+    L = ref.lib
+    (L.init_for_nw if nw else L.init_for_sw).argtypes = [C.c_void_p, C.c_int, C.c_int]
+    (L.init_for_nw if nw else L.init_for_sw)(q, bit_width, 0)
+    L.s_search.restype = C.POINTER(_SearchResult)
+    L.s_search.argtypes = [C.POINTER(C.c_size_t)]
+    L.minheap_init.restype = C.POINTER(_MinHeap)
+    L.minheap_init.argtypes = [C.c_size_t]
+    L.minheap_add.argtypes = [C.POINTER(_MinHeap), C.POINTER(_Elem)]
+    L.minheap_sort.argtypes = [C.POINTER(_MinHeap)]
+    L.minheap_exit.argtypes = [C.POINTER(_MinHeap)]
+    L.s_free.argtypes = [C.POINTER(_SearchResult)]
+    k = C.c_size_t(hitcount)
+    res = L.s_search(C.byref(k))
+    r = res.contents
+    merged = L.minheap_init(hitcount)
+    for j in range(r.heap.contents.count):
+        L.minheap_add(merged, C.byref(r.heap.contents.array[j]))
+    L.minheap_sort(merged)
+    out = []
+    for j in range(merged.contents.count):
+        e = merged.contents.array[j]
+        out.append((int(e.score), int(e.db_id), int(e.db_frame), int(e.db_strand), int(e.query_id)))
+    o8, o16 = int(r.overflow_8_bit_count), int(r.overflow_16_bit_count)
+    L.adp_exit()
+    L.minheap_exit(merged)
+    L.s_free(res)
+    return out, o8, o16
+
+
 _ref = None
 
 

@@ -183,3 +183,80 @@ def test_sharded_merge_two_ranks_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count("MERGE_OK") == 2, out.stdout
+
+
+@pytest.mark.parametrize("gencode", [1, 2, 4, 11, 16, 22, 23])
+def test_query_translation_matches_reference(prod_host, ref, gencode):
+    """6-frame translation of a nucleotide query (reference src/util/util_sequence.c:200-382, src/query.c:146-159)"""
+    from libssa_b200 import synth
+    text = synth.random_nucleotide(gencode, 311, iupac_rate=0.15)
+    for strands in (1, 2, 3):
+        frames = []
+        for lib in (prod_host, ref):
+            lib.set_output_mode(0)
+            lib.init_symbol_translation(cases.TRANS_QUERY if hasattr(cases, "TRANS_QUERY") else 2, strands, gencode, gencode)
+            q = lib.init_sequence_fasta(cases.READ_FROM_STRING, text)
+            s = C.cast(q, C.POINTER(_Query)).contents
+            frames.append([_codes(s.aa[i]) if s.aa[i].seq else None for i in range(6)])
+            lib.free_sequence(q)
+        assert frames[0] == frames[1], (gencode, strands)
+        assert sum(f is not None for f in frames[0]) == (6 if strands == 3 else 3)
+    for lib in (prod_host, ref):
+        lib.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+
+
+@pytest.mark.parametrize("mode", __import__("frames").MODES, ids=__import__("frames").MODE_IDS)
+def test_frames_replay_matches_reference(prod_host, ref, port, tmp_path, mode):
+    """Strand / reading-frame searches: the host-side replay of the reference's schedule (chunks x frames x
+    overflow lists, heaps, both sorts), fed with oracle scores of the reference's own entry sequences, must give
+    the hit list the reference's search phase produces (src/algo/8/search_8.c:94-124, src/algo/manager.c:141-176),
+    and the committed fixture must be what the reference produces."""
+    import frames as F
+    symtype, strands = mode
+    out = tmp_path / "ref.json"
+    F.run_reference_worker(symtype, strands, out, entries=True)   # own process: see tests/frames_ref_worker.py
+    R = json.load(open(out))
+    gold = json.load(open(os.path.join(GOLD, "frames.json")))[F.MODE_IDS[F.MODES.index(mode)]]
+    assert gold["searches"] == R["searches"]
+    chunk, k = R["chunk"], R["k"]
+    recs, query = F.workload(symtype)
+    F.configure(prod_host, symtype, strands)
+    M = prod_host.score_matrix()
+    spec, go, ge = F.scoring(symtype)
+    qf = [(np.array(c, dtype=np.uint8), s, f) for c, s, f in R["query_frames"]]
+    assert [(c.tolist(), s, f) for c, s, f in F.query_frames(prod_host, symtype, strands, query)] == \
+           [(c.tolist(), s, f) for c, s, f in qf]
+    entries = [np.array(e, dtype=np.uint8) for e in R["entries"]]
+    bm = F.buffer_max(symtype, strands)
+    assert len(entries) == bm * len(recs)
+    lens = np.array([len(e) for e in entries], dtype=np.uint64)
+    Q, n = len(qf), len(entries)
+    for nw in (False, True):
+        score = np.zeros((Q, n), dtype=np.int32)
+        fn = port.nw_score if nw else port.sw_score
+        for q in range(Q):
+            for s in range(n):
+                if lens[s]:
+                    score[q, s] = fn(entries[s], qf[q][0], M, go, ge)
+        for bits in (64, 16, 8):
+            o8 = np.full((Q, n), -1, dtype=np.int32)
+            o16 = np.full((Q, n), -1, dtype=np.int32)
+            if bits != 64:
+                for q in range(Q):
+                    for s in range(n):
+                        if not lens[s]:
+                            continue
+                        if nw:
+                            if bits == 8:
+                                o8[q, s] = port.nw_simd_channel(entries[s], qf[q][0], M, go, ge, 8)[1]
+                            o16[q, s] = port.nw_simd_channel(entries[s], qf[q][0], M, go, ge, 16)[1]
+                        elif score[q, s] >= 255:
+                            _, b8, b16 = port.sw_score_blocks(entries[s], qf[q][0], M, go, ge)
+                            o8[q, s], o16[q, s] = (b8 if bits == 8 else -1), b16
+            got = prod_host.host_frames_replay(lens, chunk * bm, bits, bm, score, k, o8, o16)
+            got = [[sc, slot // bm] + list(reversed(F.entry_fields(symtype, strands, slot % bm))) + [q] for sc, slot, q in got]
+            want = R["searches"]["%s%d" % ("nw" if nw else "sw", bits)]
+            assert got == want["phase"], (mode, nw, bits)
+            if not nw and bits == 8:
+                assert want["overflow_8"] > 0, "workload must exercise the overflow lists"
+    prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
