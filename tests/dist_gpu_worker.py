@@ -18,6 +18,13 @@ def main():
             assert g == e, (rank, entry["case"]["name"], run, g[:3], e[:3])
         st = lib.stats()
         assert st.local_seqs < st.n_seqs or st.n_seqs < world
+    # strand / reading-frame searches, sharded: every frame's shard scores are gathered, every rank replays
+    import tempfile
+    import frames as F
+    from oracle import port
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ((F.NUCLEOTIDE, F.BOTH), (F.TRANS_QUERY, F.BOTH), (F.TRANS_DB, F.FORWARD), (F.TRANS_BOTH, F.BOTH)):
+            F.check_product_mode(lib, port, mode, tmp)
     import torch.distributed as dist
     dist.barrier()
     print("MULTI_OK rank %d of %d" % (rank, world))

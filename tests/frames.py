@@ -53,6 +53,7 @@ def workload(symtype, seed=1):
     """-> (db records (text), query text).  DNA database unless the mode searches proteins (TRANS_QUERY)."""
     rng = np.random.default_rng(seed)
     qd = _rand_dna(rng, 330)
+    qd = qd[:200] + "A" * 45 + qd[245:]                                 # a poly-K stretch in every forward frame
     aa = "ACDEFGHIKLMNPQRSTVWY"
     recs = []
     if symtype == TRANS_QUERY:
@@ -79,6 +80,10 @@ def workload(symtype, seed=1):
         for r in (9, 12, 12, 31):
             recs.append(recs[r])
         recs.append(_mutate(rng, recs[2], 0.02, "ACGT"))
+        # entries of ONE record that tie: a reverse-complement palindrome (both strands identical) and a homopolymer of
+        # length 3n+2 (all three frames identical) - their order is decided by the reference's sorts alone
+        recs.insert(20, qd[:100] + revcomp(qd[:100]))
+        recs.insert(33, "A" * 62)
         query = translate(qd, 0) if symtype == TRANS_DB else qd
     return recs, query
 
@@ -201,3 +206,59 @@ def run_reference_worker(symtype, strands, out, entries=False):
         cmd.append("--entries")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def frame_fields(symtype, strands):
+    """(strand, frame) of every query frame, in the reference's order (src/algo/searcher.c:42-90)"""
+    if symtype == NUCLEOTIDE:
+        return [(s, 0) for s in range(2) if (s + 1) & strands]
+    if symtype in (AMINOACID, TRANS_DB):
+        return [(0, 0)]
+    return [(s, f) for s in range(2) if (s + 1) & strands for f in range(3)]
+
+
+def check_product_mode(prod, port, mode, tmp_path):
+    """Runs every search of one mode through the product's libssa.h calls (GPU) and compares with the fixture
+    tests/golden/frames.json; used one-GPU (tests/test_gpu_frames.py) and sharded (tests/dist_gpu_worker.py)."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.json")))
+    symtype, strands = mode
+    gold = gold[MODE_IDS[MODES.index(mode)]]
+    recs, query = workload(symtype)
+    db = os.path.join(str(tmp_path), "db_%d_%d.fas" % (symtype, strands))
+    with open(db, "w") as f:
+        for i, r in enumerate(recs):
+            f.write(">r%d\n%s\n" % (i, r))
+    configure(prod, symtype, strands)
+    prod.set_chunk_size(gold["chunk"])
+    prod.init_db(db)
+    q = prod.init_sequence_fasta(cases.READ_FROM_STRING, query)
+    qfields = frame_fields(symtype, strands)
+    qf = query_frames(prod, symtype, strands, query)
+    M = prod.score_matrix()
+    _, go, ge = scoring(symtype)
+    try:
+        for nw in (False, True):
+            for bits in (64, 16, 8):
+                want = gold["searches"]["%s%d" % ("nw" if nw else "sw", bits)]
+                for align in (cases.COMPUTE_SCORE, cases.COMPUTE_ALIGNMENT):
+                    hits = (prod.nw_align if nw else prod.sw_align)(q, gold["k"], bits, align)
+                    got = [[h.score, h.db_id, h.db_strand, h.db_frame, qfields.index((h.q_strand, h.q_frame))] for h in hits]
+                    assert got == want["phase"], (mode, nw, bits, align)
+                st = prod.stats()
+                if not nw or st.overflow_8 or st.overflow_16:   # NW: only known when the saturating tiers had to be emulated
+                    assert (st.overflow_8, st.overflow_16) == (want["overflow_8"], want["overflow_16"]), (mode, nw, bits)
+                if "hits" in want:
+                    assert [hit_record(h) for h in hits] == want["hits"], (mode, nw, bits)
+                else:
+                    # no reference record to compare with: the alignment must be the oracle's for the sequences returned
+                    for h in hits[:8]:
+                        d = np.frombuffer(h.db_seq, dtype=np.uint8)
+                        a = qf[qfields.index((h.q_strand, h.q_frame))][0]
+                        exp = port.cigar(a, d, M, go, ge, nw)
+                        assert ([h.q_start, h.q_end, h.d_start, h.d_end], h.cigar) == (list(exp[0]), exp[1]), (mode, nw, bits)
+    finally:
+        prod.free_sequence(q)
+        prod.set_chunk_size(1000)
+        prod.init_symbol_translation(AMINOACID, 1, 1, 1)

@@ -6,64 +6,12 @@ fixture tests/golden/frames.json, which tests/golden/make_frames_golden.py gener
 For TRANS_DB / TRANS_BOTH the reference crashes while it builds the result records (us_prepare_sequence reallocs
 an uninitialised pointer, src/util/util_sequence.c:385,408), so for those two the fixture holds the hit list as it
 leaves the reference's search phase and the alignment is checked against the oracle instead."""
-import json
-import os
-
-import numpy as np
 import pytest
 
-import cases
 import frames as F
-
-GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.json")))
-
-
-def _frame_fields(symtype, strands):
-    if symtype == F.NUCLEOTIDE:
-        return [(s, 0) for s in range(2) if (s + 1) & strands]
-    if symtype in (F.AMINOACID, F.TRANS_DB):
-        return [(0, 0)]
-    return [(s, f) for s in range(2) if (s + 1) & strands for f in range(3)]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", F.MODES, ids=F.MODE_IDS)
 def test_strand_and_frame_searches_match_reference(prod, port, tmp_path, mode):
-    symtype, strands = mode
-    gold = GOLD[F.MODE_IDS[F.MODES.index(mode)]]
-    recs, query = F.workload(symtype)
-    db = tmp_path / "db.fas"
-    with open(db, "w") as f:
-        for i, r in enumerate(recs):
-            f.write(">r%d\n%s\n" % (i, r))
-    F.configure(prod, symtype, strands)
-    prod.set_chunk_size(gold["chunk"])
-    prod.init_db(str(db))
-    q = prod.init_sequence_fasta(cases.READ_FROM_STRING, query)
-    qfields = _frame_fields(symtype, strands)
-    qf = F.query_frames(prod, symtype, strands, query)
-    M = prod.score_matrix()
-    _, go, ge = F.scoring(symtype)
-    try:
-        for nw in (False, True):
-            for bits in (64, 16, 8):
-                want = gold["searches"]["%s%d" % ("nw" if nw else "sw", bits)]
-                for align in (cases.COMPUTE_SCORE, cases.COMPUTE_ALIGNMENT):
-                    hits = (prod.nw_align if nw else prod.sw_align)(q, gold["k"], bits, align)
-                    got = [[h.score, h.db_id, h.db_strand, h.db_frame, qfields.index((h.q_strand, h.q_frame))] for h in hits]
-                    assert got == want["phase"], (mode, nw, bits, align)
-                st = prod.stats()
-                assert (st.overflow_8, st.overflow_16) == (want["overflow_8"], want["overflow_16"]), (mode, nw, bits)
-                if "hits" in want:
-                    assert [F.hit_record(h) for h in hits] == want["hits"], (mode, nw, bits)
-                else:
-                    # no reference record to compare with: the alignment must be the oracle's for the sequences returned
-                    for h in hits[:8]:
-                        d = np.frombuffer(h.db_seq, dtype=np.uint8)
-                        a = qf[qfields.index((h.q_strand, h.q_frame))][0]
-                        exp = port.cigar(a, d, M, go, ge, nw)
-                        assert ([h.q_start, h.q_end, h.d_start, h.d_end], h.cigar) == (list(exp[0]), exp[1]), (mode, nw, bits)
-    finally:
-        prod.free_sequence(q)
-        prod.set_chunk_size(1000)
-        prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    F.check_product_mode(prod, port, mode, tmp_path)
