@@ -260,3 +260,18 @@ def test_frames_replay_matches_reference(prod_host, ref, port, tmp_path, mode):
             if not nw and bits == 8:
                 assert want["overflow_8"] > 0, "workload must exercise the overflow lists"
     prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+
+
+def test_reference_translated_query_vectors_oracle(prod_host, port):
+    """The reference's known answers for a six-frame query (tests/algo/test_searcher.c:247-325) hold for the oracle's
+    scores of the frames the product's query reader translates (genetic code 3)."""
+    import frames as F
+    prod_host.set_output_mode(0)
+    prod_host.init_constant_scores(1, -1)
+    M = prod_host.score_matrix()
+    qf = F.query_frames(prod_host, F.TRANS_QUERY, F.BOTH, "ATGCCCAAAATTGACTTGAATAGGGGCGTGAGGAGGGGTTTTCAATACTATTTTTTG", 3)
+    assert [len(c) for c, _, _ in qf] == [19, 18, 18, 19, 18, 18]
+    rec = port.map_db("".join(l.strip() for l in open(os.path.join(cases.DATA, "short_AA.fas")) if not l.startswith(">")), False)
+    assert sorted((int(port.nw_score(rec, c, M, -1, -1)) for c, _, _ in qf), reverse=True) == [-109, -109, -110, -110, -110, -113]
+    assert sorted((int(port.sw_score(rec, c, M, -1, -1)) for c, _, _ in qf), reverse=True) == [2, 2, 2, 2, 2, 1]
+    prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
