@@ -228,3 +228,40 @@ def test_c_host_program_drop_in(prod, tmp_path):
         assert [(int(g[0]), int(g[1])) for g in got] == [(e[0], e[1]) for e in exp]
         if align == "align":
             assert [g[4] for g in got] == [e[2] for e in exp]
+
+
+def test_cli_and_benchmark_driver_match_reference_build(prod, ref, tmp_path):
+    """examples/ssa_cli (the reference example's option letters, reference src/libssa_example.c:44-196) and
+    examples/ssa_benchmark (reference benchmark/src/benchmark_queries.c:32-79) are single C sources written against
+    libssa.h; built once against libssa_b200.so and once against the compiled reference they must print the same
+    hit lines."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    refdir = os.path.join(root, "oracle", "_ref")
+    for prog in ("ssa_cli", "ssa_benchmark"):
+        subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(root, "include"), "-o", str(tmp_path / prog),
+                               os.path.join(root, "examples", prog + ".c"), "-L" + refdir, "-lssa_ref", "-Wl,-rpath," + refdir])
+    db = cases.db_path(["protein", 2000, 11, "P07327"])
+    qf = os.path.join(cases.DATA, "P07327")
+
+    def hit_lines(text):
+        return [l for l in text.split("\n") if l and not l.startswith("libssa")]
+
+    for args in (["-N", "1", "-O", "-3", "-E", "-1", "-M", "BLOSUM50", "-c", "10", "-i", qf, "-d", db, "-t", "SW", "-b", "16", "-s", "AVX2"],
+                 ["-N", "1", "-O", "-11", "-E", "-1", "-M", "BLOSUM62", "-c", "6", "-i", qf, "-d", db, "-t", "NW", "-b", "8", "-s", "SSE41", "-a"]):
+        outs = []
+        for exe in (os.path.join(root, "examples", "ssa_cli"), str(tmp_path / "ssa_cli")):
+            r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr
+            outs.append(hit_lines(r.stdout))
+        assert outs[0] == outs[1] and outs[0][0].startswith("Nr of alignments: ")
+    rows = []
+    for exe in (os.path.join(root, "examples", "ssa_benchmark"), str(tmp_path / "ssa_benchmark")):
+        r = subprocess.run([exe, "-n", "2", "-N", "1", "-b", "8,16", "-t", "SW,NW", "-d", db, qf, os.path.join(cases.DATA, "O74807")],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        lines = [l.split(",") for l in hit_lines(r.stdout)]
+        assert lines[0][:4] == ["query", "qlen", "type", "bit_width"] and len(lines) == 1 + 2 * 2 * 2
+        rows.append([l[:5] + l[9:] for l in lines[1:]])     # query, qlen, type, width, iterations, top score, top id
+    assert rows[0] == rows[1]

@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Small mixed workload for compute-sanitizer (memcheck / racecheck): every kernel family of the library runs at
+least once - packed and wide scoring tiers (single- and multi-pass), SW overflow tracking, NW saturating-tier
+emulation, arrival order, top-k, traceback, strand / reading-frame searches."""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import libssa_b200 as L  # noqa: E402
+from libssa_b200 import synth  # noqa: E402
+
+D = os.path.join(ROOT, "tests/golden/data")
+tmp = tempfile.mkdtemp()
+lib = L.load()
+lib.set_output_mode(L.OUTPUT_SILENT)
+
+q0 = open(D + "/P07327").read().split("\n", 1)[1].replace("\n", "")
+prot = os.path.join(tmp, "prot.fas")
+synth.write_fasta(prot, synth.protein_db(1500, 7, query=q0))
+lib.init_symbol_translation(L.AMINOACID)
+lib.init_score_matrix(L.MATRIX_BUILDIN, "blosum62")
+lib.init_gap_penalties(-11, -1)
+lib.init_db(prot)
+for name in ("O74807", "P07327", "P04775", "P33450"):
+    q = lib.init_sequence_fasta(L.READ_FROM_FILE, D + "/" + name)
+    for bits in (8, 16, 64):
+        h = lib.sw_align(q, 10, bits, L.COMPUTE_SCORE)
+    h = lib.nw_align(q, 10, 16, L.COMPUTE_SCORE)
+    if name == "P07327":
+        h = lib.nw_align(q, 1400, 8, L.COMPUTE_SCORE)      # ties straddle the cut-off: emulation + replay
+        h = lib.sw_align(q, 1400, 8, L.COMPUTE_SCORE)
+        h = lib.sw_align(q, 5, 16, L.COMPUTE_ALIGNMENT)
+        h = lib.nw_align(q, 5, 64, L.COMPUTE_ALIGNMENT)
+    print(name, h[0].score, flush=True)
+    lib.free_sequence(q)
+
+# nucleotide, long query (multi-pass shapes) and both strands (several frames, host replay)
+nuc = os.path.join(tmp, "nuc.fas")
+synth.write_fasta(nuc, synth.nucleotide_db(300, 11, max_len=4000))
+lib.init_symbol_translation(L.NUCLEOTIDE)
+lib.init_constant_scores(5, -4)
+lib.init_gap_penalties(-6, -2)
+lib.init_db(nuc)
+q = lib.init_sequence_fasta(L.READ_FROM_STRING, synth.random_nucleotide(5, 3000))
+print("nuc", lib.sw_align(q, 10, 16, L.COMPUTE_SCORE)[0].score, lib.nw_align(q, 10, 16, L.COMPUTE_SCORE)[0].score, flush=True)
+lib.free_sequence(q)
+lib.init_symbol_translation(L.NUCLEOTIDE, 3)
+q = lib.init_sequence_fasta(L.READ_FROM_STRING, synth.random_nucleotide(6, 400))
+print("both", lib.sw_align(q, 10, 8, L.COMPUTE_ALIGNMENT)[0].score, flush=True)
+lib.free_sequence(q)
+lib.init_symbol_translation(4, 3)   # TRANS_BOTH, both strands: 6 x 6 frames
+lib.init_score_matrix(L.MATRIX_BUILDIN, "blosum62")
+lib.init_gap_penalties(-7, -1)
+q = lib.init_sequence_fasta(L.READ_FROM_STRING, synth.random_nucleotide(6, 400))
+print("tboth", lib.sw_align(q, 10, 8, L.COMPUTE_ALIGNMENT)[0].score, flush=True)
+lib.free_sequence(q)
+lib.ssa_exit()
+print("SANITIZE_TARGET_OK")
