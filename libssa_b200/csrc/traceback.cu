@@ -10,10 +10,18 @@
 //   * direction bits per cell of a column-major Gotoh pass with strict comparisons (cigar.c:48-198);
 //   * walk: left/ext-left before up/ext-up before diagonal, looking only at the CURRENT cell (cigar.c:299-335).
 //
-// One CTA per hit sweeps the DP matrix by anti-diagonals; every cell needs its diagonal, upper and left
-// neighbour, which live in rotating per-diagonal arrays (3 x H, 2 x E, 2 x F).  All three passes share that
-// engine and differ only in the cell function and the boundary values.  Arithmetic is int32, exact for the
-// supported lengths (< 2^24 symbols: |value| < 2^31).
+// Engine: the DP matrix of a hit is cut into tiles of 256 rows x 256 columns.  ONE WARP sweeps a tile as a systolic
+// array - lane l owns 8 consecutive rows whose left-neighbour state (H, E of the previous column) lives in
+// registers, columns stream through the lanes one per step, the H/F of a lane's last row reach the next lane by
+// __shfl_up_sync - exactly the decomposition of the scoring kernels (score_kernel.cuh), in exact int32 and with the
+// reference's cell functions.  Tiles on one anti-diagonal of the tile grid are independent: one launch per tile
+// anti-diagonal processes them for all hits at once (a 10 kbp x 10 kbp pair has up to 40 tiles in flight per hit);
+// tile boundaries (bottom row H/F, right column H/E) pass through global memory.  All three passes share that
+// engine and differ only in the cell function and the boundary values.  Substitution scores come from a per-tile
+// profile in shared memory laid out [row][residue][lane] (bank-conflict free whatever residues the lanes hold).
+// The direction bytes are stored in 128-byte blocks of 8 rows x 16 columns, so that a lane writes its 8 rows of a
+// column with one 64-bit store and the backward walk - a serial chain of dependent loads - stays inside one cache
+// line for many steps.  Arithmetic is int32, exact for the supported lengths (< 2^24 symbols: |value| < 2^31).
 #include "traceback.h"
 
 #include <algorithm>
@@ -28,7 +36,9 @@
 
 namespace {
 
-constexpr int TB_THREADS = 512;
+constexpr int TB_R = 8;                 // rows per lane
+constexpr int TILE_R = 32 * TB_R;       // rows per tile
+constexpr int TILE_C = 256;             // columns per tile
 
 enum Pass { PASS_FORWARD = 0, PASS_REVERSE = 1, PASS_DIRECTIONS = 2 };
 
@@ -36,8 +46,14 @@ struct HitTask {              // one reported hit
     const uint8_t * a;        // query codes (shared by all hits)
     const uint8_t * b;        // database sequence codes
     int32_t alen, blen;
-    int32_t * scratch;        // 9 * alen int32: H[3], E[2], F[2], final HH, final EE
-    uint8_t * dir;            // (a_end+1) x (b_end+1) direction bytes, column-major
+    // tile boundaries, set 0 for the forward and reverse pass, set 1 for the direction pass (which runs beside the reverse pass)
+    int32_t * rowH[2], * rowF[2];   // [tile row][ldc]: H / F of the last row of every tile row, per column
+    int32_t * colH[2], * colE[2];   // [tile column][ldr]: H / E of the last column of every tile column, per row
+    int32_t * HHf, * EEf;     // forward pass: H / E of the last column, per row (inherited by the reverse pass)
+    int64_t * tile_key;       // per tile: partial results of the forward (best cell) / reverse (first cell) pass
+    int32_t * tile_val;
+    int32_t ldr, ldc, ntc_cap;
+    uint8_t * dir;            // direction bytes of rows 0..a_end x columns 0..b_end, blocked 8 rows x 16 columns
     int32_t * result;         // [0] score [1] a_end [2] b_end [3] a_begin [4] b_begin [5] found [6] nruns
     uint32_t * runs;          // walk output: (count << 8) | op, in walk order
     int32_t runs_cap;
@@ -50,67 +66,290 @@ struct TbParams {
 
 __device__ __forceinline__ int32_t max2( int32_t a, int32_t b ) { return a > b ? a : b; }
 
-// Sweeps rows 0..nr-1 x columns 0..nc-1 by anti-diagonals.  F(r, c, diag, h_up, f_up, h_left, e_left, &h, &e, &f)
-// computes one cell; B supplies the boundary values of row -1 / column -1.
-template<typename Cell, typename Bound>
-__device__ void sweep( int nr, int nc, int32_t * H0, int32_t * H1, int32_t * H2, int32_t * E0, int32_t * E1, int32_t * F0, int32_t * F1,
-        Cell cell, Bound bound ) {
-    int32_t * H[3] = { H0, H1, H2 };
-    int32_t * E[2] = { E0, E1 };
-    int32_t * F[2] = { F0, F1 };
-    const int ndiag = nr + nc - 1;
-    for( int d = 0; d < ndiag; d++ ) {
-        const int lo = d - nc + 1 > 0 ? d - nc + 1 : 0;
-        const int hi = d < nr - 1 ? d : nr - 1;
-        int32_t * Hc = H[d % 3];
-        const int32_t * Hp = H[( d + 2 ) % 3];   // diagonal d-1
-        const int32_t * Hpp = H[( d + 1 ) % 3];  // diagonal d-2
-        int32_t * Ec = E[d & 1];
-        const int32_t * Ep = E[( d + 1 ) & 1];
-        int32_t * Fc = F[d & 1];
-        const int32_t * Fp = F[( d + 1 ) & 1];
-        for( int r = lo + (int) threadIdx.x; r <= hi; r += blockDim.x ) {
-            const int c = d - r;
-            int32_t diag, h_up, f_up, h_left, e_left;
-            if( r == 0 ) {
-                h_up = bound.top_h( c );
-                f_up = bound.top_f( c );
-                diag = c == 0 ? bound.corner() : bound.top_diag( c );
-            }
-            else {
-                h_up = Hp[r - 1];
-                f_up = Fp[r - 1];
-                diag = c == 0 ? bound.left_h( r - 1 ) : Hpp[r - 1];
-            }
-            if( c == 0 ) {
-                h_left = bound.left_h( r );
-                e_left = bound.left_e( r );
-            }
-            else {
-                h_left = Hp[r];
-                e_left = Ep[r];
-            }
-            int32_t h, e, f;
-            cell( r, c, diag, h_up, f_up, h_left, e_left, h, e, f );
-            Hc[r] = h;
-            Ec[r] = e;
-            Fc[r] = f;
+__device__ __forceinline__ size_t dir_offset( int nrb, int r, int c ) {
+    return ( (size_t) ( c >> 4 ) * nrb + ( r >> 3 ) ) * 128 + ( ( c & 15 ) << 3 ) + ( r & 7 );
+}
+
+// boundary values of row -1 / column -1 of the three passes
+template<int PASS> struct Bound {
+    int32_t gapO, gapE, a_end, b_end;
+    bool nw;
+    const int32_t * HHf, * EEf;
+    __device__ __forceinline__ int32_t top_h( int c ) const {   // also the diagonal neighbour of (0, c+1)
+        if( PASS == PASS_FORWARD ) return 0;
+        if( PASS == PASS_REVERSE ) return -1;
+        return nw ? gapO + ( c + 1 ) * gapE : 0;
+    }
+    __device__ __forceinline__ int32_t top_f( int c ) const {
+        if( PASS == PASS_FORWARD ) return gapO;
+        if( PASS == PASS_REVERSE ) return -1;
+        return nw ? 2 * gapO + ( c + 2 ) * gapE : 0;
+    }
+    __device__ __forceinline__ int32_t corner() const { return 0; }
+    __device__ __forceinline__ int32_t left_h( int r ) const {
+        if( PASS == PASS_FORWARD ) return 0;
+        if( PASS == PASS_REVERSE ) {
+            // query positions above b_end were not reset to -1 (align.c:86-89): they keep the forward pass' last column
+            const int j = a_end - r;
+            return j > b_end ? HHf[j] : -1;
         }
-        __syncthreads();
+        return nw ? gapO + ( r + 1 ) * gapE : 0;
+    }
+    __device__ __forceinline__ int32_t left_e( int r ) const {
+        if( PASS == PASS_FORWARD ) return gapO;
+        if( PASS == PASS_REVERSE ) {
+            const int j = a_end - r;
+            return j > b_end ? EEf[j] : -1;
+        }
+        return nw ? 2 * gapO + ( r + 2 ) * gapE : 0;
+    }
+};
+
+// One tile: see the header comment.
+template<int PASS>
+__device__ __forceinline__ void tile_sweep( int32_t * prof, const HitTask * tasks, const int32_t * matrix, const TbParams prm, int diag, int maxd ) {
+    const int lane = threadIdx.x;
+    const HitTask t = tasks[blockIdx.x / maxd];
+    constexpr int SET = PASS == PASS_DIRECTIONS ? 1 : 0;
+    int32_t * const rowH = t.rowH[SET], * const rowF = t.rowF[SET], * const colH = t.colH[SET], * const colE = t.colE[SET];
+    const int slot = blockIdx.x % maxd;
+    const int32_t gapO = prm.gapO, gapE = prm.gapE;
+    const int32_t score = t.result[0], a_end = t.result[1], b_end = t.result[2];
+    const int nr = PASS == PASS_FORWARD ? t.alen : a_end + 1;
+    const int nc = PASS == PASS_FORWARD ? t.blen : b_end + 1;
+    if( PASS != PASS_FORWARD && score <= 0 && !prm.nw ) return;   // no local alignment: reported as an error by the host
+    const int ntr = ( nr + TILE_R - 1 ) / TILE_R, ntc = ( nc + TILE_C - 1 ) / TILE_C;
+    const int ti = ( diag - ( ntc - 1 ) > 0 ? diag - ( ntc - 1 ) : 0 ) + slot;
+    const int tj = diag - ti;
+    if( ti >= ntr || tj < 0 ) return;
+    const int r0 = ti * TILE_R + lane * TB_R;   // first row of this lane
+    const int c0 = tj * TILE_C;
+    const int ncols = nc - c0 < TILE_C ? nc - c0 : TILE_C;
+    const int nvalid = nr - r0 < 0 ? 0 : ( nr - r0 > TB_R ? TB_R : nr - r0 );   // real rows of this lane
+    const uint8_t * a = t.a;
+    const uint8_t * b = t.b;
+    const Bound<PASS> bound{ gapO, gapE, a_end, b_end, prm.nw != 0, t.HHf, t.EEf };
+
+    // profile of this tile's rows: forward / reverse read M[query][db] (align.c:64,106), the direction pass M[db][query] (cigar.c:79,152)
+#pragma unroll
+    for( int r = 0; r < TB_R; r++ ) {
+        const int gr = r0 + r;
+        int code = 0;
+        if( gr < nr ) code = PASS == PASS_REVERSE ? a[a_end - gr] : a[gr];
+        for( int res = 0; res < 32; res++ )
+            prof[( r * 32 + res ) * 32 + lane] = __ldg( matrix + ( PASS == PASS_DIRECTIONS ? ( res << 5 ) + code : ( code << 5 ) + res ) );
+    }
+    __syncwarp();
+
+    int32_t Hl[TB_R], El[TB_R];
+#pragma unroll
+    for( int r = 0; r < TB_R; r++ ) Hl[r] = El[r] = 0;
+    int32_t prev_up = 0, h_out = 0, f_out = 0;
+    int32_t best_val = 0, best_pos = 0x7fffffff;     // forward: best cell of this lane; reverse: first cell reaching the score
+    const int32_t * rowH_in = rowH + (size_t) ( ti > 0 ? ti - 1 : 0 ) * t.ldc;   // only read when ti > 0
+    const int32_t * rowF_in = rowF + (size_t) ( ti > 0 ? ti - 1 : 0 ) * t.ldc;
+    const int nrb = ( nr + 7 ) >> 3;
+
+    // software prefetch of the next step's column code (every lane) and top boundary (lane 0)
+    auto column_code = [&]( int cc ) -> uint32_t {
+        if( cc < 0 || cc >= ncols ) return 0;
+        return PASS == PASS_REVERSE ? b[b_end - ( c0 + cc )] : b[c0 + cc];
+    };
+    uint32_t code_n = column_code( -lane );
+    int32_t toph_n = 0, topf_n = 0;
+    if( lane == 0 ) {
+        toph_n = ti == 0 ? bound.top_h( c0 ) : rowH_in[c0];
+        topf_n = ti == 0 ? bound.top_f( c0 ) : rowF_in[c0];
+    }
+
+    const int nsteps = ncols + 31;
+    for( int s = 0; s < nsteps; s++ ) {
+        const int cc = s - lane;
+        const uint32_t code = code_n;
+        code_n = column_code( cc + 1 );
+        int32_t h_up = __shfl_up_sync( 0xffffffffu, h_out, 1 );
+        int32_t f_up = __shfl_up_sync( 0xffffffffu, f_out, 1 );
+        if( lane == 0 ) {
+            h_up = toph_n;
+            f_up = topf_n;
+            if( cc + 1 < ncols ) {
+                toph_n = ti == 0 ? bound.top_h( c0 + cc + 1 ) : rowH_in[c0 + cc + 1];
+                topf_n = ti == 0 ? bound.top_f( c0 + cc + 1 ) : rowF_in[c0 + cc + 1];
+            }
+        }
+        if( cc < 0 || cc >= ncols || nvalid == 0 ) continue;   // shuffles above are executed by all lanes
+        const int gc = c0 + cc;
+        if( cc == 0 ) {  // this lane enters the tile: left boundary and the corner above-left of its first row
+            if( tj == 0 ) {
+#pragma unroll
+                for( int r = 0; r < TB_R; r++ ) {
+                    Hl[r] = bound.left_h( r0 + r );
+                    El[r] = bound.left_e( r0 + r );
+                }
+            }
+            else {
+                const int32_t * ch = colH + (size_t) ( tj - 1 ) * t.ldr + r0;
+                const int32_t * ce = colE + (size_t) ( tj - 1 ) * t.ldr + r0;
+#pragma unroll
+                for( int r = 0; r < TB_R; r++ ) {
+                    Hl[r] = ch[r];
+                    El[r] = ce[r];
+                }
+            }
+            if( r0 == 0 )
+                prev_up = c0 == 0 ? bound.corner() : bound.top_h( c0 - 1 );
+            else if( c0 == 0 )
+                prev_up = bound.left_h( r0 - 1 );
+            else
+                prev_up = colH[(size_t) ( tj - 1 ) * t.ldr + r0 - 1];
+        }
+        int32_t hd = prev_up;
+        prev_up = h_up;
+        int32_t hu = h_up, fu = f_up;
+        const int32_t * pp = prof + ( code << 5 ) + lane;
+        uint32_t bits_lo = 0, bits_hi = 0;
+#pragma unroll
+        for( int r = 0; r < TB_R; r++ ) {
+            const int32_t v = pp[r * 1024];
+            const int32_t hl = Hl[r], el = El[r];
+            int32_t h, e, f;
+            if( PASS == PASS_DIRECTIONS ) {   // cigar.c:48-198, strict comparisons
+                uint32_t bits = 0;
+                h = hd + v;
+                f = fu;
+                e = el;
+                if( f > h ) {
+                    bits |= 1;
+                    h = f;
+                }
+                if( e > h ) {
+                    bits |= 2;
+                    h = e;
+                }
+                if( !prm.nw && h < 0 ) h = 0;
+                const int32_t open = h + gapO + gapE;
+                f += gapE;
+                e += gapE;
+                if( f > open )
+                    bits |= 4;
+                else
+                    f = open;
+                if( e > open )
+                    bits |= 8;
+                else
+                    e = open;
+                if( r < 4 )
+                    bits_lo |= bits << ( 8 * r );
+                else
+                    bits_hi |= bits << ( 8 * ( r - 4 ) );
+            }
+            else {   // align.c:56-83 / 99-127: E and F are advanced before H
+                f = max2( fu, hu + gapO ) + gapE;
+                e = max2( el, hl + gapO ) + gapE;
+                h = hd + v;
+                if( PASS == PASS_FORWARD && h < 0 ) h = 0;
+                if( f > h ) h = f;
+                if( e > h ) h = e;
+                if( PASS == PASS_FORWARD ) {
+                    // first strict maximum in (column outer, row inner) order; a lane meets its cells in that order
+                    if( h > best_val && r < nvalid ) {
+                        best_val = h;
+                        best_pos = ( cc << 3 ) | r;
+                    }
+                }
+                else {
+                    if( h >= score && best_pos == 0x7fffffff && r < nvalid ) best_pos = ( cc << 3 ) | r;
+                }
+            }
+            hd = hl;
+            Hl[r] = h;
+            El[r] = e;
+            hu = h;
+            fu = f;
+        }
+        h_out = hu;
+        f_out = fu;
+        if( PASS == PASS_DIRECTIONS )
+            *(uint2 *) ( t.dir + dir_offset( nrb, r0, gc ) ) = make_uint2( bits_lo, bits_hi );
+        if( lane == 31 ) {  // bottom boundary of this tile row (only read if a tile row follows)
+            rowH[(size_t) ti * t.ldc + gc] = h_out;
+            rowF[(size_t) ti * t.ldc + gc] = f_out;
+        }
+        if( cc == ncols - 1 ) {  // right boundary of this tile column
+            int32_t * ch = colH + (size_t) tj * t.ldr + r0;
+            int32_t * ce = colE + (size_t) tj * t.ldr + r0;
+#pragma unroll
+            for( int r = 0; r < TB_R; r++ ) {
+                ch[r] = Hl[r];
+                ce[r] = El[r];
+                if( PASS == PASS_FORWARD && gc == nc - 1 && r < nvalid ) {  // state the reverse pass inherits (align.c:86-89)
+                    t.HHf[r0 + r] = Hl[r];
+                    t.EEf[r0 + r] = El[r];
+                }
+            }
+        }
+    }
+
+    if( PASS != PASS_DIRECTIONS ) {
+        // tile result: forward = largest value, then smallest (column, row); reverse = smallest (column, row)
+        int64_t key = INT64_MAX;
+        if( best_pos != 0x7fffffff ) key = ( (int64_t) ( c0 + ( best_pos >> 3 ) ) << 32 ) | (uint32_t) ( r0 + ( best_pos & 7 ) );
+        int32_t val = PASS == PASS_FORWARD ? best_val : 0;
+        for( int o = 16; o > 0; o >>= 1 ) {
+            const int64_t k2 = __shfl_xor_sync( 0xffffffffu, key, o );
+            const int32_t v2 = __shfl_xor_sync( 0xffffffffu, val, o );
+            if( v2 > val || ( v2 == val && k2 < key ) ) {
+                val = v2;
+                key = k2;
+            }
+        }
+        if( lane == 0 ) {
+            t.tile_key[ti * t.ntc_cap + tj] = key;
+            t.tile_val[ti * t.ntc_cap + tj] = val;
+        }
     }
 }
 
-// ---- block-wide lexicographic reductions ----
-__device__ void block_best_max( int64_t & key, int32_t & val ) {  // max val, ties: min key
-    __shared__ int64_t skey[TB_THREADS];
-    __shared__ int32_t sval[TB_THREADS];
+// One launch = one anti-diagonal `diag` of the tile grid, for all hits: block = one warp = one tile.  SECOND >= 0 runs a
+// second pass beside the first (blockIdx.y selects): the reverse and the direction pass are independent of each other.
+template<int FIRST, int SECOND>
+__global__ void __launch_bounds__( 32 ) traceback_tile_kernel( const HitTask * tasks, const int32_t * matrix, TbParams prm, int diag, int maxd ) {
+    __shared__ int32_t prof[TB_R * 32 * 32];   // [row][residue][lane]
+    if( SECOND >= 0 && blockIdx.y == 1 )
+        tile_sweep < SECOND < 0 ? FIRST : SECOND > ( prof, tasks, matrix, prm, diag, maxd );
+    else
+        tile_sweep<FIRST>( prof, tasks, matrix, prm, diag, maxd );
+}
+
+// combines the tile results of a pass into the hit's result record
+template<int PASS>
+__global__ void traceback_reduce_kernel( const HitTask * tasks, TbParams prm ) {
+    const HitTask t = tasks[blockIdx.x];
+    const int32_t score = t.result[0], a_end = t.result[1], b_end = t.result[2];
+    const int nr = PASS == PASS_FORWARD ? t.alen : a_end + 1;
+    const int nc = PASS == PASS_FORWARD ? t.blen : b_end + 1;
+    const int ntr = ( nr + TILE_R - 1 ) / TILE_R, ntc = ( nc + TILE_C - 1 ) / TILE_C;
+    int64_t key = INT64_MAX;
+    int32_t val = 0;
+    if( PASS == PASS_FORWARD || score > 0 )
+        for( int i = threadIdx.x; i < ntr * ntc; i += blockDim.x ) {
+            const int idx = ( i / ntc ) * t.ntc_cap + ( i % ntc );
+            const int64_t k2 = t.tile_key[idx];
+            const int32_t v2 = t.tile_val[idx];
+            if( v2 > val || ( v2 == val && k2 < key ) ) {
+                val = v2;
+                key = k2;
+            }
+        }
+    __shared__ int64_t skey[128];
+    __shared__ int32_t sval[128];
     skey[threadIdx.x] = key;
     sval[threadIdx.x] = val;
     __syncthreads();
     for( int s = blockDim.x / 2; s > 0; s >>= 1 ) {
         if( (int) threadIdx.x < s ) {
-            int32_t v2 = sval[threadIdx.x + s];
-            int64_t k2 = skey[threadIdx.x + s];
+            const int32_t v2 = sval[threadIdx.x + s];
+            const int64_t k2 = skey[threadIdx.x + s];
             if( v2 > sval[threadIdx.x] || ( v2 == sval[threadIdx.x] && k2 < skey[threadIdx.x] ) ) {
                 sval[threadIdx.x] = v2;
                 skey[threadIdx.x] = k2;
@@ -118,158 +357,20 @@ __device__ void block_best_max( int64_t & key, int32_t & val ) {  // max val, ti
         }
         __syncthreads();
     }
-    key = skey[0];
-    val = sval[0];
-    __syncthreads();
-}
-
-__device__ void block_min_key( int64_t & key ) {
-    __shared__ int64_t skey[TB_THREADS];
-    skey[threadIdx.x] = key;
-    __syncthreads();
-    for( int s = blockDim.x / 2; s > 0; s >>= 1 ) {
-        if( (int) threadIdx.x < s && skey[threadIdx.x + s] < skey[threadIdx.x] ) skey[threadIdx.x] = skey[threadIdx.x + s];
-        __syncthreads();
-    }
-    key = skey[0];
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__( TB_THREADS ) traceback_pass_kernel( const HitTask * tasks, const int32_t * matrix, TbParams prm, int pass ) {
-    __shared__ int32_t M[1024];
-    for( int i = threadIdx.x; i < 1024; i += blockDim.x ) M[i] = matrix[i];
-    __syncthreads();
-    const HitTask t = tasks[blockIdx.x];
-    const int32_t gapO = prm.gapO, gapE = prm.gapE;
-    const uint8_t * a = t.a;
-    const uint8_t * b = t.b;
-    int32_t * S = t.scratch;
-    const int alen = t.alen, blen = t.blen;
-    int32_t * H0 = S, * H1 = S + alen, * H2 = S + 2 * alen, * E0 = S + 3 * alen, * E1 = S + 4 * alen, * F0 = S + 5 * alen,
-            * F1 = S + 6 * alen, * HHf = S + 7 * alen, * EEf = S + 8 * alen;
-
-    if( pass == PASS_FORWARD ) {
-        // align.c:49-83.  rows = query positions, columns = database positions.
-        int64_t best_key = INT64_MAX;
-        int32_t best_val = 0;
-        struct B {
-            int32_t gapO;
-            __device__ int32_t top_h( int ) const { return 0; }
-            __device__ int32_t top_f( int ) const { return gapO; }
-            __device__ int32_t top_diag( int ) const { return 0; }
-            __device__ int32_t corner() const { return 0; }
-            __device__ int32_t left_h( int ) const { return 0; }
-            __device__ int32_t left_e( int ) const { return gapO; }
-        } bound{ gapO };
-        auto cell = [&]( int r, int c, int32_t diag, int32_t h_up, int32_t f_up, int32_t h_left, int32_t e_left, int32_t & h,
-                            int32_t & e, int32_t & f ) {
-            f = max2( f_up, h_up + gapO ) + gapE;
-            e = max2( e_left, h_left + gapO ) + gapE;
-            h = diag + M[( (int) a[r] << 5 ) + b[c]];
-            if( h < 0 ) h = 0;
-            if( f > h ) h = f;
-            if( e > h ) h = e;
-            // first strict maximum in (column outer, row inner) order = largest value, then smallest (c, r)
-            const int64_t key = ( (int64_t) c << 32 ) | (uint32_t) r;
-            if( h > best_val || ( h == best_val && h > 0 && key < best_key ) ) {
-                best_val = h;
-                best_key = key;
-            }
-            if( c == blen - 1 ) {  // state the reverse pass inherits for rows it fails to re-initialise
-                HHf[r] = h;
-                EEf[r] = e;
-            }
-        };
-        sweep( alen, blen, H0, H1, H2, E0, E1, F0, F1, cell, bound );
-        block_best_max( best_key, best_val );
-        if( threadIdx.x == 0 ) {
-            t.result[0] = best_val;
-            t.result[1] = best_val > 0 ? (int32_t) ( best_key & 0xffffffff ) : 0;  // a_end
-            t.result[2] = best_val > 0 ? (int32_t) ( best_key >> 32 ) : 0;         // b_end
+    if( threadIdx.x == 0 ) {
+        key = skey[0];
+        val = sval[0];
+        if( PASS == PASS_FORWARD ) {
+            t.result[0] = val;
+            t.result[1] = val > 0 ? (int32_t) ( key & 0xffffffff ) : 0;  // a_end
+            t.result[2] = val > 0 ? (int32_t) ( key >> 32 ) : 0;         // b_end
         }
-    }
-    else if( pass == PASS_REVERSE ) {
-        // align.c:86-127 on reversed coordinates: row r <-> query position a_end - r, column c <-> db position b_end - c
-        const int32_t score = t.result[0], a_end = t.result[1], b_end = t.result[2];
-        const int nr = a_end + 1, nc = b_end + 1;
-        int64_t first_key = INT64_MAX;
-        struct B {
-            int32_t a_end, b_end;
-            const int32_t * HHf, * EEf;
-            __device__ int32_t top_h( int ) const { return -1; }
-            __device__ int32_t top_f( int ) const { return -1; }
-            __device__ int32_t top_diag( int ) const { return -1; }
-            __device__ int32_t corner() const { return 0; }
-            // query positions above b_end were not reset to -1 (align.c:86-89): they keep the forward pass' last column
-            __device__ int32_t left_h( int r ) const { int j = a_end - r; return j > b_end ? HHf[j] : -1; }
-            __device__ int32_t left_e( int r ) const { int j = a_end - r; return j > b_end ? EEf[j] : -1; }
-        } bound{ a_end, b_end, HHf, EEf };
-        auto cell = [&]( int r, int c, int32_t diag, int32_t h_up, int32_t f_up, int32_t h_left, int32_t e_left, int32_t & h,
-                            int32_t & e, int32_t & f ) {
-            f = max2( f_up, h_up + gapO ) + gapE;
-            e = max2( e_left, h_left + gapO ) + gapE;
-            h = diag + M[( (int) a[a_end - r] << 5 ) + b[b_end - c]];
-            if( f > h ) h = f;
-            if( e > h ) h = e;
-            if( h >= score ) {
-                const int64_t key = ( (int64_t) c << 32 ) | (uint32_t) r;
-                if( key < first_key ) first_key = key;
-            }
-        };
-        sweep( nr, nc, H0, H1, H2, E0, E1, F0, F1, cell, bound );
-        block_min_key( first_key );
-        if( threadIdx.x == 0 ) {
-            const bool found = first_key != INT64_MAX && score > 0;
+        else {
+            const bool found = key != INT64_MAX && score > 0;
             t.result[5] = found ? 1 : 0;
-            t.result[3] = found ? a_end - (int32_t) ( first_key & 0xffffffff ) : 0;  // a_begin
-            t.result[4] = found ? b_end - (int32_t) ( first_key >> 32 ) : 0;         // b_begin
+            t.result[3] = found ? a_end - (int32_t) ( key & 0xffffffff ) : 0;  // a_begin
+            t.result[4] = found ? b_end - (int32_t) ( key >> 32 ) : 0;         // b_begin
         }
-    }
-    else {
-        // cigar.c:48-198 restricted to the rectangle the walk can reach: rows 0..a_end, columns 0..b_end
-        const int32_t a_end = t.result[1], b_end = t.result[2];
-        const int nr = a_end + 1, nc = b_end + 1;
-        const bool nw = prm.nw != 0;
-        uint8_t * dir = t.dir;
-        struct B {
-            int32_t gapO, gapE;
-            bool nw;
-            __device__ int32_t top_h( int ) const { return 0; }  // unused by this cell function
-            __device__ int32_t top_f( int c ) const { return nw ? 2 * gapO + ( c + 2 ) * gapE : 0; }
-            __device__ int32_t top_diag( int c ) const { return nw ? gapO + c * gapE : 0; }
-            __device__ int32_t corner() const { return 0; }
-            __device__ int32_t left_h( int r ) const { return nw ? gapO + ( r + 1 ) * gapE : 0; }
-            __device__ int32_t left_e( int r ) const { return nw ? 2 * gapO + ( r + 2 ) * gapE : 0; }
-        } bound{ gapO, gapE, nw };
-        auto cell = [&]( int r, int c, int32_t diag, int32_t h_up, int32_t f_up, int32_t h_left, int32_t e_left, int32_t & h,
-                            int32_t & e, int32_t & f ) {
-            uint8_t bits = 0;
-            h = diag + M[( (int) b[c] << 5 ) + a[r]];
-            f = f_up;
-            e = e_left;
-            if( f > h ) {
-                bits |= 1;
-                h = f;
-            }
-            if( e > h ) {
-                bits |= 2;
-                h = e;
-            }
-            if( !nw && h < 0 ) h = 0;
-            const int32_t open = h + gapO + gapE;
-            f += gapE;
-            e += gapE;
-            if( f > open )
-                bits |= 4;
-            else
-                f = open;
-            if( e > open )
-                bits |= 8;
-            else
-                e = open;
-            dir[(size_t) nr * c + r] = bits;
-        };
-        sweep( nr, nc, H0, H1, H2, E0, E1, F0, F1, cell, bound );
     }
 }
 
@@ -279,12 +380,12 @@ __global__ void traceback_walk_kernel( const HitTask * tasks, int ntasks ) {
     if( k >= ntasks ) return;
     const HitTask t = tasks[k];
     const int32_t a_end = t.result[1], b_end = t.result[2], a_begin = t.result[3], b_begin = t.result[4];
-    const int nr = a_end + 1;
+    const int nrb = ( a_end + 1 + 7 ) >> 3;
     int i = a_end, j = b_end;
     int nruns = 0;
     uint32_t prev = 0, count = 0;
     while( i >= 0 && j >= 0 && i >= a_begin && j >= b_begin ) {
-        const uint8_t d = t.dir[(size_t) nr * j + i];
+        const uint8_t d = t.dir[dir_offset( nrb, i, j )];
         uint32_t op;
         if( d & ( 2 | 8 ) ) {
             j--;
@@ -356,100 +457,150 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
     }
     TbParams prm{ g_gapO, g_gapE, nw ? 1 : 0 };
 
-    // ---- stage A: sequences, scratch, results; SW forward pass finds the region end ----
+    // ---- stage A: sequences, tile boundaries, results; SW forward pass finds the region end ----
+    auto tiles_r = []( size_t rows ) { return (int) ( ( rows + TILE_R - 1 ) / TILE_R ); };
+    auto tiles_c = []( size_t cols ) { return (int) ( ( cols + TILE_C - 1 ) / TILE_C ); };
+    auto dir_bytes = []( size_t rows, size_t cols ) { return ( ( cols + 15 ) / 16 ) * ( ( rows + 7 ) / 8 ) * 128; };
     size_t off = 0;
     const size_t off_tasks = off;
     off = align_up( off + n * sizeof( HitTask ), 256 );
+    const size_t off_results = off;
+    off = align_up( off + (size_t) n * 8 * sizeof( int32_t ), 256 );
     const size_t off_query = off;
     off = align_up( off + qlen + 1, 256 );
-    std::vector<size_t> off_b( n ), off_scratch( n ), off_result( n ), off_runs( n ), off_dir( n );
+    std::vector<HitTask> tasks( n );
+    std::vector<size_t> off_b( n );
+    auto carve = [&]( size_t bytes ) {
+        const size_t at = off;
+        off = align_up( off + bytes, 256 );
+        return at;
+    };
+    std::vector<std::vector<size_t>> offs( n );
     for( int k = 0; k < n; k++ ) {
-        off_b[k] = off;
-        off = align_up( off + hits[k].db_codes.size() + 1, 256 );
-        off_scratch[k] = off;
-        off = align_up( off + 9 * qlen * sizeof( int32_t ), 256 );
-        off_result[k] = off;
-        off = align_up( off + 8 * sizeof( int32_t ), 256 );
-        off_runs[k] = off;
-        off = align_up( off + ( qlen + hits[k].db_codes.size() + 2 ) * sizeof( uint32_t ), 256 );
+        const size_t dlen = hits[k].db_codes.size();
+        const size_t ntr = (size_t) tiles_r( qlen ), ntc = (size_t) tiles_c( dlen );
+        const size_t ldr = ntr * TILE_R, ldc = ntc * TILE_C;
+        off_b[k] = carve( dlen + 1 );
+        std::vector<size_t> & o = offs[k];
+        for( int set = 0; set < 2; set++ ) {
+            o.push_back( carve( ntr * ldc * sizeof( int32_t ) ) );   // rowH
+            o.push_back( carve( ntr * ldc * sizeof( int32_t ) ) );   // rowF
+            o.push_back( carve( ntc * ldr * sizeof( int32_t ) ) );   // colH
+            o.push_back( carve( ntc * ldr * sizeof( int32_t ) ) );   // colE
+        }
+        o.push_back( carve( ldr * sizeof( int32_t ) ) );             // HHf
+        o.push_back( carve( ldr * sizeof( int32_t ) ) );             // EEf
+        o.push_back( carve( ntr * ntc * sizeof( int64_t ) ) );       // tile_key
+        o.push_back( carve( ntr * ntc * sizeof( int32_t ) ) );       // tile_val
+        o.push_back( carve( ( qlen + dlen + 2 ) * sizeof( uint32_t ) ) );  // runs
     }
     const size_t stage_a_bytes = off;
     // the direction matrices are sized after the forward pass; reserve the worst case up front so that the pool
     // does not move between the stages
     size_t worst = stage_a_bytes;
-    for( int k = 0; k < n; k++ ) worst = align_up( worst + qlen * hits[k].db_codes.size(), 256 );
+    for( int k = 0; k < n; k++ ) worst = align_up( worst + dir_bytes( qlen, hits[k].db_codes.size() ), 256 );
     uint8_t * pool = (uint8_t *) pool_reserve( worst );
 
-    std::vector<HitTask> tasks( n );
     CUDA_OK( cudaMemcpyAsync( pool + off_query, query, qlen, cudaMemcpyHostToDevice, stream ) );
     stats->h2d_bytes += qlen;
+    int ntr_max = 0, ntc_max = 0;
     for( int k = 0; k < n; k++ ) {
         HitTask & t = tasks[k];
+        const size_t dlen = hits[k].db_codes.size();
+        const std::vector<size_t> & o = offs[k];
         t.a = pool + off_query;
         t.b = pool + off_b[k];
         t.alen = (int32_t) qlen;
-        t.blen = (int32_t) hits[k].db_codes.size();
-        t.scratch = (int32_t *) ( pool + off_scratch[k] );
+        t.blen = (int32_t) dlen;
+        for( int set = 0; set < 2; set++ ) {
+            t.rowH[set] = (int32_t *) ( pool + o[4 * set] );
+            t.rowF[set] = (int32_t *) ( pool + o[4 * set + 1] );
+            t.colH[set] = (int32_t *) ( pool + o[4 * set + 2] );
+            t.colE[set] = (int32_t *) ( pool + o[4 * set + 3] );
+        }
+        t.HHf = (int32_t *) ( pool + o[8] );
+        t.EEf = (int32_t *) ( pool + o[9] );
+        t.tile_key = (int64_t *) ( pool + o[10] );
+        t.tile_val = (int32_t *) ( pool + o[11] );
+        t.ldr = tiles_r( qlen ) * TILE_R;
+        t.ldc = tiles_c( dlen ) * TILE_C;
+        t.ntc_cap = tiles_c( dlen );
         t.dir = nullptr;
-        t.result = (int32_t *) ( pool + off_result[k] );
-        t.runs = (uint32_t *) ( pool + off_runs[k] );
-        t.runs_cap = (int32_t) ( qlen + hits[k].db_codes.size() + 2 );
-        CUDA_OK( cudaMemcpyAsync( pool + off_b[k], hits[k].db_codes.data(), hits[k].db_codes.size(), cudaMemcpyHostToDevice, stream ) );
-        stats->h2d_bytes += hits[k].db_codes.size();
+        t.result = (int32_t *) ( pool + off_results ) + 8 * k;
+        t.runs = (uint32_t *) ( pool + o[12] );
+        t.runs_cap = (int32_t) ( qlen + dlen + 2 );
+        ntr_max = std::max( ntr_max, tiles_r( qlen ) );
+        ntc_max = std::max( ntc_max, tiles_c( dlen ) );
+        CUDA_OK( cudaMemcpyAsync( pool + off_b[k], hits[k].db_codes.data(), dlen, cudaMemcpyHostToDevice, stream ) );
+        stats->h2d_bytes += dlen;
     }
     std::vector<int32_t> res( 8 * n, 0 );
     if( nw ) {  // align.c:141-150: the whole rectangle
         for( int k = 0; k < n; k++ ) {
-            int32_t r[8] = { (int32_t) hits[k].hit.score, tasks[k].alen - 1, tasks[k].blen - 1, 0, 0, 1, 0, 0 };
-            CUDA_OK( cudaMemcpyAsync( tasks[k].result, r, sizeof( r ), cudaMemcpyHostToDevice, stream ) );
+            const int32_t r[8] = { (int32_t) hits[k].hit.score, tasks[k].alen - 1, tasks[k].blen - 1, 0, 0, 1, 0, 0 };
             memcpy( &res[8 * k], r, sizeof( r ) );
         }
     }
+    CUDA_OK( cudaMemcpyAsync( pool + off_results, res.data(), res.size() * sizeof( int32_t ), cudaMemcpyHostToDevice, stream ) );
     CUDA_OK( cudaMemcpyAsync( pool + off_tasks, tasks.data(), n * sizeof( HitTask ), cudaMemcpyHostToDevice, stream ) );
+    const HitTask * d_tasks = (const HitTask *) ( pool + off_tasks );
     if( !nw ) {
-        traceback_pass_kernel<<<n, TB_THREADS, 0, stream>>>( (const HitTask *) ( pool + off_tasks ), tb.d_matrix, prm, PASS_FORWARD );
-        stats->launches++;
-        for( int k = 0; k < n; k++ )
-            CUDA_OK( cudaMemcpyAsync( &res[8 * k], tasks[k].result, 8 * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
+        const int maxd = std::min( ntr_max, ntc_max );
+        for( int d = 0; d < ntr_max + ntc_max - 1; d++ )
+            traceback_tile_kernel<PASS_FORWARD, -1><<<n * maxd, 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
+        traceback_reduce_kernel<PASS_FORWARD><<<n, 128, 0, stream>>>( d_tasks, prm );
+        stats->launches += ntr_max + ntc_max;
+        CUDA_OK( cudaMemcpyAsync( res.data(), pool + off_results, res.size() * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
         CUDA_OK( cudaStreamSynchronize( stream ) );
-        stats->d2h_bytes += n * 8 * sizeof( int32_t );
+        stats->d2h_bytes += res.size() * sizeof( int32_t );
     }
 
-    // ---- stage B: direction matrices over (a_end+1) x (b_end+1), reverse pass, walk ----
+    // ---- stage B: direction matrices over (a_end+1) x (b_end+1) beside the reverse pass, then the walk ----
     off = stage_a_bytes;
+    ntr_max = ntc_max = 0;
     for( int k = 0; k < n; k++ ) {
-        const size_t cells = (size_t) ( res[8 * k + 1] + 1 ) * (size_t) ( res[8 * k + 2] + 1 );
-        off_dir[k] = off;
-        off = align_up( off + cells, 256 );
-        tasks[k].dir = pool + off_dir[k];
+        const size_t rows = (size_t) res[8 * k + 1] + 1, cols = (size_t) res[8 * k + 2] + 1;
+        tasks[k].dir = pool + carve( dir_bytes( rows, cols ) );
+        ntr_max = std::max( ntr_max, tiles_r( rows ) );
+        ntc_max = std::max( ntc_max, tiles_c( cols ) );
     }
     CUDA_OK( cudaMemcpyAsync( pool + off_tasks, tasks.data(), n * sizeof( HitTask ), cudaMemcpyHostToDevice, stream ) );
-    if( !nw ) {
-        traceback_pass_kernel<<<n, TB_THREADS, 0, stream>>>( (const HitTask *) ( pool + off_tasks ), tb.d_matrix, prm, PASS_REVERSE );
-        stats->launches++;
+    {
+        const int maxd = std::min( ntr_max, ntc_max );
+        for( int d = 0; d < ntr_max + ntc_max - 1; d++ ) {
+            if( nw )
+                traceback_tile_kernel<PASS_DIRECTIONS, -1><<<n * maxd, 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
+            else
+                traceback_tile_kernel<PASS_REVERSE, PASS_DIRECTIONS><<<dim3( n * maxd, 2 ), 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
+        }
+        if( !nw ) traceback_reduce_kernel<PASS_REVERSE><<<n, 128, 0, stream>>>( d_tasks, prm );
+        traceback_walk_kernel<<<( n + 31 ) / 32, 32, 0, stream>>>( d_tasks, n );
+        stats->launches += ntr_max + ntc_max + 1;
     }
-    traceback_pass_kernel<<<n, TB_THREADS, 0, stream>>>( (const HitTask *) ( pool + off_tasks ), tb.d_matrix, prm, PASS_DIRECTIONS );
-    traceback_walk_kernel<<<( n + 31 ) / 32, 32, 0, stream>>>( (const HitTask *) ( pool + off_tasks ), n );
-    stats->launches += 2;
-    for( int k = 0; k < n; k++ )
-        CUDA_OK( cudaMemcpyAsync( &res[8 * k], tasks[k].result, 8 * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
+    CUDA_OK( cudaMemcpyAsync( res.data(), pool + off_results, res.size() * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
     CUDA_OK( cudaStreamSynchronize( stream ) );
-    stats->d2h_bytes += n * 8 * sizeof( int32_t );
+    stats->d2h_bytes += res.size() * sizeof( int32_t );
 
-    std::vector<uint32_t> runs;
+    // run lists of all hits: one round trip
+    std::vector<std::vector<uint32_t>> all_runs( n );
     for( int k = 0; k < n; k++ ) {
         const int32_t * r = &res[8 * k];
         if( scored_sequence && !nw && r[0] != (int32_t) hits[k].hit.score )
             fatal( "libssa_b200: internal error: alignment score %d differs from search score %ld for sequence %ld", r[0],
                     (long) hits[k].hit.score, (long) hits[k].hit.db_id );
         if( !r[5] ) fatal( "Internal error in align function." );  // align.c:131
-        const int nruns = r[6];
-        runs.resize( nruns );
-        if( nruns > 0 ) {
-            CUDA_OK( cudaMemcpyAsync( runs.data(), tasks[k].runs, nruns * sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ) );
-            CUDA_OK( cudaStreamSynchronize( stream ) );
-            stats->d2h_bytes += nruns * sizeof( uint32_t );
+        all_runs[k].resize( r[6] );
+        if( r[6] > 0 ) {
+            CUDA_OK( cudaMemcpyAsync( all_runs[k].data(), tasks[k].runs, r[6] * sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ) );
+            stats->d2h_bytes += r[6] * sizeof( uint32_t );
         }
+    }
+    CUDA_OK( cudaStreamSynchronize( stream ) );
+
+    for( int k = 0; k < n; k++ ) {
+        const int32_t * r = &res[8 * k];
+        const std::vector<uint32_t> & runs = all_runs[k];
+        const int nruns = r[6];
         std::string cigar;  // cigar.c:221-263: runs front to back, count omitted when 1
         for( int i = nruns - 1; i >= 0; i-- ) {
             const uint32_t count = runs[i] >> 8;
