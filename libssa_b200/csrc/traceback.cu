@@ -107,7 +107,7 @@ template<int PASS> struct Bound {
 
 // One tile: see the header comment.
 template<int PASS>
-__device__ __forceinline__ void tile_sweep( int32_t * prof, const HitTask * tasks, const int32_t * matrix, const TbParams prm, int diag, int maxd ) {
+__device__ __forceinline__ void tile_sweep( int32_t * prof, int32_t * s_toph, int32_t * s_topf, uint8_t * s_code, const HitTask * tasks, const int32_t * matrix, const TbParams prm, int diag, int maxd ) {
     const int lane = threadIdx.x;
     const HitTask t = tasks[blockIdx.x / maxd];
     constexpr int SET = PASS == PASS_DIRECTIONS ? 1 : 0;
@@ -150,59 +150,54 @@ __device__ __forceinline__ void tile_sweep( int32_t * prof, const HitTask * task
     const int32_t * rowF_in = rowF + (size_t) ( ti > 0 ? ti - 1 : 0 ) * t.ldc;
     const int nrb = ( nr + 7 ) >> 3;
 
-    // software prefetch of the next step's column code (every lane) and top boundary (lane 0)
-    auto column_code = [&]( int cc ) -> uint32_t {
-        if( cc < 0 || cc >= ncols ) return 0;
-        return PASS == PASS_REVERSE ? b[b_end - ( c0 + cc )] : b[c0 + cc];
-    };
-    uint32_t code_n = column_code( -lane );
-    int32_t toph_n = 0, topf_n = 0;
-    if( lane == 0 ) {
-        toph_n = ti == 0 ? bound.top_h( c0 ) : rowH_in[c0];
-        topf_n = ti == 0 ? bound.top_f( c0 ) : rowF_in[c0];
+    // the tile's column codes and top boundary go through shared memory (global latency would otherwise sit on every
+    // step's critical path); every lane's left boundary is fetched before the sweep starts
+    for( int i = lane; i < ncols; i += 32 ) {
+        s_code[i] = PASS == PASS_REVERSE ? b[b_end - ( c0 + i )] : b[c0 + i];
+        s_toph[i] = ti == 0 ? bound.top_h( c0 + i ) : rowH_in[c0 + i];
+        s_topf[i] = ti == 0 ? bound.top_f( c0 + i ) : rowF_in[c0 + i];
     }
+    if( nvalid > 0 ) {
+        if( tj == 0 ) {
+#pragma unroll
+            for( int r = 0; r < TB_R; r++ ) {
+                Hl[r] = bound.left_h( r0 + r );
+                El[r] = bound.left_e( r0 + r );
+            }
+        }
+        else {
+            const int32_t * ch = colH + (size_t) ( tj - 1 ) * t.ldr + r0;
+            const int32_t * ce = colE + (size_t) ( tj - 1 ) * t.ldr + r0;
+#pragma unroll
+            for( int r = 0; r < TB_R; r++ ) {
+                Hl[r] = ch[r];
+                El[r] = ce[r];
+            }
+        }
+        // the cell above-left of this lane's first row
+        if( r0 == 0 )
+            prev_up = c0 == 0 ? bound.corner() : bound.top_h( c0 - 1 );
+        else if( c0 == 0 )
+            prev_up = bound.left_h( r0 - 1 );
+        else
+            prev_up = colH[(size_t) ( tj - 1 ) * t.ldr + r0 - 1];
+    }
+    __syncwarp();
+    uint32_t code_n = lane == 0 ? s_code[0] : 0;   // column code of the next step
 
     const int nsteps = ncols + 31;
     for( int s = 0; s < nsteps; s++ ) {
         const int cc = s - lane;
         const uint32_t code = code_n;
-        code_n = column_code( cc + 1 );
+        code_n = ( cc + 1 >= 0 && cc + 1 < ncols ) ? s_code[cc + 1] : 0;
         int32_t h_up = __shfl_up_sync( 0xffffffffu, h_out, 1 );
         int32_t f_up = __shfl_up_sync( 0xffffffffu, f_out, 1 );
+        if( cc < 0 || cc >= ncols || nvalid == 0 ) continue;   // the shuffles above are executed by all lanes
         if( lane == 0 ) {
-            h_up = toph_n;
-            f_up = topf_n;
-            if( cc + 1 < ncols ) {
-                toph_n = ti == 0 ? bound.top_h( c0 + cc + 1 ) : rowH_in[c0 + cc + 1];
-                topf_n = ti == 0 ? bound.top_f( c0 + cc + 1 ) : rowF_in[c0 + cc + 1];
-            }
+            h_up = s_toph[cc];
+            f_up = s_topf[cc];
         }
-        if( cc < 0 || cc >= ncols || nvalid == 0 ) continue;   // shuffles above are executed by all lanes
         const int gc = c0 + cc;
-        if( cc == 0 ) {  // this lane enters the tile: left boundary and the corner above-left of its first row
-            if( tj == 0 ) {
-#pragma unroll
-                for( int r = 0; r < TB_R; r++ ) {
-                    Hl[r] = bound.left_h( r0 + r );
-                    El[r] = bound.left_e( r0 + r );
-                }
-            }
-            else {
-                const int32_t * ch = colH + (size_t) ( tj - 1 ) * t.ldr + r0;
-                const int32_t * ce = colE + (size_t) ( tj - 1 ) * t.ldr + r0;
-#pragma unroll
-                for( int r = 0; r < TB_R; r++ ) {
-                    Hl[r] = ch[r];
-                    El[r] = ce[r];
-                }
-            }
-            if( r0 == 0 )
-                prev_up = c0 == 0 ? bound.corner() : bound.top_h( c0 - 1 );
-            else if( c0 == 0 )
-                prev_up = bound.left_h( r0 - 1 );
-            else
-                prev_up = colH[(size_t) ( tj - 1 ) * t.ldr + r0 - 1];
-        }
         int32_t hd = prev_up;
         prev_up = h_up;
         int32_t hu = h_up, fu = f_up;
@@ -315,10 +310,12 @@ __device__ __forceinline__ void tile_sweep( int32_t * prof, const HitTask * task
 template<int FIRST, int SECOND>
 __global__ void __launch_bounds__( 32 ) traceback_tile_kernel( const HitTask * tasks, const int32_t * matrix, TbParams prm, int diag, int maxd ) {
     __shared__ int32_t prof[TB_R * 32 * 32];   // [row][residue][lane]
+    __shared__ int32_t s_toph[TILE_C], s_topf[TILE_C];
+    __shared__ uint8_t s_code[TILE_C];
     if( SECOND >= 0 && blockIdx.y == 1 )
-        tile_sweep < SECOND < 0 ? FIRST : SECOND > ( prof, tasks, matrix, prm, diag, maxd );
+        tile_sweep < SECOND < 0 ? FIRST : SECOND > ( prof, s_toph, s_topf, s_code, tasks, matrix, prm, diag, maxd );
     else
-        tile_sweep<FIRST>( prof, tasks, matrix, prm, diag, maxd );
+        tile_sweep<FIRST>( prof, s_toph, s_topf, s_code, tasks, matrix, prm, diag, maxd );
 }
 
 // combines the tile results of a pass into the hit's result record
@@ -375,9 +372,11 @@ __global__ void traceback_reduce_kernel( const HitTask * tasks, TbParams prm ) {
 }
 
 // cigar.c:299-346: backward walk over the direction matrix, run-length encoded in walk order
+// One warp per hit, lane 0 walks: the walk is a serial chain of dependent loads with data-dependent branches, and
+// several walks in one warp would serialise each other's divergent paths.
 __global__ void traceback_walk_kernel( const HitTask * tasks, int ntasks ) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if( k >= ntasks ) return;
+    const int k = blockIdx.x;
+    if( k >= ntasks || threadIdx.x != 0 ) return;
     const HitTask t = tasks[k];
     const int32_t a_end = t.result[1], b_end = t.result[2], a_begin = t.result[3], b_begin = t.result[4];
     const int nrb = ( a_end + 1 + 7 ) >> 3;
@@ -416,6 +415,8 @@ __global__ void traceback_walk_kernel( const HitTask * tasks, int ntasks ) {
 struct TbState {
     void * d_pool = nullptr;
     size_t pool_cap = 0;
+    void * h_stage = nullptr;   // pinned staging buffer for the one upload / one download of a call
+    size_t stage_cap = 0;
     int32_t * d_matrix = nullptr;
     uint64_t matrix_version = ~0ull;
 } tb;
@@ -429,6 +430,15 @@ void * pool_reserve( size_t bytes ) {
     return tb.d_pool;
 }
 
+void * stage_reserve( size_t bytes ) {
+    if( bytes > tb.stage_cap ) {
+        if( tb.h_stage ) cudaFreeHost( tb.h_stage );
+        tb.stage_cap = bytes + bytes / 4 + 4096;
+        CUDA_OK( cudaHostAlloc( &tb.h_stage, tb.stage_cap, cudaHostAllocDefault ) );
+    }
+    return tb.h_stage;
+}
+
 size_t align_up( size_t v, size_t a ) { return ( v + a - 1 ) / a * a; }
 
 }  // namespace
@@ -436,6 +446,9 @@ size_t align_up( size_t v, size_t a ) { return ( v + a - 1 ) / a * a; }
 void traceback_release() {
     if( tb.d_pool ) cudaFree( tb.d_pool );
     if( tb.d_matrix ) cudaFree( tb.d_matrix );
+    if( tb.h_stage ) cudaFreeHost( tb.h_stage );
+    tb.h_stage = nullptr;
+    tb.stage_cap = 0;
     tb.d_pool = nullptr;
     tb.pool_cap = 0;
     tb.d_matrix = nullptr;
@@ -457,30 +470,36 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
     }
     TbParams prm{ g_gapO, g_gapE, nw ? 1 : 0 };
 
-    // ---- stage A: sequences, tile boundaries, results; SW forward pass finds the region end ----
+    // Everything is enqueued without a host round trip in between: the passes after the forward pass take their
+    // extents (a_end, b_end) from the device-side result record, launch counts and buffer sizes use the upper bounds
+    // (query length x database sequence length).  One upload (tasks, result records, sequences), one download
+    // (result records, run lists).
     auto tiles_r = []( size_t rows ) { return (int) ( ( rows + TILE_R - 1 ) / TILE_R ); };
     auto tiles_c = []( size_t cols ) { return (int) ( ( cols + TILE_C - 1 ) / TILE_C ); };
     auto dir_bytes = []( size_t rows, size_t cols ) { return ( ( cols + 15 ) / 16 ) * ( ( rows + 7 ) / 8 ) * 128; };
     size_t off = 0;
-    const size_t off_tasks = off;
-    off = align_up( off + n * sizeof( HitTask ), 256 );
-    const size_t off_results = off;
-    off = align_up( off + (size_t) n * 8 * sizeof( int32_t ), 256 );
-    const size_t off_query = off;
-    off = align_up( off + qlen + 1, 256 );
-    std::vector<HitTask> tasks( n );
-    std::vector<size_t> off_b( n );
     auto carve = [&]( size_t bytes ) {
         const size_t at = off;
         off = align_up( off + bytes, 256 );
         return at;
     };
+    // upload blob
+    const size_t off_tasks = carve( n * sizeof( HitTask ) );
+    const size_t off_query = carve( qlen + 1 );
+    std::vector<size_t> off_b( n );
+    for( int k = 0; k < n; k++ ) off_b[k] = carve( hits[k].db_codes.size() + 1 );
+    // download blob: result records (also uploaded: NW presets them), run lists
+    const size_t off_results = carve( (size_t) n * 8 * sizeof( int32_t ) );
+    const size_t upload_bytes = off;
+    std::vector<size_t> off_runs( n );
+    for( int k = 0; k < n; k++ ) off_runs[k] = carve( ( qlen + hits[k].db_codes.size() + 2 ) * sizeof( uint32_t ) );
+    const size_t download_bytes = off - off_results;
+    // device-only: tile boundaries, partial results, direction bytes
     std::vector<std::vector<size_t>> offs( n );
     for( int k = 0; k < n; k++ ) {
         const size_t dlen = hits[k].db_codes.size();
         const size_t ntr = (size_t) tiles_r( qlen ), ntc = (size_t) tiles_c( dlen );
         const size_t ldr = ntr * TILE_R, ldc = ntc * TILE_C;
-        off_b[k] = carve( dlen + 1 );
         std::vector<size_t> & o = offs[k];
         for( int set = 0; set < 2; set++ ) {
             o.push_back( carve( ntr * ldc * sizeof( int32_t ) ) );   // rowH
@@ -492,17 +511,13 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
         o.push_back( carve( ldr * sizeof( int32_t ) ) );             // EEf
         o.push_back( carve( ntr * ntc * sizeof( int64_t ) ) );       // tile_key
         o.push_back( carve( ntr * ntc * sizeof( int32_t ) ) );       // tile_val
-        o.push_back( carve( ( qlen + dlen + 2 ) * sizeof( uint32_t ) ) );  // runs
+        o.push_back( carve( dir_bytes( qlen, dlen ) ) );             // dir
     }
-    const size_t stage_a_bytes = off;
-    // the direction matrices are sized after the forward pass; reserve the worst case up front so that the pool
-    // does not move between the stages
-    size_t worst = stage_a_bytes;
-    for( int k = 0; k < n; k++ ) worst = align_up( worst + dir_bytes( qlen, hits[k].db_codes.size() ), 256 );
-    uint8_t * pool = (uint8_t *) pool_reserve( worst );
+    uint8_t * pool = (uint8_t *) pool_reserve( off );
+    uint8_t * stage = (uint8_t *) stage_reserve( std::max( upload_bytes, download_bytes ) );
 
-    CUDA_OK( cudaMemcpyAsync( pool + off_query, query, qlen, cudaMemcpyHostToDevice, stream ) );
-    stats->h2d_bytes += qlen;
+    HitTask * tasks = (HitTask *) ( stage + off_tasks );
+    memcpy( stage + off_query, query, qlen );
     int ntr_max = 0, ntc_max = 0;
     for( int k = 0; k < n; k++ ) {
         HitTask & t = tasks[k];
@@ -525,81 +540,53 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
         t.ldr = tiles_r( qlen ) * TILE_R;
         t.ldc = tiles_c( dlen ) * TILE_C;
         t.ntc_cap = tiles_c( dlen );
-        t.dir = nullptr;
+        t.dir = pool + o[12];
         t.result = (int32_t *) ( pool + off_results ) + 8 * k;
-        t.runs = (uint32_t *) ( pool + o[12] );
+        t.runs = (uint32_t *) ( pool + off_runs[k] );
         t.runs_cap = (int32_t) ( qlen + dlen + 2 );
         ntr_max = std::max( ntr_max, tiles_r( qlen ) );
         ntc_max = std::max( ntc_max, tiles_c( dlen ) );
-        CUDA_OK( cudaMemcpyAsync( pool + off_b[k], hits[k].db_codes.data(), dlen, cudaMemcpyHostToDevice, stream ) );
-        stats->h2d_bytes += dlen;
-    }
-    std::vector<int32_t> res( 8 * n, 0 );
-    if( nw ) {  // align.c:141-150: the whole rectangle
-        for( int k = 0; k < n; k++ ) {
-            const int32_t r[8] = { (int32_t) hits[k].hit.score, tasks[k].alen - 1, tasks[k].blen - 1, 0, 0, 1, 0, 0 };
-            memcpy( &res[8 * k], r, sizeof( r ) );
+        memcpy( stage + off_b[k], hits[k].db_codes.data(), dlen );
+        int32_t * r = (int32_t *) ( stage + off_results ) + 8 * k;
+        memset( r, 0, 8 * sizeof( int32_t ) );
+        if( nw ) {  // align.c:141-150: the whole rectangle
+            r[0] = (int32_t) hits[k].hit.score;
+            r[1] = t.alen - 1;
+            r[2] = t.blen - 1;
+            r[5] = 1;
         }
     }
-    CUDA_OK( cudaMemcpyAsync( pool + off_results, res.data(), res.size() * sizeof( int32_t ), cudaMemcpyHostToDevice, stream ) );
-    CUDA_OK( cudaMemcpyAsync( pool + off_tasks, tasks.data(), n * sizeof( HitTask ), cudaMemcpyHostToDevice, stream ) );
+    CUDA_OK( cudaMemcpyAsync( pool, stage, upload_bytes, cudaMemcpyHostToDevice, stream ) );
+    stats->h2d_bytes += upload_bytes;
     const HitTask * d_tasks = (const HitTask *) ( pool + off_tasks );
-    if( !nw ) {
-        const int maxd = std::min( ntr_max, ntc_max );
-        for( int d = 0; d < ntr_max + ntc_max - 1; d++ )
+    const int maxd = std::min( ntr_max, ntc_max ), ndiag = ntr_max + ntc_max - 1;
+    if( !nw ) {  // SW: the forward pass finds the region end
+        for( int d = 0; d < ndiag; d++ )
             traceback_tile_kernel<PASS_FORWARD, -1><<<n * maxd, 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
         traceback_reduce_kernel<PASS_FORWARD><<<n, 128, 0, stream>>>( d_tasks, prm );
-        stats->launches += ntr_max + ntc_max;
-        CUDA_OK( cudaMemcpyAsync( res.data(), pool + off_results, res.size() * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
-        CUDA_OK( cudaStreamSynchronize( stream ) );
-        stats->d2h_bytes += res.size() * sizeof( int32_t );
+        stats->launches += ndiag + 1;
     }
-
-    // ---- stage B: direction matrices over (a_end+1) x (b_end+1) beside the reverse pass, then the walk ----
-    off = stage_a_bytes;
-    ntr_max = ntc_max = 0;
-    for( int k = 0; k < n; k++ ) {
-        const size_t rows = (size_t) res[8 * k + 1] + 1, cols = (size_t) res[8 * k + 2] + 1;
-        tasks[k].dir = pool + carve( dir_bytes( rows, cols ) );
-        ntr_max = std::max( ntr_max, tiles_r( rows ) );
-        ntc_max = std::max( ntc_max, tiles_c( cols ) );
+    // direction bytes over (a_end+1) x (b_end+1) beside the reverse pass (SW: region begin), then the walk
+    for( int d = 0; d < ndiag; d++ ) {
+        if( nw )
+            traceback_tile_kernel<PASS_DIRECTIONS, -1><<<n * maxd, 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
+        else
+            traceback_tile_kernel<PASS_REVERSE, PASS_DIRECTIONS><<<dim3( n * maxd, 2 ), 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
     }
-    CUDA_OK( cudaMemcpyAsync( pool + off_tasks, tasks.data(), n * sizeof( HitTask ), cudaMemcpyHostToDevice, stream ) );
-    {
-        const int maxd = std::min( ntr_max, ntc_max );
-        for( int d = 0; d < ntr_max + ntc_max - 1; d++ ) {
-            if( nw )
-                traceback_tile_kernel<PASS_DIRECTIONS, -1><<<n * maxd, 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
-            else
-                traceback_tile_kernel<PASS_REVERSE, PASS_DIRECTIONS><<<dim3( n * maxd, 2 ), 32, 0, stream>>>( d_tasks, tb.d_matrix, prm, d, maxd );
-        }
-        if( !nw ) traceback_reduce_kernel<PASS_REVERSE><<<n, 128, 0, stream>>>( d_tasks, prm );
-        traceback_walk_kernel<<<( n + 31 ) / 32, 32, 0, stream>>>( d_tasks, n );
-        stats->launches += ntr_max + ntc_max + 1;
-    }
-    CUDA_OK( cudaMemcpyAsync( res.data(), pool + off_results, res.size() * sizeof( int32_t ), cudaMemcpyDeviceToHost, stream ) );
+    if( !nw ) traceback_reduce_kernel<PASS_REVERSE><<<n, 128, 0, stream>>>( d_tasks, prm );
+    traceback_walk_kernel<<<n, 32, 0, stream>>>( d_tasks, n );
+    stats->launches += ndiag + 2;
+    CUDA_OK( cudaMemcpyAsync( stage, pool + off_results, download_bytes, cudaMemcpyDeviceToHost, stream ) );
     CUDA_OK( cudaStreamSynchronize( stream ) );
-    stats->d2h_bytes += res.size() * sizeof( int32_t );
+    stats->d2h_bytes += download_bytes;
 
-    // run lists of all hits: one round trip
-    std::vector<std::vector<uint32_t>> all_runs( n );
     for( int k = 0; k < n; k++ ) {
-        const int32_t * r = &res[8 * k];
+        const int32_t * r = (const int32_t *) stage + 8 * k;
         if( scored_sequence && !nw && r[0] != (int32_t) hits[k].hit.score )
             fatal( "libssa_b200: internal error: alignment score %d differs from search score %ld for sequence %ld", r[0],
                     (long) hits[k].hit.score, (long) hits[k].hit.db_id );
         if( !r[5] ) fatal( "Internal error in align function." );  // align.c:131
-        all_runs[k].resize( r[6] );
-        if( r[6] > 0 ) {
-            CUDA_OK( cudaMemcpyAsync( all_runs[k].data(), tasks[k].runs, r[6] * sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ) );
-            stats->d2h_bytes += r[6] * sizeof( uint32_t );
-        }
-    }
-    CUDA_OK( cudaStreamSynchronize( stream ) );
-
-    for( int k = 0; k < n; k++ ) {
-        const int32_t * r = &res[8 * k];
-        const std::vector<uint32_t> & runs = all_runs[k];
+        const uint32_t * runs = (const uint32_t *) ( stage + ( off_runs[k] - off_results ) );
         const int nruns = r[6];
         std::string cigar;  // cigar.c:221-263: runs front to back, count omitted when 1
         for( int i = nruns - 1; i >= 0; i-- ) {
