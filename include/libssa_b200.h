@@ -95,6 +95,15 @@ size_t ssa_b200_host_frames_replay( const uint64_t * slot_lens, size_t nslots, s
         int buffer_max, const int32_t * scores, const int32_t * ovf8, const int32_t * ovf16, size_t hitcount,
         uint32_t * slots_out, uint8_t * frames_out, int64_t * scores_out );
 
+/*
+ * Batched searches (the reference API has one call per query, src/libssa.h:229-251): out[i] receives
+ * exactly what sw_align / nw_align( queries[i], hitcount, bit_width, align_type ) returns (free each with
+ * free_alignment).  The library overlaps the host's share of query i with the GPU's work on query i+1.
+ * nw: 0 = Smith-Waterman, 1 = Needleman-Wunsch.
+ */
+void ssa_b200_align_batch( int nw, const p_query * queries, size_t nqueries, size_t hitcount, int bit_width, int align_type,
+        p_alignment_list * out );
+
 /* copies the current 32x32 score table (index (db_symbol << 5) + query_symbol); 0 if scoring is not initialised */
 int ssa_b200_get_score_matrix( int64_t * out_1024 );
 

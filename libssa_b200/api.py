@@ -163,6 +163,17 @@ class LibSSA:
     def nw_align(self, query, hitcount, bit_width=BIT_WIDTH_16, align_type=COMPUTE_SCORE):
         return self._collect(self.lib.nw_align(query, hitcount, bit_width, align_type))
 
+    def align_batch(self, queries, hitcount, bit_width=BIT_WIDTH_16, align_type=COMPUTE_SCORE, nw=False):
+        """One hit list per query: the lists sw_align / nw_align would return, computed as one pipelined batch."""
+        n = len(queries)
+        qs = (C.c_void_p * n)(*queries)
+        out = (C.POINTER(_AlignmentList) * n)()
+        f = self.lib.ssa_b200_align_batch
+        f.restype = None
+        f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        f(1 if nw else 0, qs, n, hitcount, bit_width, align_type, out)
+        return [self._collect(out[i]) for i in range(n)]
+
     # ---- libssa_b200.h ----
     def set_device(self, device): self.lib.ssa_b200_set_device(device)
     def set_shard(self, rank, world_size): self.lib.ssa_b200_set_shard(rank, world_size)

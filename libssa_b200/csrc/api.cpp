@@ -110,22 +110,21 @@ static std::vector<QueryFrame> query_frames( p_query query ) {
     return frames;
 }
 
-static p_alignment_list run_search( p_query query, size_t hitcount, int bit_width, int align_type, int search_type ) {
+static SearchRequest make_request( p_query query, size_t hitcount, int bit_width, int align_type, int search_type ) {
     test_configuration( query );
     if( bit_width != BIT_WIDTH_64 && bit_width != BIT_WIDTH_16 && bit_width != BIT_WIDTH_8 )
         fatal( "\nunknown bit width provided: %d\n\n", bit_width );  // reference src/algo/searcher.c:115-117
-
     SearchRequest req;
     req.frames = query_frames( query );
     req.search_type = search_type;
     req.bit_width = bit_width;
     req.hitcount = hitcount;
     req.align_type = align_type;
+    return req;
+}
 
-    std::vector<HitAlignment> hits;
-    gpu_search( req, hits );
-
-    // result records: reference src/algo/aligner.c:62-93 (init_alignment), src/algo/manager.c:83-113
+// result records: reference src/algo/aligner.c:62-93 (init_alignment), src/algo/manager.c:83-113
+static p_alignment_list make_list( const SearchRequest & req, const std::vector<HitAlignment> & hits ) {
     p_alignment_list alist = (p_alignment_list) xmalloc( sizeof( alignment_list_t ) );
     alist->len = hits.size();
     alist->alignments = (p_alignment *) xmalloc( ( hits.size() ? hits.size() : 1 ) * sizeof( p_alignment ) );
@@ -148,7 +147,7 @@ static p_alignment_list run_search( p_query query, size_t hitcount, int bit_widt
         a->alignment = nullptr;
         a->alignment_len = 0;  // left uninitialised by the reference for COMPUTE_SCORE; we define it as 0
         a->align_q_start = a->align_q_end = a->align_d_start = a->align_d_end = 0;
-        if( align_type != COMPUTE_SCORE ) {
+        if( req.align_type != COMPUTE_SCORE ) {
             a->alignment = (char *) xmalloc( h.cigar.size() + 1 );
             memcpy( a->alignment, h.cigar.c_str(), h.cigar.size() + 1 );
             a->alignment_len = h.cigar.size();
@@ -160,6 +159,25 @@ static p_alignment_list run_search( p_query query, size_t hitcount, int bit_widt
         alist->alignments[i] = a;
     }
     return alist;
+}
+
+static p_alignment_list run_search( p_query query, size_t hitcount, int bit_width, int align_type, int search_type ) {
+    SearchRequest req = make_request( query, hitcount, bit_width, align_type, search_type );
+    std::vector<HitAlignment> hits;
+    gpu_search( req, hits );
+    return make_list( req, hits );
+}
+
+// Batched entry point (include/libssa_b200.h): out[i] is what sw_align / nw_align( queries[i], ... ) returns.
+API void ssa_b200_align_batch( int nw, const p_query * queries, size_t nqueries, size_t hitcount, int bit_width, int align_type,
+        p_alignment_list * out ) {
+    std::vector<SearchRequest> reqs;
+    reqs.reserve( nqueries );
+    for( size_t i = 0; i < nqueries; i++ )
+        reqs.push_back( make_request( queries[i], hitcount, bit_width, align_type, nw ? NEEDLEMAN_WUNSCH : SMITH_WATERMAN ) );
+    std::vector<std::vector<HitAlignment>> hits;
+    gpu_search_batch( reqs, hits );
+    for( size_t i = 0; i < nqueries; i++ ) out[i] = make_list( reqs[i], hits[i] );
 }
 
 API p_alignment_list sw_align( p_query query, size_t hitcount, int bit_width, int align_type ) {

@@ -133,6 +133,7 @@ struct HitAlignment {
     size_t q_start = 0, q_end = 0, d_start = 0, d_end = 0;
 };
 void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out );
+void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std::vector<HitAlignment>> & outs );
 size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64_t * scores, uint64_t * ids );
 int db_buffer_max();  // database entries per provider record for the current symbol type / strands (reference adp_init)
 void gpu_prepare_db();

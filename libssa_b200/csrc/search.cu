@@ -36,7 +36,10 @@ template<typename T> struct DevBuf {  // grow-only device buffer
     size_t cap = 0;
     void reserve( size_t n ) {
         if( n <= cap ) return;
-        if( p ) cudaFree( p );
+        if( p ) {
+            cudaDeviceSynchronize();   // a batch may still have work in flight that uses the old buffer
+            cudaFree( p );
+        }
         size_t want = n + n / 4 + 64;
         CUDA_OK( cudaMalloc( &p, want * sizeof( T ) ) );
         cap = want;
@@ -53,7 +56,10 @@ template<typename T> struct PinBuf {  // grow-only pinned host buffer
     size_t cap = 0;
     void reserve( size_t n ) {
         if( n <= cap ) return;
-        if( p ) cudaFreeHost( p );
+        if( p ) {
+            cudaDeviceSynchronize();
+            cudaFreeHost( p );
+        }
         size_t want = n + n / 4 + 64;
         CUDA_OK( cudaMallocHost( &p, want * sizeof( T ) ) );
         cap = want;
@@ -124,28 +130,32 @@ struct Ctx {
     PackedDb db;
     DevBuf<uint32_t> d_profile, d_profile_long, d_out_packed, d_counter, d_bnd, d_bnd_wide;
     DevBuf<Batch> d_long_batches;
-    PinBuf<Batch> h_long_batches;
-    PinBuf<uint32_t> h_profile_long;
+    // pinned upload staging exists twice (index ss): a batch of queries is enqueued one query ahead (gpu_search_batch)
+    int ss = 0;
+    PinBuf<Batch> h_long_batches[2];
+    PinBuf<uint32_t> h_profile_long[2];
     DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
+    DevBuf<int32_t> d_all_slot[2];      // batch: the gathered scores of the two queries in flight
     std::vector<uint32_t> order_tmp;
     DevBuf<Batch> d_wide_batches[2];
     DevBuf<uint32_t> d_profile_wide[2];
-    PinBuf<uint32_t> h_profile_wide[2];
+    PinBuf<uint32_t> h_profile_wide[2][2];
     DevBuf<uint32_t> d_order, d_wave_list, d_topk_ids;
     DevBuf<int32_t> d_topk_scores;
     DevBuf<SelectState> d_select;
-    PinBuf<SelectState> h_select;
-    PinBuf<uint32_t> h_topk_ids;
-    PinBuf<int32_t> h_topk_scores;
+    PinBuf<SelectState> h_select[2];      // top-k results, per pipeline slot
+    PinBuf<uint32_t> h_topk_ids[2], h_counts[2];
+    PinBuf<int32_t> h_topk_scores[2];
+    cudaEvent_t ev_topk[2] = { nullptr, nullptr };
     DevBuf<int16_t> d_nw_scratch;
     DevBuf<uint8_t> d_query;
     DevBuf<int32_t> d_matrix32;
     uint64_t matrix32_version = ~0ull;
     PinBuf<uint32_t> h_order;
     DevBuf<uint32_t> d_flag_list;
-    PinBuf<uint32_t> h_profile, h_list;
+    PinBuf<uint32_t> h_profile[2], h_list;
     PinBuf<int32_t> h_scores, h_first, h_pos;
-    PinBuf<Batch> h_wide_batches[2];
+    PinBuf<Batch> h_wide_batches[2][2];
     ssa_b200_stats_t stats;
 };
 
@@ -174,6 +184,7 @@ void ensure_ctx() {
     CUDA_OK( cudaEventCreate( &ctx.ev_k0 ) );
     CUDA_OK( cudaEventCreate( &ctx.ev_k1 ) );
     CUDA_OK( cudaEventCreate( &ctx.ev_end ) );
+    for( int i = 0; i < 2; i++ ) CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_topk[i], cudaEventDisableTiming ) );
     memset( &ctx.stats, 0, sizeof( ctx.stats ) );
     ctx.init = true;
 }
@@ -663,7 +674,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     PackedDb & db = ctx.db;
     if( slots.empty() ) return;
     const size_t n = slots.size();
-    ctx.h_wide_batches[slot].reserve( n );
+    ctx.h_wide_batches[ctx.ss][slot].reserve( n );
     uint64_t bnd = 0;
     for( size_t i = 0; i < n; i++ ) {
         Batch b;
@@ -675,17 +686,17 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         b.out0 = s;
         b.half = s & 1;
         bnd += b.ncols;
-        ctx.h_wide_batches[slot].p[i] = b;
+        ctx.h_wide_batches[ctx.ss][slot].p[i] = b;
     }
     ctx.d_wide_batches[slot].reserve( n );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[ctx.ss][slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
     ctx.stats.h2d_bytes += n * sizeof( Batch );
     const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
-    ctx.h_profile_wide[slot].reserve( words * npass );
-    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile_wide[slot].p + p * words, q, qlen, pl, p );
+    ctx.h_profile_wide[ctx.ss][slot].reserve( words * npass );
+    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile_wide[ctx.ss][slot].p + p * words, q, qlen, pl, p );
     ctx.d_profile_wide[slot].reserve( words * npass );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[ctx.ss][slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
     ctx.stats.h2d_bytes += words * npass * 4;
     if( npass > 1 ) ctx.d_bnd_wide.reserve( 4 * bnd + 256 );
     ctx.d_counter.reserve( 64 );
@@ -879,7 +890,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
         run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0, ctx.stream_aux );
     }
     if( n_long > 0 ) {
-        ctx.h_long_batches.reserve( n_long );
+        ctx.h_long_batches[ctx.ss].reserve( n_long );
         for( size_t i = 0; i < n_long; i++ ) {
             Batch b;
             memset( &b, 0, sizeof( b ) );
@@ -888,26 +899,26 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             b.bnd0 = db.pair_col[p];
             b.ncols = (uint32_t) ( db.pair_col[p + 1] - db.pair_col[p] );
             b.out0 = (uint32_t) p;
-            ctx.h_long_batches.p[i] = b;
+            ctx.h_long_batches[ctx.ss].p[i] = b;
         }
         ctx.d_long_batches.reserve( n_long );
         const size_t words = (size_t) ( long_R / 2 ) * 1024;
-        ctx.h_profile_long.reserve( words );
+        ctx.h_profile_long[ctx.ss].reserve( words );
         ctx.d_profile_long.reserve( words );
-        CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches.p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
+        CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches[ctx.ss].p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
         ctx.stats.h2d_bytes += n_long * sizeof( Batch );
         launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, 32, long_R, 1, ctx.d_long_batches.p, (uint32_t) n_long, ctx.d_counter.p + 8,
-                ctx.d_profile_long.p, ctx.h_profile_long.p, offset );
+                ctx.d_profile_long.p, ctx.h_profile_long[ctx.ss].p, offset );
     }
     if( use_aux ) CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
     // ---- bulk class ----
     if( b0 < bt.batches.size() ) {
         const size_t words = (size_t) ( R / 2 ) * 1024;
-        ctx.h_profile.reserve( words * npass );
+        ctx.h_profile[ctx.ss].reserve( words * npass );
         ctx.d_profile.reserve( words * npass );
         if( npass > 1 ) ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
         launch_packed_class( ctx.stream, q, qlen, nw, pl, G, R, npass, bt.d_batches.p + b0, (uint32_t) ( bt.batches.size() - b0 ), ctx.d_counter.p,
-                ctx.d_profile.p, ctx.h_profile.p, offset );
+                ctx.d_profile.p, ctx.h_profile[ctx.ss].p, offset );
     }
     if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
     if( wide_pairs < db.npairs ) {
@@ -1138,6 +1149,8 @@ void gpu_release() {
     ctx.d_bnd.release();
     ctx.d_bnd_wide.release();
     ctx.d_scores.release();
+    ctx.d_all_slot[0].release();
+    ctx.d_all_slot[1].release();
     ctx.d_arrival_scores.release();
     ctx.d_first.release();
     ctx.d_first_compact.release();
@@ -1146,17 +1159,25 @@ void gpu_release() {
     ctx.d_guard.release();
     for( int i = 0; i < 2; i++ ) {
         ctx.d_wide_batches[i].release();
-        ctx.h_wide_batches[i].release();
         ctx.d_profile_wide[i].release();
-        ctx.h_profile_wide[i].release();
+        for( int j = 0; j < 2; j++ ) {
+            ctx.h_wide_batches[i][j].release();
+            ctx.h_profile_wide[i][j].release();
+        }
+        ctx.h_long_batches[i].release();
+        ctx.h_profile_long[i].release();
+        ctx.h_profile[i].release();
+        ctx.h_select[i].release();
+        ctx.h_topk_ids[i].release();
+        ctx.h_topk_scores[i].release();
+        ctx.h_counts[i].release();
+        if( ctx.ev_topk[i] ) cudaEventDestroy( ctx.ev_topk[i] );
+        ctx.ev_topk[i] = nullptr;
     }
     ctx.d_order.release();
     ctx.d_topk_ids.release();
     ctx.d_topk_scores.release();
     ctx.d_select.release();
-    ctx.h_select.release();
-    ctx.h_topk_ids.release();
-    ctx.h_topk_scores.release();
     ctx.d_wave_list.release();
     ctx.d_nw_scratch.release();
     ctx.d_query.release();
@@ -1164,7 +1185,7 @@ void gpu_release() {
     ctx.matrix32_version = ~0ull;
     ctx.h_order.release();
     ctx.d_flag_list.release();
-    ctx.h_profile.release();
+    ctx.h_profile[ctx.ss].release();
     ctx.h_list.release();
     ctx.h_scores.release();
     ctx.h_first.release();
@@ -1180,8 +1201,8 @@ void gpu_release() {
     cudaStreamDestroy( ctx.stream );
     ctx.d_profile_long.release();
     ctx.d_long_batches.release();
-    ctx.h_long_batches.release();
-    ctx.h_profile_long.release();
+    ctx.h_long_batches[ctx.ss].release();
+    ctx.h_profile_long[ctx.ss].release();
     ctx.init = false;
 }
 
@@ -1218,85 +1239,126 @@ size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64
     return nloc;
 }
 
+// ---- top-k on the device ----
+// Radix-select the k-th largest score T and count the ties at T (topk.cuh).  If no more than k records score >= T the
+// reported set is {score >= T} whatever the arrival order, so the k hits are compacted on the device and nothing else
+// crosses PCIe.  Only when the tie at T straddles the cut-off does the reference's tie behaviour matter; then the
+// arrival-order replay of search_single runs.  Split in two so that a batch of queries can keep the GPU busy with the
+// next query while the host picks up the results of this one.
+static bool topk_applicable( PackedDb::Arrival & base, size_t k ) { return k > 0 && k < base.order.size() && !ctx.db.sorted_all.empty(); }
+
+static void enqueue_topk( const int32_t * d_all, PackedDb::Arrival & base, size_t k, bool count_overflow, int slot ) {
+    PackedDb & db = ctx.db;
+    const size_t nglob = db.sorted_all.size();
+    const size_t world = (size_t) ctx.world;
+    const size_t stride = ( nglob + world - 1 ) / world;
+    ctx.d_select.reserve( 1 );
+    ctx.h_select[slot].reserve( 1 );
+    SelectArgs sa;
+    sa.scores = d_all;
+    sa.pos = base.d_pos_of_sorted.p;
+    sa.stride = (uint32_t) stride;
+    sa.world = (uint32_t) world;
+    sa.nglobal = (uint32_t) nglob;
+    sa.state = ctx.d_select.p;
+    const uint32_t total = (uint32_t) ( stride * world );
+    const unsigned grid = std::min<unsigned>( ( total + 255 ) / 256, 148 * 8 );
+    select_init_kernel<<<1, 256, 0, ctx.stream>>>( ctx.d_select.p, (uint32_t) k );
+    const int shifts[3] = { 21, 10, 0 };
+    const uint32_t masks[3] = { 0x7ff, 0x7ff, 0x3ff };
+    for( int p = 0; p < 3; p++ ) {
+        select_hist_kernel<<<grid, 256, 0, ctx.stream>>>( sa, shifts[p], masks[p] );
+        select_pick_kernel<<<1, 1024, 0, ctx.stream>>>( ctx.d_select.p, shifts[p], masks[p], p == 2 );
+    }
+    ctx.d_topk_scores.reserve( k + 1 );
+    ctx.d_topk_ids.reserve( k + 1 );
+    select_compact_kernel<<<grid, 256, 0, ctx.stream>>>( sa, db.d_sorted_all.p, ctx.d_topk_scores.p, ctx.d_topk_ids.p, (uint32_t) k );
+    ctx.stats.launches += 8;
+    ctx.h_topk_scores[slot].reserve( k + 1 );
+    ctx.h_topk_ids[slot].reserve( k + 1 );
+    ctx.h_counts[slot].reserve( 2 );
+    ctx.h_counts[slot].p[0] = ctx.h_counts[slot].p[1] = 0;
+    if( count_overflow ) {  // the reference's overflow counters (informational, manager.c:157-160)
+        ctx.d_counter.reserve( 64 );
+        uint32_t * d_c = ctx.d_counter.p + 40;
+        CUDA_OK( cudaMemsetAsync( d_c, 0, 8, ctx.stream ) );
+        count_ge_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world, (uint32_t) nglob, 255, 65535, d_c );
+        ctx.stats.launches++;
+        CUDA_OK( cudaMemcpyAsync( ctx.h_counts[slot].p, d_c, 8, cudaMemcpyDeviceToHost, ctx.stream ) );
+    }
+    CUDA_OK( cudaMemcpyAsync( ctx.h_select[slot].p, ctx.d_select.p, 32, cudaMemcpyDeviceToHost, ctx.stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.h_topk_scores[slot].p, ctx.d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx.h_topk_ids[slot].p, ctx.d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx.ev_topk[slot], ctx.stream ) );
+    ctx.stats.d2h_bytes += 40 + k * 8;
+}
+
+// waits for the slot's results; true (and the sorted hit list) if the set does not depend on the arrival order
+static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & hits ) {
+    CUDA_OK( cudaEventSynchronize( ctx.ev_topk[slot] ) );
+    const SelectState & st = *ctx.h_select[slot].p;
+    hits.clear();
+    if( (size_t) st.count_gt + st.count_eq > k ) return false;
+    const size_t n = (size_t) st.count_gt + st.count_eq;
+    hits.resize( n );
+    for( size_t i = 0; i < n; i++ ) hits[i] = Hit{ ctx.h_topk_ids[slot].p[i], ctx.h_topk_scores[slot].p[i] };
+    std::sort( hits.begin(), hits.end(), []( const Hit & x, const Hit & y ) {
+        if( x.score != y.score ) return x.score > y.score;
+        return x.db_id > y.db_id;
+    } );
+    if( bit_width == 8 ) ctx.stats.overflow_8 = ctx.h_counts[slot].p[0];
+    if( bit_width == 8 || bit_width == 16 ) ctx.stats.overflow_16 = ctx.h_counts[slot].p[1];
+    return true;
+}
+
 // One query frame against the entry stream: top-k with the reference's one-thread tie behaviour.  Hit ids are entry
 // (slot) indices.  Every key (score, id) is distinct, so the final order does not depend on the sort algorithm.
-static void search_single( const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
+// scores of this shard's entries -> every rank; returns the gathered score vector (rank-major blocks of `stride`)
+static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw ) {
     PackedDb & db = ctx.db;
-    const size_t nloc = db.sorted_id.size();
     const size_t nglob = db.sorted_all.size();
     const size_t world = (size_t) ctx.world;
     const size_t stride = ( nglob + world - 1 ) / world;  // local positions per rank, padded
-    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
-    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
     ctx.d_scores.reserve( stride + 2 );
     score_shard( query, qlen, nw );
-
     // ---- shard results -> every rank (NCCL all-gather over NVLink, supplied by the host language) ----
-    int32_t * d_all = ctx.d_scores.p;
-    if( world > 1 ) {
-        ctx.d_gathered.reserve( stride * world + 2 );
-        gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
-        d_all = ctx.d_gathered.p;
-    }
+    if( world == 1 ) return ctx.d_scores.p;
+    ctx.d_gathered.reserve( stride * world + 2 );
+    gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
+    return ctx.d_gathered.p;
+}
 
+static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits );
 
-    // ---- top-k on the device ----
-    // Radix-select the k-th largest score T and count the ties at T (topk.cuh).  If no more than k records score
-    // >= T the reported set is {score >= T} whatever the arrival order, so the k hits are compacted on the device
-    // and nothing else crosses PCIe.  Only when the tie at T straddles the cut-off does the reference's tie
-    // behaviour matter; then the arrival-order replay below runs.
+static void search_single( const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
+    PackedDb & db = ctx.db;
+    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
+    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
+    const int32_t * d_all = score_query( query, qlen, nw );
+    // ---- top-k on the device (see enqueue_topk) ----
     const size_t chunk = g_chunk_size * (size_t) db.buffer_max;  // entries per reference chunk (db_adapter.c:196)
-    const bool use_gpu_arrival = chunk <= (size_t) ARRIVAL_MAX_CHUNK;
-    bool fast_done = false;
+    PackedDb::Arrival & base = arrival_for( req.bit_width, chunk, chunk <= (size_t) ARRIVAL_MAX_CHUNK );  // validity: records the reference reaches
     hits.clear();
-    {
-        PackedDb::Arrival & base = arrival_for( req.bit_width, chunk, use_gpu_arrival );  // validity: records the reference reaches
-        const size_t n_valid = base.order.size();
-        const size_t k = req.hitcount;
-        if( k > 0 && k < n_valid && nglob > 0 ) {
-            ctx.d_select.reserve( 1 );
-            ctx.h_select.reserve( 1 );
-            SelectArgs sa;
-            sa.scores = d_all;
-            sa.pos = base.d_pos_of_sorted.p;
-            sa.stride = (uint32_t) stride;
-            sa.world = (uint32_t) world;
-            sa.nglobal = (uint32_t) nglob;
-            sa.state = ctx.d_select.p;
-            const uint32_t total = (uint32_t) ( stride * world );
-            const unsigned grid = std::min<unsigned>( ( total + 255 ) / 256, 148 * 8 );
-            select_init_kernel<<<1, 256, 0, ctx.stream>>>( ctx.d_select.p, (uint32_t) k );
-            const int shifts[3] = { 21, 10, 0 };
-            const uint32_t masks[3] = { 0x7ff, 0x7ff, 0x3ff };
-            for( int p = 0; p < 3; p++ ) {
-                select_hist_kernel<<<grid, 256, 0, ctx.stream>>>( sa, shifts[p], masks[p] );
-                select_pick_kernel<<<1, 1024, 0, ctx.stream>>>( ctx.d_select.p, shifts[p], masks[p], p == 2 );
-            }
-            ctx.d_topk_scores.reserve( k + 1 );
-            ctx.d_topk_ids.reserve( k + 1 );
-            select_compact_kernel<<<grid, 256, 0, ctx.stream>>>( sa, db.d_sorted_all.p, ctx.d_topk_scores.p, ctx.d_topk_ids.p, (uint32_t) k );
-            ctx.stats.launches += 8;
-            ctx.h_topk_scores.reserve( k + 1 );
-            ctx.h_topk_ids.reserve( k + 1 );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_select.p, ctx.d_select.p, 32, cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_topk_scores.p, ctx.d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_topk_ids.p, ctx.d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += 32 + k * 8;
-            const SelectState & st = *ctx.h_select.p;
-            if( (size_t) st.count_gt + st.count_eq <= k ) {  // no tie straddles the cut-off: the set is order-independent
-                const size_t n = (size_t) st.count_gt + st.count_eq;
-                hits.resize( n );
-                for( size_t i = 0; i < n; i++ ) hits[i] = Hit{ ctx.h_topk_ids.p[i], ctx.h_topk_scores.p[i] };
-                std::sort( hits.begin(), hits.end(), []( const Hit & x, const Hit & y ) {
-                    if( x.score != y.score ) return x.score > y.score;
-                    return x.db_id > y.db_id;
-                } );
-                fast_done = true;
-            }
-        }
+    if( topk_applicable( base, req.hitcount ) ) {
+        enqueue_topk( d_all, base, req.hitcount, !nw && ( req.bit_width == 8 || req.bit_width == 16 ), 0 );
+        if( collect_topk( req.hitcount, req.bit_width, 0, hits ) ) return;
     }
+    select_replay( d_all, query, qlen, req, hits );
+}
+
+// The reference's tie behaviour in full: which records overflow a narrow tier and where, the heap-arrival order of the
+// emulated one-thread run, and the heap replay (used when ties straddle the cut-off of the hit list).
+static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
+    PackedDb & db = ctx.db;
+    const size_t nglob = db.sorted_all.size();
+    const size_t world = (size_t) ctx.world;
+    const size_t stride = ( nglob + world - 1 ) / world;
+    const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
+    const size_t chunk = g_chunk_size * (size_t) db.buffer_max;
+    const bool use_gpu_arrival = chunk <= (size_t) ARRIVAL_MAX_CHUNK;
+    const bool fast_done = false;
+    hits.clear();
 
     // ---- which records would the reference have pushed through its overflow cascade? (SW only) ----
     // A record overflows the 8-bit tier when its score reaches 255 and the 16-bit tier at 65535
@@ -1440,19 +1502,7 @@ static void search_single( const uint8_t * query, size_t qlen, const SearchReque
         d_pos = &ctx.d_pos_tmp;
     }
     if( fast_done ) {
-        if( !nw && ( req.bit_width == 8 || req.bit_width == 16 ) ) {  // the reference's overflow counters (informational)
-            ctx.d_counter.reserve( 64 );
-            uint32_t * d_c = ctx.d_counter.p + 40;
-            CUDA_OK( cudaMemsetAsync( d_c, 0, 8, ctx.stream ) );
-            const uint32_t total = (uint32_t) ( stride * world );
-            count_ge_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world, (uint32_t) nglob, 255, 65535, d_c );
-            ctx.stats.launches++;
-            uint32_t c[2];
-            CUDA_OK( cudaMemcpyAsync( c, d_c, 8, cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            if( req.bit_width == 8 ) ctx.stats.overflow_8 = c[0];
-            ctx.stats.overflow_16 = c[1];
-        }
+        // nothing to replay
     }
     else if( narr > 0 && nglob > 0 ) {
         ctx.d_arrival_scores.reserve( narr + 1 );
@@ -1573,47 +1623,17 @@ static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh
     ctx.stats.overflow_8 = n8;
     ctx.stats.overflow_16 = n16;
 }
-void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
-    const double t_call = wall_ms();
-    build_db();
-    PackedDb & db = ctx.db;
-    const size_t nloc = db.sorted_id.size();
+// ---- result records: reference src/algo/aligner.c:62-93 ----
+// The reference rebuilds the database side from the record with us_prepare_sequence( seq, len, frame, strand )
+// (src/util/util_sequence.c:384-417): nucleotide records always come back as the forward strand, and a translated
+// record of a one-strand search is translated from the complementary strand whichever strand was scored.  The
+// alignment is computed on that sequence; reproduced as is.
+static void finish_results( const SearchRequest & req, const std::vector<FrameHit> & fh, std::vector<HitAlignment> & out, cudaStream_t tb_stream ) {
+    const uint32_t bm = (uint32_t) ctx.db.buffer_max;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
-    const uint32_t bm = (uint32_t) db.buffer_max;
-    out.clear();
-    ctx.stats.launches = 0;
-    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
-    ctx.stats.wide_tier_seqs = 0;
-    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
-    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
-
-    std::vector<FrameHit> fh;
-    bool done = false;
-    if( req.frames.size() == 1 ) {
-        std::vector<Hit> hits;
-        search_single( req.frames[0].seq, req.frames[0].len, req, hits );
-        // entries of one record that tie on the score are ordered by the C library's sort in the reference: replay then
-        done = true;
-        for( size_t i = 1; i < hits.size() && bm > 1; i++ )
-            if( hits[i].score == hits[i - 1].score && hits[i].db_id / bm == hits[i - 1].db_id / bm ) done = false;
-        if( done ) {
-            fh.resize( hits.size() );
-            for( size_t i = 0; i < hits.size(); i++ ) fh[i] = FrameHit{ (uint32_t) hits[i].db_id, 0, hits[i].score };
-        }
-    }
-    if( !done ) search_frames( req, fh );
-
-    if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
-        print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
-                (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
-
-    // ---- result records: reference src/algo/aligner.c:62-93 ----
-    // The reference rebuilds the database side from the record with us_prepare_sequence( seq, len, frame, strand )
-    // (src/util/util_sequence.c:384-417): nucleotide records always come back as the forward strand, and a translated
-    // record of a one-strand search is translated from the complementary strand whichever strand was scored.  The
-    // alignment is computed on that sequence; reproduced as is.
     const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
     const signed char * map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
+    out.clear();
     out.resize( fh.size() );
     bool scored_sequence = true;  // the alignment runs on the very sequence that was scored
     for( size_t i = 0; i < fh.size(); i++ ) {
@@ -1644,7 +1664,7 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     }
     if( req.align_type == COMPUTE_ALIGNMENT && !out.empty() ) {
         if( req.frames.size() == 1 ) {
-            traceback_hits( ctx.stream, req.frames[0].seq, req.frames[0].len, nw, out, &ctx.stats, scored_sequence );
+            traceback_hits( tb_stream, req.frames[0].seq, req.frames[0].len, nw, out, &ctx.stats, scored_sequence );
         }
         else {
             for( size_t q = 0; q < req.frames.size(); q++ ) {
@@ -1656,11 +1676,51 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
                         group.push_back( std::move( out[i] ) );
                     }
                 if( group.empty() ) continue;
-                traceback_hits( ctx.stream, req.frames[q].seq, req.frames[q].len, nw, group, &ctx.stats, scored_sequence );
+                traceback_hits( tb_stream, req.frames[q].seq, req.frames[q].len, nw, group, &ctx.stats, scored_sequence );
                 for( size_t j = 0; j < where.size(); j++ ) out[where[j]] = std::move( group[j] );
             }
         }
     }
+}
+
+static void reset_call_stats() {
+    ctx.stats.launches = 0;
+    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
+    ctx.stats.wide_tier_seqs = 0;
+    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
+}
+
+void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
+    const double t_call = wall_ms();
+    build_db();
+    PackedDb & db = ctx.db;
+    const size_t nloc = db.sorted_id.size();
+    const uint32_t bm = (uint32_t) db.buffer_max;
+    out.clear();
+    reset_call_stats();
+    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+
+    std::vector<FrameHit> fh;
+    bool done = false;
+    if( req.frames.size() == 1 ) {
+        std::vector<Hit> hits;
+        search_single( req.frames[0].seq, req.frames[0].len, req, hits );
+        // entries of one record that tie on the score are ordered by the C library's sort in the reference: replay then
+        done = true;
+        for( size_t i = 1; i < hits.size() && bm > 1; i++ )
+            if( hits[i].score == hits[i - 1].score && hits[i].db_id / bm == hits[i - 1].db_id / bm ) done = false;
+        if( done ) {
+            fh.resize( hits.size() );
+            for( size_t i = 0; i < hits.size(); i++ ) fh[i] = FrameHit{ (uint32_t) hits[i].db_id, 0, hits[i].score };
+        }
+    }
+    if( !done ) search_frames( req, fh );
+
+    if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
+        print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
+                (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
+
+    finish_results( req, fh, out, ctx.stream );
 
     float ms = 0;
     if( nloc ) {
@@ -1669,6 +1729,76 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     }
     cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
     ctx.stats.device_ms = ms;
+    ctx.stats.call_ms = wall_ms() - t_call;
+}
+
+// A batch of independent queries with the same search parameters: the results are those of one
+// gpu_search per query.  Queries that take the device-side top-k path are software-pipelined: the scoring and
+// selection kernels of query i+1 are enqueued before the host waits for the results of query i, so the GPU does not
+// idle during the host's share of a call (result records, launches, the PCIe round trip); alignments of query i run on
+// the auxiliary stream beside the scoring of query i+1.  Device buffers are shared (one in-order stream: the copies
+// of query i leave before query i+1 overwrites them), pinned staging buffers exist twice.
+void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std::vector<HitAlignment>> & outs ) {
+    const double t_call = wall_ms();
+    build_db();
+    PackedDb & db = ctx.db;
+    const size_t n = reqs.size();
+    outs.assign( n, std::vector<HitAlignment>() );
+    bool pipelined = db.buffer_max == 1 && n > 1;
+    for( const SearchRequest & r : reqs ) pipelined = pipelined && r.frames.size() == 1;
+    if( !pipelined ) {
+        for( size_t i = 0; i < n; i++ ) gpu_search( reqs[i], outs[i] );
+        return;
+    }
+    reset_call_stats();
+    const size_t nglob = db.sorted_all.size();
+    const size_t world = (size_t) ctx.world;
+    const size_t stride = ( nglob + world - 1 ) / world;
+    uint64_t cells = 0;
+    bool armed[2] = { false, false };
+    const size_t chunk = g_chunk_size;
+    auto enqueue = [&]( size_t i ) {
+        const SearchRequest & r = reqs[i];
+        const int slot = (int) ( i & 1 );
+        ctx.ss = slot;
+        const bool nw = r.search_type == NEEDLEMAN_WUNSCH;
+        const int32_t * d_all = score_query( r.frames[0].seq, r.frames[0].len, nw );
+        // the replay path of this query, should it be needed, runs after the next query's scoring has overwritten d_all
+        ctx.d_all_slot[slot].reserve( stride * world + 2 );
+        if( nglob ) CUDA_OK( cudaMemcpyAsync( ctx.d_all_slot[slot].p, d_all, stride * world * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx.stream ) );
+        PackedDb::Arrival & base = arrival_for( r.bit_width, chunk, chunk <= (size_t) ARRIVAL_MAX_CHUNK );
+        armed[slot] = topk_applicable( base, r.hitcount );
+        if( armed[slot] ) enqueue_topk( d_all, base, r.hitcount, !nw && ( r.bit_width == 8 || r.bit_width == 16 ), slot );
+    };
+    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    enqueue( 0 );
+    for( size_t i = 0; i < n; i++ ) {
+        if( i + 1 < n ) enqueue( i + 1 );
+        const SearchRequest & r = reqs[i];
+        const int slot = (int) ( i & 1 );
+        std::vector<Hit> hits;
+        ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
+        if( !( armed[slot] && collect_topk( r.hitcount, r.bit_width, slot, hits ) ) ) {
+            // ties straddle the cut-off (or the hit count covers the database): the arrival-order replay, from this query's
+            // own copy of the scores; it queues behind the next query's scoring
+            ctx.ss = slot;
+            select_replay( ctx.d_all_slot[slot].p, r.frames[0].seq, r.frames[0].len, r, hits );
+        }
+        if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )
+            print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
+                    (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
+        cells += (uint64_t) r.frames[0].len * db.local_residues;
+        std::vector<FrameHit> fh( hits.size() );
+        for( size_t j = 0; j < hits.size(); j++ ) fh[j] = FrameHit{ (uint32_t) hits[j].db_id, 0, hits[j].score };
+        finish_results( r, fh, outs[i], ctx.stream_aux );
+    }
+    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    ctx.ss = 0;
+    float ms = 0;
+    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
+    ctx.stats.device_ms = ms;
+    ctx.stats.score_kernel_ms = 0;
+    ctx.stats.cells = cells;
     ctx.stats.call_ms = wall_ms() - t_call;
 }
 

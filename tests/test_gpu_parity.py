@@ -265,3 +265,60 @@ def test_cli_and_benchmark_driver_match_reference_build(prod, ref, tmp_path):
         assert lines[0][:4] == ["query", "qlen", "type", "bit_width"] and len(lines) == 1 + 2 * 2 * 2
         rows.append([l[:5] + l[9:] for l in lines[1:]])     # query, qlen, type, width, iterations, top score, top id
     assert rows[0] == rows[1]
+
+
+def _key(h, align):
+    return (h.score, h.db_id) + ((h.cigar, h.q_start, h.q_end, h.d_start, h.d_end) if align else ())
+
+
+def test_batched_queries_equal_single_calls(prod, ref):
+    """ssa_b200_align_batch: the pipelined batch returns, query by query, the lists of single
+    sw_align / nw_align calls - which in turn are the compiled reference's (checked here for a sample of the queries).
+    The batch mixes query lengths (different kernel shapes, buffer growth mid-batch), queries whose hit list has ties
+    across the cut-off (full replay path inside the pipeline) and a hit count larger than the database."""
+    from libssa_b200 import synth
+    case = {"symtype": cases.AMINOACID, "scoring": "blosum62", "gaps": [-11, -1], "db": ["protein", 3000, 31, "P07327"], "query": "P07327", "runs": []}
+    q0 = cases.configure(prod, case)
+    prod.free_sequence(q0)
+    rng = np.random.default_rng(5)
+    texts = [cases.query_text(n) for n in ("P07327", "O74807", "P27895", "P56980")]
+    texts += [synth.random_protein(rng, int(n)) for n in (35, 64, 200, 333, 700, 1300, 90, 410)]
+    queries = [prod.init_sequence_fasta(cases.READ_FROM_STRING, t) for t in texts]
+    try:
+        for nw, bits, k, align in ((False, 8, 10, 0), (True, 16, 10, 1), (False, 16, 60, 0), (True, 8, 25, 0), (False, 64, 5000, 0), (False, 16, 7, 1)):
+            single = [[_key(h, align) for h in (prod.nw_align if nw else prod.sw_align)(q, k, bits, align)] for q in queries]
+            batch = [[_key(h, align) for h in hits] for hits in prod.align_batch(queries, k, bits, align, nw=nw)]
+            assert batch == single, (nw, bits, k, align)
+            again = [[_key(h, align) for h in (prod.nw_align if nw else prod.sw_align)(q, k, bits, align)] for q in queries[:3]]
+            assert again == single[:3]          # the pipeline leaves no state behind
+        # sample against the reference
+        cases.configure(ref, case)
+        for t, q in list(zip(texts, queries))[:3]:
+            rq = ref.init_sequence_fasta(cases.READ_FROM_STRING, t)
+            want = [_key(h, 1) for h in ref.nw_align(rq, 10, 16, 1)]
+            ref.free_sequence(rq)
+            assert [_key(h, 1) for h in prod.align_batch([q, q], 10, 16, 1, nw=True)[1]] == want
+    finally:
+        for q in queries:
+            prod.free_sequence(q)
+
+
+def test_batched_queries_multi_frame_fallback(prod, tmp_path):
+    """batches of multi-frame searches run query by query (no pipelining) and must still equal single calls"""
+    import frames as F
+    recs, query = F.workload(F.TRANS_QUERY)
+    db = tmp_path / "db.fas"
+    with open(db, "w") as f:
+        for i, r in enumerate(recs):
+            f.write(">r%d\n%s\n" % (i, r))
+    F.configure(prod, F.TRANS_QUERY, F.BOTH)
+    prod.init_db(str(db))
+    qs = [prod.init_sequence_fasta(cases.READ_FROM_STRING, query[i:] + query[:i]) for i in (0, 7, 50)]
+    try:
+        single = [[(h.score, h.db_id, h.q_strand, h.q_frame, h.cigar) for h in prod.sw_align(q, 12, 8, 1)] for q in qs]
+        batch = [[(h.score, h.db_id, h.q_strand, h.q_frame, h.cigar) for h in hits] for hits in prod.align_batch(qs, 12, 8, 1)]
+        assert batch == single
+    finally:
+        for q in qs:
+            prod.free_sequence(q)
+        prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
