@@ -18,9 +18,11 @@
 //   * PACKED tier: every 32-bit register holds the same DP cell of TWO database sequences (A in the high, B in the
 //     low 16 bits): inter-sequence SIMD-in-word.  All arithmetic is one SASS instruction per packed word:
 //     VIADD.16x2 (FMA-side pipe), VIMNMX3.S16x2[.RELU] and VIADDMNMX.S16x2 (ALU pipe, DPX);
-//   * substitution scores come from a query profile in shared memory laid out [row quad][residue][lane] (64-bit
-//     entries), so a warp-wide lookup is bank-conflict free whatever residues the lanes hold: one LDS.64 fetches the
-//     scores of four query rows for sequence A resp. B, PRMT interleaves them into the (A:B) words of the rows;
+//   * substitution scores come from a query profile in shared memory laid out [row quad][residue][lane], so a
+//     warp-wide lookup is bank-conflict free whatever residues the lanes hold.  For the first MR rows of a lane an
+//     entry is 128 bits - four rows, one ZERO-EXTENDED int16 each - and the (A:B) word of a row is one multiply-add
+//     a * 65536 + b on the FMA-side pipe (IMAD); for the remaining rows an entry is 64 bits - four rows, two per
+//     word - and a PRMT on the ALU pipe interleaves A and B (see merge_rows);
 //   * WIDE tier (PACKED=false): the same systolic array on plain int32 for the (rare) sequences whose scores
 //     cannot be guaranteed to fit 16 bits - the counterpart of the reference's 16->64 bit overflow cascade.
 //     Optionally tracks the first column whose running maximum reaches 255 / 65535, which is what the
@@ -57,6 +59,7 @@ struct ScoreArgs {
     uint32_t * counter;        // work queue head
     const uint32_t * profile;  // this pass' query profile, laid out for shared memory
     uint32_t group;            // lanes per systolic array: 4, 8, 16 or 32
+    uint32_t k65536;           // the constant 65536 (see the profile merge in score_kernel)
     uint32_t qr_word;          // gapO + gapE as the tier's register word (packed: replicated in both halves)
     uint32_t rg_word;          // gapE likewise
     int32_t gap_open_extend;   // gapO + gapE (negative)
@@ -112,8 +115,22 @@ __device__ __forceinline__ uint2 lds64( uint32_t addr ) {
     return v;
 }
 
+__device__ __forceinline__ uint4 lds128( uint32_t addr ) {
+    uint4 v;
+    asm volatile( "ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"( v.x ), "=r"( v.y ), "=r"( v.z ), "=r"( v.w ) : "r"( addr ) );
+    return v;
+}
+
+// Packed tier: rows of a lane whose profile entries hold one zero-extended int16 per 32-bit word (merged by IMAD);
+// the other R - MR rows hold two scores per word (merged by PRMT).  The IMAD form pays where the ALU pipe throttles:
+// the shapes with 3-4 resident CTAs per SM (R <= 16: +5 % [B200]).  The 2-CTA shapes (R >= 24) are issue-bound at
+// 4 warps per scheduler and gain nothing from it (measured -1..+2 %), so they keep the smaller PRMT profile.
+__host__ __device__ constexpr int merge_rows( int R ) { return R <= 16 ? R : 0; }
+
 // words of shared memory the profile of one pass needs
-template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() { return PACKED ? ( R / 2 ) * 1024 : R * 1024; }
+template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
+    return PACKED ? merge_rows( R ) * 1024 + ( ( R - merge_rows( R ) ) / 2 ) * 1024 : R * 1024;
+}
 
 // resident CTAs per SM the register allocator has to make room for (64K registers / 256 threads / blocks)
 template<bool PACKED, int R> __host__ __device__ constexpr int min_blocks() { return PACKED ? ( R <= 12 ? 4 : ( R <= 20 ? 3 : 2 ) ) : 2; }
@@ -142,7 +159,12 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     const bool is_top = gl == 0;
     const bool is_bottom = gl == gmask;
     // packed tier: 64-bit entries [row quad][residue][lane] = two (row pair) words; wide tier: 32-bit entries [row][residue][lane]
-    const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * ( PACKED ? 8 : 4 );
+    constexpr int MR = PACKED ? merge_rows( R ) : 0;
+    // packed tier: 128-bit entries for the first MR rows, then 64-bit entries; wide tier: 32-bit entries [row][residue][lane]
+    const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * ( PACKED ? 16 : 4 );
+    const uint32_t prof_base16 = (uint32_t) __cvta_generic_to_shared( prof ) + MR * 4096 + lane * 8;
+    const uint32_t K65536 = a.k65536;    // 65536 as a kernel argument: the merge stays an IMAD with a constant-bank operand
+                                         // (FMA-side pipe) instead of being strength-reduced to a shift/LEA on the ALU pipe
     const T QR = (T) a.qr_word;   // gapO + gapE, replicated per half for the packed tier
     const T RG = (T) a.rg_word;   // gapE
     const int row0 = a.rowbase + gl * R;
@@ -178,18 +200,39 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         T hd = diag;
         diag = h_in;
         if( PACKED ) {
-            const uint32_t pa = prof_base + ( ( ci & 31u ) << 8 );
-            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 8 );
+            const uint32_t pa = prof_base + ( ( ci & 31u ) << 9 );
+            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 9 );
+            const uint32_t pa16 = prof_base16 + ( ( ci & 31u ) << 8 );
+            const uint32_t pb16 = prof_base16 + ( ( ( ci >> 5 ) & 31u ) << 8 );
             T hd2 = hd;
 #pragma unroll
             for( int k2 = 0; k2 < R / 4; k2++ ) {
-                const uint2 la2 = lds64( pa + k2 * 8192 ), lb2 = lds64( pb + k2 * 8192 );
+                const bool m32 = 4 * k2 < MR;
+                uint2 la2 = make_uint2( 0, 0 ), lb2 = make_uint2( 0, 0 );
+                uint4 la4 = make_uint4( 0, 0, 0, 0 ), lb4 = make_uint4( 0, 0, 0, 0 );
+                if( m32 ) {
+                    la4 = lds128( pa + k2 * 16384 );
+                    lb4 = lds128( pb + k2 * 16384 );
+                }
+                else {
+                    la2 = lds64( pa16 + ( k2 - MR / 4 ) * 8192 );
+                    lb2 = lds64( pb16 + ( k2 - MR / 4 ) * 8192 );
+                }
 #pragma unroll
                 for( int j = 0; j < 2; j++ ) {
                     const int k = 2 * k2 + j;
-                    const uint32_t la = j ? la2.y : la2.x, lb = j ? lb2.y : lb2.x;
-                    const T t0 = A::add( hd2, (T) __byte_perm( lb, la, 0x5410 ) );
-                    const T t1 = A::add( Hp[2 * k], (T) __byte_perm( lb, la, 0x7632 ) );
+                    uint32_t v0, v1;   // (A:B) substitution scores of rows 2k, 2k+1
+                    if( m32 ) {
+                        v0 = ( j ? la4.z : la4.x ) * K65536 + ( j ? lb4.z : lb4.x );
+                        v1 = ( j ? la4.w : la4.y ) * K65536 + ( j ? lb4.w : lb4.y );
+                    }
+                    else {
+                        const uint32_t la = j ? la2.y : la2.x, lb = j ? lb2.y : lb2.x;
+                        v0 = __byte_perm( lb, la, 0x5410 );
+                        v1 = __byte_perm( lb, la, 0x7632 );
+                    }
+                    const T t0 = A::add( hd2, (T) v0 );
+                    const T t1 = A::add( Hp[2 * k], (T) v1 );
                     hd2 = Hp[2 * k + 1];
                     T hq;
                     Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
@@ -386,27 +429,54 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // needs neither, so the two F chains overlap.  The diagonal candidate of the NEXT row of column A
                 // (old H + substitution score) is formed before that row's H register is overwritten, so every H
                 // stays in one physical register across steps.
-                const uint32_t paa = prof_base + ( ( cia & 31u ) << 8 );
-                const uint32_t pba = prof_base + ( ( ( cia >> 5 ) & 31u ) << 8 );
-                const uint32_t pab = prof_base + ( ( cib & 31u ) << 8 );
-                const uint32_t pbb = prof_base + ( ( ( cib >> 5 ) & 31u ) << 8 );
+                const uint32_t ra = cia & 31u, rb = ( cia >> 5 ) & 31u, sa = cib & 31u, sb = ( cib >> 5 ) & 31u;
+                const uint32_t paa = prof_base + ( ra << 9 ), pba = prof_base + ( rb << 9 );
+                const uint32_t pab = prof_base + ( sa << 9 ), pbb = prof_base + ( sb << 9 );
+                const uint32_t paa16 = prof_base16 + ( ra << 8 ), pba16 = prof_base16 + ( rb << 8 );
+                const uint32_t pab16 = prof_base16 + ( sa << 8 ), pbb16 = prof_base16 + ( sb << 8 );
                 T fa = fa_in, fb = fb_in;
                 T ha_prev = ha_in;                       // H of column A, previous row (diagonal of column B)
                 T hda = diag;                            // H of column A-1, previous row (diagonal of column A)
                 diag = hb_in;
 #pragma unroll
                 for( int k2 = 0; k2 < R / 4; k2++ ) {
-                    // one 64-bit shared load per sequence and column fetches the scores of four query rows
-                    const uint2 laa2 = lds64( paa + k2 * 8192 ), lba2 = lds64( pba + k2 * 8192 );
-                    const uint2 lab2 = lds64( pab + k2 * 8192 ), lbb2 = lds64( pbb + k2 * 8192 );
+                    // one shared load per sequence and column fetches the scores of four query rows
+                    const bool m32 = 4 * k2 < MR;
+                    uint2 laa2 = make_uint2( 0, 0 ), lba2 = laa2, lab2 = laa2, lbb2 = laa2;
+                    uint4 laa4 = make_uint4( 0, 0, 0, 0 ), lba4 = laa4, lab4 = laa4, lbb4 = laa4;
+                    if( m32 ) {
+                        laa4 = lds128( paa + k2 * 16384 );
+                        lba4 = lds128( pba + k2 * 16384 );
+                        lab4 = lds128( pab + k2 * 16384 );
+                        lbb4 = lds128( pbb + k2 * 16384 );
+                    }
+                    else {
+                        laa2 = lds64( paa16 + ( k2 - MR / 4 ) * 8192 );
+                        lba2 = lds64( pba16 + ( k2 - MR / 4 ) * 8192 );
+                        lab2 = lds64( pab16 + ( k2 - MR / 4 ) * 8192 );
+                        lbb2 = lds64( pbb16 + ( k2 - MR / 4 ) * 8192 );
+                    }
 #pragma unroll
                     for( int j = 0; j < 2; j++ ) {
                         const int k = 2 * k2 + j;
-                        const uint32_t laa = j ? laa2.y : laa2.x, lba = j ? lba2.y : lba2.x;
-                        const uint32_t lab = j ? lab2.y : lab2.x, lbb = j ? lbb2.y : lbb2.x;
+                        uint32_t va0, va1, vb0, vb1;   // (A:B) substitution scores of rows 2k, 2k+1 in column A resp. B
+                        if( m32 ) {
+                            va0 = ( j ? laa4.z : laa4.x ) * K65536 + ( j ? lba4.z : lba4.x );
+                            va1 = ( j ? laa4.w : laa4.y ) * K65536 + ( j ? lba4.w : lba4.y );
+                            vb0 = ( j ? lab4.z : lab4.x ) * K65536 + ( j ? lbb4.z : lbb4.x );
+                            vb1 = ( j ? lab4.w : lab4.y ) * K65536 + ( j ? lbb4.w : lbb4.y );
+                        }
+                        else {
+                            const uint32_t laa = j ? laa2.y : laa2.x, lba = j ? lba2.y : lba2.x;
+                            const uint32_t lab = j ? lab2.y : lab2.x, lbb = j ? lbb2.y : lbb2.x;
+                            va0 = __byte_perm( lba, laa, 0x5410 );
+                            va1 = __byte_perm( lba, laa, 0x7632 );
+                            vb0 = __byte_perm( lbb, lab, 0x5410 );
+                            vb1 = __byte_perm( lbb, lab, 0x7632 );
+                        }
                         // diagonal candidates of column A are formed from the OLD H registers before they are overwritten
-                        const T ta0 = A::add( hda, (T) __byte_perm( lba, laa, 0x5410 ) );
-                        const T ta1 = A::add( Hp[2 * k], (T) __byte_perm( lba, laa, 0x7632 ) );
+                        const T ta0 = A::add( hda, (T) va0 );
+                        const T ta1 = A::add( Hp[2 * k], (T) va1 );
                         hda = Hp[2 * k + 1];
                         T hq;
                         // column A, row 2k
@@ -415,7 +485,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                         const T ea0 = A::addmax( E[2 * k], RG, hq );
                         fa = A::addmax( fa, RG, hq );
                         // column B, row 2k
-                        const T tb0 = A::add( ha_prev, (T) __byte_perm( lbb, lab, 0x5410 ) );
+                        const T tb0 = A::add( ha_prev, (T) vb0 );
                         Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
                         hq = A::add( Hp[2 * k], QR );
                         E[2 * k] = A::addmax( ea0, RG, hq );
@@ -426,7 +496,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                         const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
                         fa = A::addmax( fa, RG, hq );
                         // column B, row 2k+1
-                        const T tb1 = A::add( ha0, (T) __byte_perm( lbb, lab, 0x7632 ) );
+                        const T tb1 = A::add( ha0, (T) vb1 );
                         Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
                         hq = A::add( Hp[2 * k + 1], QR );
                         E[2 * k + 1] = A::addmax( ea1, RG, hq );

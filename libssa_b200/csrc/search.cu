@@ -582,21 +582,28 @@ Plan make_plan( size_t qlen ) {
     return pl;
 }
 
-// Packed profile of pass `pass`: one word per (row pair k, residue d, lane) = ( M[d][q(row 2k+1)] : M[d][q(row 2k)] ) as
-// int16, two consecutive row pairs forming one 64-bit shared-memory entry; rows counted from (pass*G + (lane mod G)) * R.  All 32 lanes have their own copy (groups repeat), so a warp-wide
-// lookup is bank-conflict free whatever residues the lanes hold.  Rows beyond the query get pad_score.
+// Packed-tier profile of pass `pass` (layout: score_kernel.cuh).  Rows are counted from (pass*G + (lane mod G)) * R; all 32
+// lanes have their own copy (groups repeat), so a warp-wide lookup is bank-conflict free whatever residues the lanes
+// hold.  First MR rows of a lane: 128-bit entries [row quad][residue][lane] = four rows, one zero-extended int16 each.
+// Remaining rows: 64-bit entries [row quad][residue][lane] = four rows, two per word (low half = even row).
+// Rows beyond the query get pad_score.
+size_t packed_profile_words( int R ) { return (size_t) merge_rows( R ) * 1024 + (size_t) ( ( R - merge_rows( R ) ) / 2 ) * 1024; }
+
 void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
-    const int R = pl.R, G = pl.G;
-    for( int k = 0; k < R / 2; k++ )
-        for( int d = 0; d < 32; d++ )
-            for( int lane = 0; lane < 32; lane++ ) {
-                size_t r0 = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R + 2 * k;
-                int v0 = r0 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0]] : pl.pad_score;
-                int v1 = r0 + 1 < qlen ? (int) g_matrix.m[( d << 5 ) + q[r0 + 1]] : pl.pad_score;
-                // 64-bit entries [row quad k/2][residue][lane]; word k%2 of an entry = rows 2k (low half), 2k+1 (high half)
-                out[( ( ( k / 2 ) * 32 + d ) * 32 + lane ) * 2 + ( k & 1 )] =
-                        ( (uint32_t) (uint16_t) (int16_t) v1 << 16 ) | (uint32_t) (uint16_t) (int16_t) v0;
+    const int R = pl.R, G = pl.G, MR = merge_rows( R );
+    uint32_t * out16 = out + (size_t) MR * 1024;
+    for( int d = 0; d < 32; d++ )
+        for( int lane = 0; lane < 32; lane++ ) {
+            const size_t row0 = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R;
+            auto score = [&]( int r ) { return row0 + r < qlen ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pl.pad_score; };
+            for( int r = 0; r < MR; r++ )
+                out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = (uint32_t) (uint16_t) (int16_t) score( r );
+            for( int r = MR; r < R; r += 2 ) {
+                const int k = ( r - MR ) / 2;   // row pair within the 64-bit part
+                out16[( ( ( k / 2 ) * 32 + d ) * 32 + lane ) * 2 + ( k & 1 )] =
+                        ( (uint32_t) (uint16_t) (int16_t) score( r + 1 ) << 16 ) | (uint32_t) (uint16_t) (int16_t) score( r );
             }
+        }
 }
 
 void fill_profile_wide( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
@@ -710,6 +717,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         a.counter = ( ctx.d_counter.p + 16 + 8 * slot );
         a.profile = ctx.d_profile_wide[slot].p + p * words;
         a.group = (uint32_t) G;
+        a.k65536 = 65536u;
         a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
         a.rg_word = (uint32_t) (int) g_gapE;
         a.gap_open_extend = (int) g_gapO + (int) g_gapE;
@@ -747,7 +755,8 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
 void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, int G, int R, int npass,
         const Batch * d_batches, uint32_t nbatches, uint32_t * d_counter, uint32_t * d_profile, uint32_t * h_profile, int32_t offset ) {
     PackedDb & db = ctx.db;
-    const size_t words = (size_t) ( R / 2 ) * 1024;
+    const bool multi = npass > 1 || getenv( "LIBSSA_B200_FORCE_MULTI" ) != nullptr;
+    const size_t words = packed_profile_words( R );
     Plan shape = pl;
     shape.G = G;
     shape.R = R;
@@ -764,6 +773,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         a.counter = d_counter;
         a.profile = d_profile + p * words;
         a.group = (uint32_t) G;
+        a.k65536 = 65536u;
         a.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
         a.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
         a.gap_open_extend = (int) g_gapO + (int) g_gapE;
@@ -788,7 +798,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
             a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
-        launch_score_packed( R, nw, npass > 1 || getenv( "LIBSSA_B200_FORCE_MULTI" ) != nullptr, a, stream );
+        launch_score_packed( R, nw, multi, a, stream );
         ctx.stats.launches++;
     }
 }
@@ -902,7 +912,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             ctx.h_long_batches[ctx.ss].p[i] = b;
         }
         ctx.d_long_batches.reserve( n_long );
-        const size_t words = (size_t) ( long_R / 2 ) * 1024;
+        const size_t words = packed_profile_words( long_R );
         ctx.h_profile_long[ctx.ss].reserve( words );
         ctx.d_profile_long.reserve( words );
         CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches[ctx.ss].p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
@@ -913,7 +923,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     if( use_aux ) CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
     // ---- bulk class ----
     if( b0 < bt.batches.size() ) {
-        const size_t words = (size_t) ( R / 2 ) * 1024;
+        const size_t words = packed_profile_words( R );
         ctx.h_profile[ctx.ss].reserve( words * npass );
         ctx.d_profile.reserve( words * npass );
         if( npass > 1 ) ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
