@@ -23,7 +23,8 @@ class LibraryMissing(RuntimeError):
 
 
 def library_path():
-    return os.path.join(HERE, "libssa_b200.so")
+    # LIBSSA_B200_LIB: development aid for A/B runs of two builds on one box
+    return os.environ.get("LIBSSA_B200_LIB") or os.path.join(HERE, "libssa_b200.so")
 
 
 def build_library(jobs=8):
