@@ -18,6 +18,20 @@ def main():
             assert g == e, (rank, entry["case"]["name"], run, g[:3], e[:3])
         st = lib.stats()
         assert st.local_seqs < st.n_seqs or st.n_seqs < world
+    # batched queries on the sharded database: the pipelined batch must equal single calls (which equal the reference)
+    big = [e for e in expected if e["case"]["name"] == "synth_protein_30000"][0]["case"]
+    q0 = cases.configure(lib, big)
+    lib.free_sequence(q0)
+    from libssa_b200 import synth
+    import numpy as np
+    rng = np.random.default_rng(9)
+    qs = [lib.init_sequence_fasta(cases.READ_FROM_STRING, synth.random_protein(rng, n)) for n in (120, 380, 45, 700)]
+    for nw, bits, k, align in ((False, 8, 50, 0), (True, 16, 10, 1)):
+        single = [[(h.score, h.db_id, h.cigar) for h in (lib.nw_align if nw else lib.sw_align)(q, k, bits, align)] for q in qs]
+        batch = [[(h.score, h.db_id, h.cigar) for h in hits] for hits in lib.align_batch(qs, k, bits, align, nw=nw)]
+        assert batch == single, (rank, nw, bits)
+    for q in qs:
+        lib.free_sequence(q)
     # strand / reading-frame searches, sharded: every frame's shard scores are gathered, every rank replays
     import tempfile
     import frames as F
