@@ -192,7 +192,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     uint32_t half = 0;
     bool done = false;
     uint32_t w_n1 = 0, w_n2 = 0;        // column words of the next two steps (software prefetch)
-    uint2 bh_n1 = make_uint2( 0, 0 ), bf_n1 = make_uint2( 0, 0 );   // MULTI: boundary row of the next step (top lane)
+    // MULTI (full-warp groups only): the previous pass' boundary row (H and F of two columns per step) is fetched by the
+    // whole warp, 32 steps at a time and one block of 32 ahead - lane l holds the entry of step 32*blk + l - and reaches
+    // the top lane through an indexed shuffle: no divergent code, no global latency on the step's path.
+    uint2 bh_cur = make_uint2( 0, 0 ), bf_cur = make_uint2( 0, 0 ), bh_nxt = make_uint2( 0, 0 ), bf_nxt = make_uint2( 0, 0 );
 
     // one database column through this lane's R rows (used where the two-column loop does not apply)
     auto single_column = [&]( const uint32_t ci, const T h_in, const T f_in, T & h_last, T & f_last ) {
@@ -320,14 +323,20 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
                 w_n1 = ( gl == 0 ) ? st[0] : 0;
                 w_n2 = ( 1 - gl >= 0 && 1 - gl < nsteps_cols ) ? st[1 - gl] : 0;
-                if( MULTI && a.bnd_h_in && is_top ) {
-                    bh_n1 = ( (const uint2 *) a.bnd_h_in )[bnd_base];
-                    bf_n1 = ( (const uint2 *) a.bnd_f_in )[bnd_base];
+                if( MULTI && a.bnd_h_in ) {
+                    if( lane < nsteps_cols ) {
+                        bh_cur = ( (const uint2 *) a.bnd_h_in )[bnd_base + lane];
+                        bf_cur = ( (const uint2 *) a.bnd_f_in )[bnd_base + lane];
+                    }
+                    if( 32 + lane < nsteps_cols ) {
+                        bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + 32 + lane];
+                        bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + 32 + lane];
+                    }
                 }
             }
             t = 0;
         }
-        if( __all_sync( FULL, done ) ) break;
+        if( __all_sync( FULL, done ) ) break;   // also the point where the groups of a warp reconverge every step
 
         // Every lane reads the column words of ITS column pair (t - gl) straight from the stream, two steps ahead
         // of use: the G lanes of a group touch G consecutive 32-bit words, all groups run the same instructions.
@@ -372,15 +381,23 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     top_f = A::add( top_f, RG );
                 }
             }
-            else if( MULTI ) {
-                ha_in = (T) bh_n1.x;
-                hb_in = (T) bh_n1.y;
-                fa_in = (T) bf_n1.x;
-                fb_in = (T) bf_n1.y;
-                if( a.bnd_h_in && t + 1 < nsteps_cols ) {  // next step's boundary row, one step ahead of use
-                    bh_n1 = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 1];
-                    bf_n1 = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 1];
+        }
+        if( MULTI && a.bnd_h_in ) {  // warp-uniform (G = 32): t is the column pair of the top lane
+            if( ( t & 31 ) == 0 && t > 0 ) {
+                bh_cur = bh_nxt;
+                bf_cur = bf_nxt;
+                if( t + 32 + lane < nsteps_cols ) {
+                    bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 32 + lane];
+                    bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 32 + lane];
                 }
+            }
+            const uint32_t bha = __shfl_sync( FULL, bh_cur.x, t & 31 ), bhb = __shfl_sync( FULL, bh_cur.y, t & 31 );
+            const uint32_t bfa = __shfl_sync( FULL, bf_cur.x, t & 31 ), bfb = __shfl_sync( FULL, bf_cur.y, t & 31 );
+            if( is_top ) {
+                ha_in = (T) bha;
+                hb_in = (T) bhb;
+                fa_in = (T) bfa;
+                fb_in = (T) bfb;
             }
         }
 
