@@ -27,8 +27,9 @@
 //     cannot be guaranteed to fit 16 bits - the counterpart of the reference's 16->64 bit overflow cascade.
 //     Optionally tracks the first column whose running maximum reaches 255 / 65535, which is what the
 //     reference's 8/16-bit tiers would have overflowed at (needed to reproduce its hit order, replay.cpp);
-//   * queries longer than G*R rows are processed in passes; the H/F of the last row of a pass is written to a
-//     boundary buffer in global memory and read back by lane 0 of the next pass.
+//   * queries longer than 32*32 rows are processed in passes: full passes of 32 lanes x 32 rows and a remainder pass
+//     whose shape (G lanes x R rows, any G) fits the rows that are left; the H/F of the last row of a pass is
+//     written to a boundary buffer in global memory and read back by the top lane(s) of the next pass.
 #pragma once
 
 #include <cstdint>
@@ -125,7 +126,10 @@ __device__ __forceinline__ uint4 lds128( uint32_t addr ) {
 // the other R - MR rows hold two scores per word (merged by PRMT).  The IMAD form pays where the ALU pipe throttles:
 // the shapes with 3-4 resident CTAs per SM (R <= 16: +5 % [B200]).  The 2-CTA shapes (R >= 24) are issue-bound at
 // 4 warps per scheduler and gain nothing from it (measured -1..+2 %), so they keep the smaller PRMT profile.
-__host__ __device__ constexpr int merge_rows( int R ) { return R <= 16 ? R : 0; }
+#ifndef SSA_MR_HI
+#define SSA_MR_HI 0
+#endif
+__host__ __device__ constexpr int merge_rows( int R ) { return R <= 16 ? R : SSA_MR_HI; }
 
 // words of shared memory the profile of one pass needs
 template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
@@ -135,7 +139,8 @@ template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
 // resident CTAs per SM the register allocator has to make room for (64K registers / 256 threads / blocks)
 template<bool PACKED, int R> __host__ __device__ constexpr int min_blocks() { return PACKED ? ( R <= 12 ? 4 : ( R <= 20 ? 3 : 2 ) ) : 2; }
 
-template<bool PACKED, int R, bool NW, bool MULTI, bool TRACK>
+// MULTI: 0 = the whole query in one pass; 1 = one pass of several, full-warp groups; 2 = one pass of several, narrow groups
+template<bool PACKED, int R, bool NW, int MULTI, bool TRACK>
 __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) score_kernel( const ScoreArgs a ) {
     typedef Arith<PACKED> A;
     typedef typename A::T T;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     uint32_t half = 0;
     bool done = false;
     uint32_t w_n1 = 0, w_n2 = 0;        // column words of the next two steps (software prefetch)
-    // MULTI (full-warp groups only): the previous pass' boundary row (H and F of two columns per step) is fetched by the
+    // MULTI, full-warp groups: the previous pass' boundary row (H and F of two columns per step) is fetched by the
     // whole warp, 32 steps at a time and one block of 32 ahead - lane l holds the entry of step 32*blk + l - and reaches
     // the top lane through an indexed shuffle: no divergent code, no global latency on the step's path.
     uint2 bh_cur = make_uint2( 0, 0 ), bf_cur = make_uint2( 0, 0 ), bh_nxt = make_uint2( 0, 0 ), bf_nxt = make_uint2( 0, 0 );
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
                 w_n1 = ( gl == 0 ) ? st[0] : 0;
                 w_n2 = ( 1 - gl >= 0 && 1 - gl < nsteps_cols ) ? st[1 - gl] : 0;
-                if( MULTI && a.bnd_h_in ) {
+                if( MULTI == 1 && a.bnd_h_in ) {
                     if( lane < nsteps_cols ) {
                         bh_cur = ( (const uint2 *) a.bnd_h_in )[bnd_base + lane];
                         bf_cur = ( (const uint2 *) a.bnd_f_in )[bnd_base + lane];
@@ -331,6 +336,18 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     if( 32 + lane < nsteps_cols ) {
                         bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + 32 + lane];
                         bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + 32 + lane];
+                    }
+                }
+                if( MULTI == 2 && a.bnd_h_in ) {
+                    if( is_top ) {  // narrow groups (remainder pass): the top lane fetches its own entries, two steps ahead
+                        if( 0 < nsteps_cols ) {
+                            bh_cur = ( (const uint2 *) a.bnd_h_in )[bnd_base];
+                            bf_cur = ( (const uint2 *) a.bnd_f_in )[bnd_base];
+                        }
+                        if( 1 < nsteps_cols ) {
+                            bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + 1];
+                            bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + 1];
+                        }
                     }
                 }
             }
@@ -382,7 +399,24 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 }
             }
         }
-        if( MULTI && a.bnd_h_in ) {  // warp-uniform (G = 32): t is the column pair of the top lane
+        if( MULTI == 2 && a.bnd_h_in ) {
+            // Narrow groups: every group has its own batch and step counter, so the top lane of each group reads the
+            // boundary entries of ITS column pair t itself (prefetched two steps ahead).  Only the remainder pass of a
+            // long query runs this way (a few per cent of the work), the full passes use the warp-wide fetch below.
+            if( is_top ) {
+                ha_in = (T) bh_cur.x;
+                hb_in = (T) bh_cur.y;
+                fa_in = (T) bf_cur.x;
+                fb_in = (T) bf_cur.y;
+                bh_cur = bh_nxt;
+                bf_cur = bf_nxt;
+                if( t + 2 < nsteps_cols ) {
+                    bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 2];
+                    bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 2];
+                }
+            }
+        }
+        if( MULTI == 1 && a.bnd_h_in ) {  // warp-uniform (G = 32): t is the column pair of the top lane
             if( ( t & 31 ) == 0 && t > 0 ) {
                 bh_cur = bh_nxt;
                 bf_cur = bf_nxt;

@@ -26,10 +26,12 @@ template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArg
 
 template<int R> static int pick( bool nw, bool multi, const ScoreArgs & a, cudaStream_t s ) {
     const int smem = profile_words<true, R>() * 4;
-    if( nw ) return multi ? launch( score_kernel<true, R, true, true, false>, smem, a, s )
-                          : launch( score_kernel<true, R, true, false, false>, smem, a, s );
-    return multi ? launch( score_kernel<true, R, false, true, false>, smem, a, s )
-                 : launch( score_kernel<true, R, false, false, false>, smem, a, s );
+    if( multi && a.group != 32 )  // remainder pass of a long query on narrow groups
+        return nw ? launch( score_kernel<true, R, true, 2, false>, smem, a, s ) : launch( score_kernel<true, R, false, 2, false>, smem, a, s );
+    if( nw ) return multi ? launch( score_kernel<true, R, true, 1, false>, smem, a, s )
+                          : launch( score_kernel<true, R, true, 0, false>, smem, a, s );
+    return multi ? launch( score_kernel<true, R, false, 1, false>, smem, a, s )
+                 : launch( score_kernel<true, R, false, 0, false>, smem, a, s );
 }
 
 template<typename K> static int occupancy( K kernel, int smem_bytes ) {
@@ -41,8 +43,8 @@ template<typename K> static int occupancy( K kernel, int smem_bytes ) {
 
 template<int R> static int occ_pick( bool nw, bool multi ) {
     const int smem = profile_words<true, R>() * 4;
-    if( nw ) return multi ? occupancy( score_kernel<true, R, true, true, false>, smem ) : occupancy( score_kernel<true, R, true, false, false>, smem );
-    return multi ? occupancy( score_kernel<true, R, false, true, false>, smem ) : occupancy( score_kernel<true, R, false, false, false>, smem );
+    if( nw ) return multi ? occupancy( score_kernel<true, R, true, 1, false>, smem ) : occupancy( score_kernel<true, R, true, 0, false>, smem );
+    return multi ? occupancy( score_kernel<true, R, false, 1, false>, smem ) : occupancy( score_kernel<true, R, false, 0, false>, smem );
 }
 
 int packed_blocks_per_sm( int R, bool nw, bool multi ) {

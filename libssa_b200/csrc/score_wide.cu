@@ -25,12 +25,12 @@ template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArg
 
 template<int R> static int pick( bool nw, bool multi, bool track, const ScoreArgs & a, cudaStream_t s ) {
     const int smem = profile_words<false, R>() * 4;
-    if( nw ) return multi ? launch( score_kernel<false, R, true, true, false>, smem, a, s )
-                          : launch( score_kernel<false, R, true, false, false>, smem, a, s );
-    if( track ) return multi ? launch( score_kernel<false, R, false, true, true>, smem, a, s )
-                             : launch( score_kernel<false, R, false, false, true>, smem, a, s );
-    return multi ? launch( score_kernel<false, R, false, true, false>, smem, a, s )
-                 : launch( score_kernel<false, R, false, false, false>, smem, a, s );
+    if( nw ) return multi ? launch( score_kernel<false, R, true, 1, false>, smem, a, s )
+                          : launch( score_kernel<false, R, true, 0, false>, smem, a, s );
+    if( track ) return multi ? launch( score_kernel<false, R, false, 1, true>, smem, a, s )
+                             : launch( score_kernel<false, R, false, 0, true>, smem, a, s );
+    return multi ? launch( score_kernel<false, R, false, 1, false>, smem, a, s )
+                 : launch( score_kernel<false, R, false, 0, false>, smem, a, s );
 }
 
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & a, cudaStream_t s ) {

@@ -96,7 +96,7 @@ struct PackedDb {
         std::vector<uint32_t> pair0;   // first pair of each batch
         DevBuf<Batch> d_batches;
     };
-    std::map<uint32_t, BatchTable> batch_tables;  // keyed by columns per batch
+    std::map<std::pair<uint32_t, uint32_t>, BatchTable> batch_tables;  // keyed by (columns per batch, first pair)
     DevBuf<uint16_t> d_stream;
     DevBuf<uint32_t> d_lens_all;           // record lengths, provider order (for the arrival-order kernel)
     DevBuf<uint64_t> d_pair_col;           // first stream column of every pair
@@ -425,12 +425,14 @@ void parallel_for( size_t n, size_t grain, const std::function<void( size_t, siz
 
 // Work batches of the packed tier: runs of whole pairs with at least `cols` columns, built on demand and cached.
 // Small batches balance the persistent grid's work queue, large ones amortise the G-1 fill/drain steps.
-PackedDb::BatchTable & batch_table( uint32_t cols ) {
+// Work batches of ~`cols` stream columns (whole pairs), starting at pair `first_pair`; cached per database.
+PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0 ) {
     PackedDb & db = ctx.db;
-    auto it = db.batch_tables.find( cols );
+    const std::pair<uint32_t, uint32_t> key( cols, first_pair );
+    auto it = db.batch_tables.find( key );
     if( it != db.batch_tables.end() ) return it->second;
-    PackedDb::BatchTable & bt = db.batch_tables[cols];
-    for( size_t p = 0; p < db.npairs; ) {
+    PackedDb::BatchTable & bt = db.batch_tables[key];
+    for( size_t p = first_pair; p < db.npairs; ) {
         Batch b;
         memset( &b, 0, sizeof( b ) );
         b.col0 = db.pair_col[p];
@@ -582,20 +584,20 @@ Plan make_plan( size_t qlen ) {
     return pl;
 }
 
-// Packed-tier profile of pass `pass` (layout: score_kernel.cuh).  Rows are counted from (pass*G + (lane mod G)) * R; all 32
-// lanes have their own copy (groups repeat), so a warp-wide lookup is bank-conflict free whatever residues the lanes
-// hold.  First MR rows of a lane: 128-bit entries [row quad][residue][lane] = four rows, one zero-extended int16 each.
-// Remaining rows: 64-bit entries [row quad][residue][lane] = four rows, two per word (low half = even row).
-// Rows beyond the query get pad_score.
+// Packed-tier profile of one pass (layout: score_kernel.cuh): G lanes x R rows starting at query row `rowbase`; lane l of a
+// group owns rows rowbase + (l mod G) * R ....  All 32 lanes have their own copy (groups repeat), so a warp-wide lookup is
+// bank-conflict free whatever residues the lanes hold.  First MR rows of a lane: 128-bit entries [row quad][residue][lane] =
+// four rows, one zero-extended int16 each.  Remaining rows: 64-bit entries [row quad][residue][lane] = four rows, two per
+// word (low half = even row).  Rows beyond the query get pad_score.
 size_t packed_profile_words( int R ) { return (size_t) merge_rows( R ) * 1024 + (size_t) ( ( R - merge_rows( R ) ) / 2 ) * 1024; }
 
-void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, const Plan & pl, int pass ) {
-    const int R = pl.R, G = pl.G, MR = merge_rows( R );
+void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G, int R, size_t rowbase, int pad_score ) {
+    const int MR = merge_rows( R );
     uint32_t * out16 = out + (size_t) MR * 1024;
     for( int d = 0; d < 32; d++ )
         for( int lane = 0; lane < 32; lane++ ) {
-            const size_t row0 = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R;
-            auto score = [&]( int r ) { return row0 + r < qlen ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pl.pad_score; };
+            const size_t row0 = rowbase + (size_t) ( lane % G ) * R;
+            auto score = [&]( int r ) { return row0 + r < qlen ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pad_score; };
             for( int r = 0; r < MR; r++ )
                 out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = (uint32_t) (uint16_t) (int16_t) score( r );
             for( int r = MR; r < R; r += 2 ) {
@@ -751,28 +753,46 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     ctx.stats.wide_tier_seqs += n;
 }
 
-// One launch (all passes) of the packed tier over `nbatches` batches with shape G x R.
-void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, int G, int R, int npass,
-        const Batch * d_batches, uint32_t nbatches, uint32_t * d_counter, uint32_t * d_profile, uint32_t * h_profile, int32_t offset ) {
+// One pass of the packed tier: G lanes x R rows from query row `rowbase` on, over its own list of work batches (the boundary
+// buffers are indexed by stream column, so the passes of one query may cut the stream into different batches).
+struct PassLaunch {
+    int G = 32, R = 4;
+    size_t rowbase = 0;
+    const Batch * d_batches = nullptr;
+    uint32_t nbatches = 0;
+};
+
+// The packed tier over one class of pairs: all passes of the query, one launch each.
+void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, const std::vector<PassLaunch> & passes,
+        uint32_t * d_counter, DevBuf<uint32_t> & d_profile_buf, PinBuf<uint32_t> & h_profile_buf, int32_t offset ) {
     PackedDb & db = ctx.db;
+    const int npass = (int) passes.size();
     const bool multi = npass > 1 || getenv( "LIBSSA_B200_FORCE_MULTI" ) != nullptr;
-    const size_t words = packed_profile_words( R );
-    Plan shape = pl;
-    shape.G = G;
-    shape.R = R;
-    for( int p = 0; p < npass; p++ ) fill_profile_packed( h_profile + p * words, q, qlen, shape, p );
-    CUDA_OK( cudaMemcpyAsync( d_profile, h_profile, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
-    ctx.stats.h2d_bytes += words * npass * 4;
+    size_t words_total = 0;
+    for( const PassLaunch & ps : passes ) words_total += packed_profile_words( ps.R );
+    h_profile_buf.reserve( words_total );
+    d_profile_buf.reserve( words_total );
+    uint32_t * const h_profile = h_profile_buf.p, * const d_profile = d_profile_buf.p;
+    size_t w0 = 0;
+    for( const PassLaunch & ps : passes ) {
+        fill_profile_packed( h_profile + w0, q, qlen, ps.G, ps.R, ps.rowbase, pl.pad_score );
+        w0 += packed_profile_words( ps.R );
+    }
+    CUDA_OK( cudaMemcpyAsync( d_profile, h_profile, words_total * 4, cudaMemcpyHostToDevice, stream ) );
+    ctx.stats.h2d_bytes += words_total * 4;
+    w0 = 0;
     for( int p = 0; p < npass; p++ ) {
+        const PassLaunch & ps = passes[p];
         CUDA_OK( cudaMemsetAsync( d_counter, 0, 4, stream ) );
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
         a.stream = db.d_stream.p;
-        a.batches = d_batches;
-        a.nbatches = nbatches;
+        a.batches = ps.d_batches;
+        a.nbatches = ps.nbatches;
         a.counter = d_counter;
-        a.profile = d_profile + p * words;
-        a.group = (uint32_t) G;
+        a.profile = d_profile + w0;
+        w0 += packed_profile_words( ps.R );
+        a.group = (uint32_t) ps.G;
         a.k65536 = 65536u;
         a.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
         a.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
@@ -780,11 +800,11 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         a.gap_extend = g_gapE;
         a.gap_open = g_gapO;
         a.offset = offset;
-        a.rowbase = p * G * R;
+        a.rowbase = (int32_t) ps.rowbase;
         a.cap_lane = -1;
-        if( nw && (size_t) a.rowbase <= qlen - 1 && qlen - 1 < (size_t) a.rowbase + (size_t) G * R ) {
-            a.cap_lane = (int) ( ( qlen - 1 - a.rowbase ) / R );
-            a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
+        if( nw && ps.rowbase <= qlen - 1 && qlen - 1 < ps.rowbase + (size_t) ps.G * ps.R ) {
+            a.cap_lane = (int) ( ( qlen - 1 - ps.rowbase ) / ps.R );
+            a.cap_row = (int) ( ( qlen - 1 - ps.rowbase ) % ps.R );
         }
         a.first_pass = ( p == 0 );
         a.out = ctx.d_out_packed.p;
@@ -798,9 +818,62 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
             a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
-        launch_score_packed( R, nw, multi, a, stream );
+        launch_score_packed( ps.R, nw, multi, a, stream );
         ctx.stats.launches++;
     }
+}
+
+// Passes of a query longer than one 32 x 32 pass.  Uniform plan (pick_shape): npass passes of 32 x R.  Mixed plan: full
+// passes of 32 x 32 rows - the shape with the least per-row cost - and a remainder pass whose shape (any G) fits the rows
+// that are left, so that at most a few rows are padding (5147 rows: 5 x 1024 + 4 x 8 instead of 6 x 896).  Narrow groups
+// process a pair from its first to its last column on G lanes: the longest pair must not outlast the rest of the pass.
+// Costs in the units of pick_shape (instructions per stream column and warp).
+std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_uniform, uint64_t total_cols, uint64_t longest_cols, int sms ) {
+    std::vector<PassLaunch> v;
+    const double uniform_cost = npass_uniform * ( 7.5 * R_uniform + 60 ) * 1.03;
+    const size_t full = qlen / 1024, rem = qlen % 1024;
+    double best = 1e300;
+    int bg = 0, br = 0;
+    if( rem > 0 )
+        for( int G = 4; G <= 32; G *= 2 )
+            for( int R : PACKED_R ) {
+                if( (size_t) G * R < rem ) continue;
+                const double step = 7.5 * R + 75;
+                // columns per scheduler if the pass were perfectly spread vs the one group that owns the longest pair
+                const double spread = (double) total_cols * G / 32.0, serial = (double) longest_cols * sms * 4 * 2.7;
+                const double cost = step * std::max( spread, serial ) / (double) std::max<uint64_t>( total_cols, 1 );
+                if( cost < best ) {
+                    best = cost;
+                    bg = G;
+                    br = R;
+                }
+            }
+    const double mixed_cost = full * ( 7.5 * 32 + 60 ) * 1.03 + ( rem > 0 ? best : 0.0 );
+    if( getenv( "LIBSSA_B200_SHAPE" ) || getenv( "LIBSSA_B200_UNIFORM_PASSES" ) || full == 0 || mixed_cost >= uniform_cost ) {
+        for( int p = 0; p < npass_uniform; p++ ) {
+            PassLaunch ps;
+            ps.G = 32;
+            ps.R = R_uniform;
+            ps.rowbase = (size_t) p * 32 * R_uniform;
+            v.push_back( ps );
+        }
+        return v;
+    }
+    for( size_t p = 0; p < full; p++ ) {
+        PassLaunch ps;
+        ps.G = 32;
+        ps.R = 32;
+        ps.rowbase = p * 1024;
+        v.push_back( ps );
+    }
+    if( rem > 0 ) {
+        PassLaunch ps;
+        ps.G = bg;
+        ps.R = br;
+        ps.rowbase = full * 1024;
+        v.push_back( ps );
+    }
+    return v;
 }
 
 // first pair (pairs are sorted by descending length of their longer sequence) whose length is <= len
@@ -828,6 +901,11 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     Plan pl = make_plan( qlen );
     int sms = 148;
     cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx.device );
+    if( db.batch_tables.size() >= 24 ) {  // bound the cache: a table's first pair depends on the query and the score matrix
+        CUDA_OK( cudaDeviceSynchronize() );
+        for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
+        db.batch_tables.clear();
+    }
 
     // ---- tier split: pairs whose longer sequence exceeds the packed tier's guaranteed range go to the wide tier ----
     int32_t offset = 0;
@@ -912,23 +990,44 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             ctx.h_long_batches[ctx.ss].p[i] = b;
         }
         ctx.d_long_batches.reserve( n_long );
-        const size_t words = packed_profile_words( long_R );
-        ctx.h_profile_long[ctx.ss].reserve( words );
-        ctx.d_profile_long.reserve( words );
         CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches[ctx.ss].p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
         ctx.stats.h2d_bytes += n_long * sizeof( Batch );
-        launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, 32, long_R, 1, ctx.d_long_batches.p, (uint32_t) n_long, ctx.d_counter.p + 8,
-                ctx.d_profile_long.p, ctx.h_profile_long[ctx.ss].p, offset );
+        PassLaunch lp;
+        lp.G = 32;
+        lp.R = long_R;
+        lp.d_batches = ctx.d_long_batches.p;
+        lp.nbatches = (uint32_t) n_long;
+        launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, { lp }, ctx.d_counter.p + 8, ctx.d_profile_long, ctx.h_profile_long[ctx.ss], offset );
     }
     if( use_aux ) CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
     // ---- bulk class ----
     if( b0 < bt.batches.size() ) {
-        const size_t words = packed_profile_words( R );
-        ctx.h_profile[ctx.ss].reserve( words * npass );
-        ctx.d_profile.reserve( words * npass );
-        if( npass > 1 ) ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
-        launch_packed_class( ctx.stream, q, qlen, nw, pl, G, R, npass, bt.d_batches.p + b0, (uint32_t) ( bt.batches.size() - b0 ), ctx.d_counter.p,
-                ctx.d_profile.p, ctx.h_profile[ctx.ss].p, offset );
+        std::vector<PassLaunch> passes;
+        if( npass > 1 ) {
+            passes = plan_passes( qlen, R, npass, db.total_cols - db.pair_col[bulk_pair0], db.sorted_len[2 * bulk_pair0], sms );
+            ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
+        }
+        else {
+            PassLaunch ps;
+            ps.G = G;
+            ps.R = R;
+            passes.push_back( ps );
+        }
+        for( PassLaunch & ps : passes ) {
+            if( ps.G == G && ps.R == R ) {  // the shape the bulk batch table was sized for
+                ps.d_batches = bt.d_batches.p + b0;
+                ps.nbatches = (uint32_t) ( bt.batches.size() - b0 );
+                continue;
+            }
+            // another shape has another number of resident groups: its own batches over the same pairs
+            const uint64_t ps_groups = (uint64_t) sms * packed_blocks_per_sm( ps.R, nw, true ) * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
+            uint32_t ps_cols = 4096;
+            while( ps_cols > 256 && db.total_cols / ps_cols < 6 * ps_groups ) ps_cols /= 2;
+            PackedDb::BatchTable & pt = batch_table( ps_cols, (uint32_t) bulk_pair0 );
+            ps.d_batches = pt.d_batches.p;
+            ps.nbatches = (uint32_t) pt.batches.size();
+        }
+        launch_packed_class( ctx.stream, q, qlen, nw, pl, passes, ctx.d_counter.p, ctx.d_profile, ctx.h_profile[ctx.ss], offset );
     }
     if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
     if( wide_pairs < db.npairs ) {

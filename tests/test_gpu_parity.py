@@ -64,9 +64,9 @@ def test_live_reference_random_inputs(prod, ref, tmp_path):
             assert_same_hits(g, e, run[0], run[1], ("trial", trial, n, qlen, scoring, gaps, run))
 
 
-@pytest.mark.parametrize("qlen", [1, 3, 64, 127, 128, 130, 255, 384, 385, 500, 768, 1024, 1025, 2100])
+@pytest.mark.parametrize("qlen", [1, 3, 64, 127, 128, 130, 255, 384, 385, 500, 768, 1024, 1025, 1100, 1500, 2048, 2100, 3100])
 def test_exact_scores_vs_oracle_port(prod, port, tmp_path, qlen):
-    """every kernel shape (rows per lane 4..32, one and several passes), both tiers, SW and NW"""
+    """every kernel shape (rows per lane 4..32, one and several passes, remainder passes on narrow groups), both tiers, SW and NW"""
     from libssa_b200 import synth
     rng = np.random.default_rng(qlen)
     q = synth.random_protein(rng, qlen)
