@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <numeric>
 #include <thread>
@@ -96,7 +97,7 @@ struct PackedDb {
         std::vector<uint32_t> pair0;   // first pair of each batch
         DevBuf<Batch> d_batches;
     };
-    std::map<std::pair<uint32_t, uint32_t>, BatchTable> batch_tables;  // keyed by (columns per batch, first pair)
+    std::map<std::array<uint32_t, 4>, BatchTable> batch_tables;  // keyed by (columns per batch, first pair, resident groups, smallest batch)
     DevBuf<uint16_t> d_stream;
     DevBuf<uint32_t> d_lens_all;           // record lengths, provider order (for the arrival-order kernel)
     DevBuf<uint64_t> d_pair_col;           // first stream column of every pair
@@ -426,9 +427,14 @@ void parallel_for( size_t n, size_t grain, const std::function<void( size_t, siz
 // Work batches of the packed tier: runs of whole pairs with at least `cols` columns, built on demand and cached.
 // Small batches balance the persistent grid's work queue, large ones amortise the G-1 fill/drain steps.
 // Work batches of ~`cols` stream columns (whole pairs), starting at pair `first_pair`; cached per database.
-PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0 ) {
+// The queue is consumed in table order by `groups` resident lane groups.  Towards the end of the table the batches shrink
+// (guided self-scheduling: at most 1/(2 groups) of the columns that are left, never below `min_cols`), so that the groups
+// finish within a small batch of each other instead of a full one - with ~8 batches per group the idle tail of a launch
+// drops from ~6 % to < 1 % of its duration, for a few more wavefront fills.  groups = 0: uniform batches.
+PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0, uint32_t groups = 0, uint32_t min_cols = 512 ) {
     PackedDb & db = ctx.db;
-    const std::pair<uint32_t, uint32_t> key( cols, first_pair );
+    if( getenv( "LIBSSA_B200_NO_TAPER" ) ) groups = 0;
+    const std::array<uint32_t, 4> key = { cols, first_pair, groups, min_cols };
     auto it = db.batch_tables.find( key );
     if( it != db.batch_tables.end() ) return it->second;
     PackedDb::BatchTable & bt = db.batch_tables[key];
@@ -438,8 +444,10 @@ PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0 ) {
         b.col0 = db.pair_col[p];
         b.bnd0 = db.pair_col[p];
         b.out0 = (uint32_t) p;
+        uint64_t want = cols;
+        if( groups > 0 ) want = std::min<uint64_t>( cols, std::max<uint64_t>( min_cols, ( db.total_cols - db.pair_col[p] ) / ( 2ull * groups ) ) );
         size_t q = p;
-        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < cols ) q++;
+        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < want ) q++;
         if( db.pair_col[q] - db.pair_col[p] > 0x7fffffffull ) fatal( "libssa_b200: batch too long." );
         b.ncols = (uint32_t) ( db.pair_col[q] - db.pair_col[p] );
         bt.batches.push_back( b );
@@ -954,7 +962,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     const uint64_t groups = (uint64_t) sms * packed_blocks_per_sm( R, nw, npass > 1 ) * ( SCORE_THREADS / 32 ) * ( 32 / G );
     uint32_t batch_cols = 4096;
     while( batch_cols > 256 && db.total_cols / batch_cols < 6 * groups ) batch_cols /= 2;
-    PackedDb::BatchTable & bt = batch_table( batch_cols );
+    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, (uint32_t) std::max( 128, 16 * G ) );
     const size_t b0 = std::lower_bound( bt.pair0.begin(), bt.pair0.end(), (uint32_t) p_long_end ) - bt.pair0.begin();
     const size_t bulk_pair0 = b0 < bt.batches.size() ? bt.pair0[b0] : db.npairs;   // bulk class = pairs [bulk_pair0, npairs)
     size_t long_pair0 = p_safe;                                                  // long class = pairs [long_pair0, bulk_pair0)
@@ -1023,7 +1031,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             const uint64_t ps_groups = (uint64_t) sms * packed_blocks_per_sm( ps.R, nw, true ) * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
             uint32_t ps_cols = 4096;
             while( ps_cols > 256 && db.total_cols / ps_cols < 6 * ps_groups ) ps_cols /= 2;
-            PackedDb::BatchTable & pt = batch_table( ps_cols, (uint32_t) bulk_pair0 );
+            PackedDb::BatchTable & pt = batch_table( ps_cols, (uint32_t) bulk_pair0, (uint32_t) ps_groups, (uint32_t) std::max( 128, 16 * ps.G ) );
             ps.d_batches = pt.d_batches.p;
             ps.nbatches = (uint32_t) pt.batches.size();
         }
