@@ -69,15 +69,15 @@ if __name__ == "__main__":
     share = launches()
     meta = json.load(open(os.path.join(G, "bench_%s.json" % tag)))
     res_per_gpu = meta["config"]["db_residues"] / meta["n_gpus"]
-    # prof_<tag>_top: P33450 (5147 aa) vs the 500k database: one pass = 896 query rows
-    top = kernel_report("prof_%s_top.ncu-rep" % tag, "ncu --set full: dominant kernel of the benchmark step (P33450, 5147 aa, one of 6 passes of 896 rows)",
-                        res_per_gpu * 5147 / 6.0,
-                        "`ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:score_kernel<1, 28 -s 13 -c 2 python tools/profile_target.py P33450 sw 500000` "
-                        "(same 500 000-record database shape as bench.py; the capture follows a plain run of the same command that exited 0).")
+    # prof_<tag>_top: P33450 (5147 aa) vs the 500k database: one full pass = 32 lanes x 32 rows = 1024 query rows
+    top = kernel_report("prof_%s_top.ncu-rep" % tag, "ncu --set full: dominant kernel of the benchmark step (P33450, 5147 aa, one of the 5 full passes of 1024 rows)",
+                        res_per_gpu * 1024.0,
+                        "`ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:score_kernel<.bool.1, .int.32, .bool.0, .int.1' -s 5 -c 2 "
+                        "python tools/profile_target.py P33450 sw 500000` (same 500 000-record database shape as bench.py; the capture follows a plain run of the same command that exited 0).")
     json.dump({"kernel": top[-1]["kernel"], "dram_bytes_per_launch": top[-1]["dram_bytes"], "seconds_under_ncu": top[-1]["seconds"],
-               "algorithmic_cells_per_launch": res_per_gpu * 5147 / 6.0, "algorithmic_bytes_per_launch": res_per_gpu * 1.0 + 4.0 * meta["config"]["db_records"] / meta["n_gpus"],
+               "algorithmic_cells_per_launch": res_per_gpu * 1024.0, "algorithmic_bytes_per_launch": res_per_gpu * 1.0 + 4.0 * meta["config"]["db_records"] / meta["n_gpus"],
                "score_kernel_share_of_step": share, "source": "profiles/prof_%s_top.md" % tag}, open(os.path.join(P, "roofline_%s.json" % tag), "w"), indent=1)
     q375 = kernel_report("prof_%s_q375.ncu-rep" % tag, "ncu --set full: bulk kernel of a 375-aa query (P07327, groups of 16 lanes x 24 rows, two columns per step)",
-                         res_per_gpu * 375, "`ncu --set full ... -k regex:score_kernel<1, 24 ... python tools/profile_target.py P07327 sw 500000`; pairs longer than the "
+                         res_per_gpu * 375, "`ncu --set full ... -k 'regex:score_kernel<.bool.1, .int.24,' ... python tools/profile_target.py P07327 sw 500000`; pairs longer than the "
                          "long-class threshold run in a separate (32 x 12) launch and are not part of this launch, so the derived GCUPS slightly overstates.")
     print("share", share, top[-1], q375[-1])
