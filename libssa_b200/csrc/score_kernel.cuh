@@ -129,7 +129,10 @@ __device__ __forceinline__ uint4 lds128( uint32_t addr ) {
 #ifndef SSA_MR_HI
 #define SSA_MR_HI 0
 #endif
-__host__ __device__ constexpr int merge_rows( int R ) { return R <= 16 ? R : SSA_MR_HI; }
+#ifndef SSA_MR_FULL
+#define SSA_MR_FULL 16
+#endif
+__host__ __device__ constexpr int merge_rows( int R ) { return R <= SSA_MR_FULL ? R : SSA_MR_HI; }
 
 // words of shared memory the profile of one pass needs
 template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     constexpr int MR = PACKED ? merge_rows( R ) : 0;
     // packed tier: 128-bit entries for the first MR rows, then 64-bit entries; wide tier: 32-bit entries [row][residue][lane]
     const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * ( PACKED ? 16 : 4 );
+    constexpr int NQ16 = PACKED ? ( R - MR ) / 4 : 0;   // 64-bit entries (4 rows, two scores per word) after the first MR rows
     const uint32_t prof_base16 = (uint32_t) __cvta_generic_to_shared( prof ) + MR * 4096 + lane * 8;
     const uint32_t K65536 = a.k65536;    // 65536 as a kernel argument: the merge stays an IMAD with a constant-bank operand
                                          // (FMA-side pipe) instead of being strength-reduced to a shift/LEA on the ALU pipe
@@ -208,51 +212,35 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         T hd = diag;
         diag = h_in;
         if( PACKED ) {
-            const uint32_t pa = prof_base + ( ( ci & 31u ) << 9 );
-            const uint32_t pb = prof_base + ( ( ( ci >> 5 ) & 31u ) << 9 );
-            const uint32_t pa16 = prof_base16 + ( ( ci & 31u ) << 8 );
-            const uint32_t pb16 = prof_base16 + ( ( ( ci >> 5 ) & 31u ) << 8 );
+            const uint32_t ra = ci & 31u, rb = ( ci >> 5 ) & 31u;
             T hd2 = hd;
+            // rows 2k, 2k+1 with their (A:B) substitution scores v0, v1
+            auto dp_pair = [&]( const int k, const uint32_t v0, const uint32_t v1 ) {
+                const T t0 = A::add( hd2, (T) v0 );
+                const T t1 = A::add( Hp[2 * k], (T) v1 );
+                hd2 = Hp[2 * k + 1];
+                T hq;
+                Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
+                hq = A::add( Hp[2 * k], QR );
+                E[2 * k] = A::addmax( E[2 * k], RG, hq );
+                f = A::addmax( f, RG, hq );
+                Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
+                hq = A::add( Hp[2 * k + 1], QR );
+                E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
+                f = A::addmax( f, RG, hq );
+                S = A::max3( S, t0, t1 );
+            };
 #pragma unroll
-            for( int k2 = 0; k2 < R / 4; k2++ ) {
-                const bool m32 = 4 * k2 < MR;
-                uint2 la2 = make_uint2( 0, 0 ), lb2 = make_uint2( 0, 0 );
-                uint4 la4 = make_uint4( 0, 0, 0, 0 ), lb4 = make_uint4( 0, 0, 0, 0 );
-                if( m32 ) {
-                    la4 = lds128( pa + k2 * 16384 );
-                    lb4 = lds128( pb + k2 * 16384 );
-                }
-                else {
-                    la2 = lds64( pa16 + ( k2 - MR / 4 ) * 8192 );
-                    lb2 = lds64( pb16 + ( k2 - MR / 4 ) * 8192 );
-                }
+            for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
+                const uint4 la = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lb = lds128( prof_base + ( rb << 9 ) + q * 16384 );
+                dp_pair( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
+                dp_pair( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+            }
 #pragma unroll
-                for( int j = 0; j < 2; j++ ) {
-                    const int k = 2 * k2 + j;
-                    uint32_t v0, v1;   // (A:B) substitution scores of rows 2k, 2k+1
-                    if( m32 ) {
-                        v0 = ( j ? la4.z : la4.x ) * K65536 + ( j ? lb4.z : lb4.x );
-                        v1 = ( j ? la4.w : la4.y ) * K65536 + ( j ? lb4.w : lb4.y );
-                    }
-                    else {
-                        const uint32_t la = j ? la2.y : la2.x, lb = j ? lb2.y : lb2.x;
-                        v0 = __byte_perm( lb, la, 0x5410 );
-                        v1 = __byte_perm( lb, la, 0x7632 );
-                    }
-                    const T t0 = A::add( hd2, (T) v0 );
-                    const T t1 = A::add( Hp[2 * k], (T) v1 );
-                    hd2 = Hp[2 * k + 1];
-                    T hq;
-                    Hp[2 * k] = NW ? A::max3( t0, E[2 * k], f ) : A::max3_relu( t0, E[2 * k], f );
-                    hq = A::add( Hp[2 * k], QR );
-                    E[2 * k] = A::addmax( E[2 * k], RG, hq );
-                    f = A::addmax( f, RG, hq );
-                    Hp[2 * k + 1] = NW ? A::max3( t1, E[2 * k + 1], f ) : A::max3_relu( t1, E[2 * k + 1], f );
-                    hq = A::add( Hp[2 * k + 1], QR );
-                    E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
-                    f = A::addmax( f, RG, hq );
-                    S = A::max3( S, t0, t1 );
-                }
+            for( int q = 0; q < NQ16; q++ ) {      // two scores per word, four rows per load
+                const uint2 la = lds64( prof_base16 + ( ra << 8 ) + q * 8192 ), lb = lds64( prof_base16 + ( rb << 8 ) + q * 8192 );
+                dp_pair( MR / 2 + 2 * q, __byte_perm( lb.x, la.x, 0x5410 ), __byte_perm( lb.x, la.x, 0x7632 ) );
+                dp_pair( MR / 2 + 2 * q + 1, __byte_perm( lb.y, la.y, 0x5410 ), __byte_perm( lb.y, la.y, 0x7632 ) );
             }
         }
         else {
@@ -481,86 +469,64 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // (old H + substitution score) is formed before that row's H register is overwritten, so every H
                 // stays in one physical register across steps.
                 const uint32_t ra = cia & 31u, rb = ( cia >> 5 ) & 31u, sa = cib & 31u, sb = ( cib >> 5 ) & 31u;
-                const uint32_t paa = prof_base + ( ra << 9 ), pba = prof_base + ( rb << 9 );
-                const uint32_t pab = prof_base + ( sa << 9 ), pbb = prof_base + ( sb << 9 );
-                const uint32_t paa16 = prof_base16 + ( ra << 8 ), pba16 = prof_base16 + ( rb << 8 );
-                const uint32_t pab16 = prof_base16 + ( sa << 8 ), pbb16 = prof_base16 + ( sb << 8 );
                 T fa = fa_in, fb = fb_in;
                 T ha_prev = ha_in;                       // H of column A, previous row (diagonal of column B)
                 T hda = diag;                            // H of column A-1, previous row (diagonal of column A)
                 diag = hb_in;
+                // rows 2k, 2k+1 of both columns; va0/va1 and vb0/vb1 = (A:B) substitution scores in column A resp. B
+                auto dp_pair = [&]( const int k, const uint32_t va0, const uint32_t va1, const uint32_t vb0, const uint32_t vb1 ) {
+                    // diagonal candidates of column A are formed from the OLD H registers before they are overwritten
+                    const T ta0 = A::add( hda, (T) va0 );
+                    const T ta1 = A::add( Hp[2 * k], (T) va1 );
+                    hda = Hp[2 * k + 1];
+                    T hq;
+                    // column A, row 2k
+                    const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
+                    hq = A::add( ha0, QR );
+                    const T ea0 = A::addmax( E[2 * k], RG, hq );
+                    fa = A::addmax( fa, RG, hq );
+                    // column B, row 2k
+                    const T tb0 = A::add( ha_prev, (T) vb0 );
+                    Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
+                    hq = A::add( Hp[2 * k], QR );
+                    E[2 * k] = A::addmax( ea0, RG, hq );
+                    fb = A::addmax( fb, RG, hq );
+                    // column A, row 2k+1
+                    const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
+                    hq = A::add( ha1, QR );
+                    const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
+                    fa = A::addmax( fa, RG, hq );
+                    // column B, row 2k+1
+                    const T tb1 = A::add( ha0, (T) vb1 );
+                    Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
+                    hq = A::add( Hp[2 * k + 1], QR );
+                    E[2 * k + 1] = A::addmax( ea1, RG, hq );
+                    fb = A::addmax( fb, RG, hq );
+                    ha_prev = ha1;
+                    // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
+                    // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
+                    // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
+                    // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
+                    // as an upper range guard.
+                    S = A::max3( S, ta0, ta1 );
+                    S = A::max3( S, tb0, tb1 );
+                };
+                // one shared load per sequence and column fetches the scores of four query rows
 #pragma unroll
-                for( int k2 = 0; k2 < R / 4; k2++ ) {
-                    // one shared load per sequence and column fetches the scores of four query rows
-                    const bool m32 = 4 * k2 < MR;
-                    uint2 laa2 = make_uint2( 0, 0 ), lba2 = laa2, lab2 = laa2, lbb2 = laa2;
-                    uint4 laa4 = make_uint4( 0, 0, 0, 0 ), lba4 = laa4, lab4 = laa4, lbb4 = laa4;
-                    if( m32 ) {
-                        laa4 = lds128( paa + k2 * 16384 );
-                        lba4 = lds128( pba + k2 * 16384 );
-                        lab4 = lds128( pab + k2 * 16384 );
-                        lbb4 = lds128( pbb + k2 * 16384 );
-                    }
-                    else {
-                        laa2 = lds64( paa16 + ( k2 - MR / 4 ) * 8192 );
-                        lba2 = lds64( pba16 + ( k2 - MR / 4 ) * 8192 );
-                        lab2 = lds64( pab16 + ( k2 - MR / 4 ) * 8192 );
-                        lbb2 = lds64( pbb16 + ( k2 - MR / 4 ) * 8192 );
-                    }
+                for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
+                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lba = lds128( prof_base + ( rb << 9 ) + q * 16384 );
+                    const uint4 lab = lds128( prof_base + ( sa << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
+                    dp_pair( 2 * q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y );
+                    dp_pair( 2 * q + 1, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
+                }
 #pragma unroll
-                    for( int j = 0; j < 2; j++ ) {
-                        const int k = 2 * k2 + j;
-                        uint32_t va0, va1, vb0, vb1;   // (A:B) substitution scores of rows 2k, 2k+1 in column A resp. B
-                        if( m32 ) {
-                            va0 = ( j ? laa4.z : laa4.x ) * K65536 + ( j ? lba4.z : lba4.x );
-                            va1 = ( j ? laa4.w : laa4.y ) * K65536 + ( j ? lba4.w : lba4.y );
-                            vb0 = ( j ? lab4.z : lab4.x ) * K65536 + ( j ? lbb4.z : lbb4.x );
-                            vb1 = ( j ? lab4.w : lab4.y ) * K65536 + ( j ? lbb4.w : lbb4.y );
-                        }
-                        else {
-                            const uint32_t laa = j ? laa2.y : laa2.x, lba = j ? lba2.y : lba2.x;
-                            const uint32_t lab = j ? lab2.y : lab2.x, lbb = j ? lbb2.y : lbb2.x;
-                            va0 = __byte_perm( lba, laa, 0x5410 );
-                            va1 = __byte_perm( lba, laa, 0x7632 );
-                            vb0 = __byte_perm( lbb, lab, 0x5410 );
-                            vb1 = __byte_perm( lbb, lab, 0x7632 );
-                        }
-                        // diagonal candidates of column A are formed from the OLD H registers before they are overwritten
-                        const T ta0 = A::add( hda, (T) va0 );
-                        const T ta1 = A::add( Hp[2 * k], (T) va1 );
-                        hda = Hp[2 * k + 1];
-                        T hq;
-                        // column A, row 2k
-                        const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
-                        hq = A::add( ha0, QR );
-                        const T ea0 = A::addmax( E[2 * k], RG, hq );
-                        fa = A::addmax( fa, RG, hq );
-                        // column B, row 2k
-                        const T tb0 = A::add( ha_prev, (T) vb0 );
-                        Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
-                        hq = A::add( Hp[2 * k], QR );
-                        E[2 * k] = A::addmax( ea0, RG, hq );
-                        fb = A::addmax( fb, RG, hq );
-                        // column A, row 2k+1
-                        const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
-                        hq = A::add( ha1, QR );
-                        const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
-                        fa = A::addmax( fa, RG, hq );
-                        // column B, row 2k+1
-                        const T tb1 = A::add( ha0, (T) vb1 );
-                        Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
-                        hq = A::add( Hp[2 * k + 1], QR );
-                        E[2 * k + 1] = A::addmax( ea1, RG, hq );
-                        fb = A::addmax( fb, RG, hq );
-                        ha_prev = ha1;
-                        // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
-                        // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
-                        // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
-                        // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
-                        // as an upper range guard.
-                        S = A::max3( S, ta0, ta1 );
-                        S = A::max3( S, tb0, tb1 );
-                    }
+                for( int q = 0; q < NQ16; q++ ) {      // two scores per word, four rows per load
+                    const uint2 laa = lds64( prof_base16 + ( ra << 8 ) + q * 8192 ), lba = lds64( prof_base16 + ( rb << 8 ) + q * 8192 );
+                    const uint2 lab = lds64( prof_base16 + ( sa << 8 ) + q * 8192 ), lbb = lds64( prof_base16 + ( sb << 8 ) + q * 8192 );
+                    dp_pair( MR / 2 + 2 * q, __byte_perm( lba.x, laa.x, 0x5410 ), __byte_perm( lba.x, laa.x, 0x7632 ),
+                            __byte_perm( lbb.x, lab.x, 0x5410 ), __byte_perm( lbb.x, lab.x, 0x7632 ) );
+                    dp_pair( MR / 2 + 2 * q + 1, __byte_perm( lba.y, laa.y, 0x5410 ), __byte_perm( lba.y, laa.y, 0x7632 ),
+                            __byte_perm( lbb.y, lab.y, 0x5410 ), __byte_perm( lbb.y, lab.y, 0x7632 ) );
                 }
                 ha_last = ha_prev;
                 fa_last = fa;
