@@ -958,10 +958,12 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
         }
     }
 
-    // batch size of the bulk class: ~6 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
+    // batch size of the bulk class: at least ~3 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
     const uint64_t groups = (uint64_t) sms * packed_blocks_per_sm( R, nw, npass > 1 ) * ( SCORE_THREADS / 32 ) * ( 32 / G );
     uint32_t batch_cols = 4096;
-    while( batch_cols > 256 && db.total_cols / batch_cols < 6 * groups ) batch_cols /= 2;   // (the choice is flat between 3 and 12 per group [B200])
+    // (with the shrinking tail of batch_table the choice is flat between 2 and 12 batches per group [B200]; fewer, longer batches
+    // mean fewer wavefront fills on small databases)
+    while( batch_cols > 256 && db.total_cols / batch_cols < 3 * groups ) batch_cols /= 2;
     PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, (uint32_t) std::max( 128, 16 * G ) );
     const size_t b0 = std::lower_bound( bt.pair0.begin(), bt.pair0.end(), (uint32_t) p_long_end ) - bt.pair0.begin();
     const size_t bulk_pair0 = b0 < bt.batches.size() ? bt.pair0[b0] : db.npairs;   // bulk class = pairs [bulk_pair0, npairs)
