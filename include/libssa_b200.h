@@ -84,6 +84,22 @@ size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint
         uint64_t * ids_out, int64_t * scores_out );
 size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out );
 /*
+ * Host-only pieces of the scoring schedule (no GPU involved), exposed so they can be tested on CPU.
+ * ssa_b200_host_plan_passes: the passes of the packed tier for a query of qlen rows - pass i covers query rows
+ * [rowbase[i], rowbase[i] + G[i] * R[i]) on groups of G[i] lanes x R[i] rows; queries beyond 1024 rows run as full
+ * passes of 32 x 32 rows plus a remainder pass (total_cols / longest_cols: stream columns of the packed class and of
+ * its longest pair; sms: multiprocessors).  Replaces the reference's "whole query per SIMD block" loop
+ * (src/algo/simd/search_simd_sw.c:238-277).  Returns the number of passes (at most max_passes are written).
+ * ssa_b200_host_partition_batches: first pair of every work batch of the persistent scoring kernels - the counterpart of
+ * the reference's chunk cursor (src/db_adapter.c:212-239): whole pairs, `cols` stream columns per batch, shrinking
+ * towards the end of the queue when groups > 0.  pair_col[npairs + 1] = first stream column of each pair.
+ */
+size_t ssa_b200_host_plan_passes( size_t qlen, uint64_t total_cols, uint64_t longest_cols, int sms, int * G_out, int * R_out,
+        size_t * rowbase_out, size_t max_passes );
+size_t ssa_b200_host_partition_batches( const uint64_t * pair_col, size_t npairs, size_t first_pair, uint32_t cols, uint32_t groups,
+        uint32_t min_cols, uint32_t * first_pair_out, size_t max_batches );
+
+/*
  * Hit selection of a search over several query frames and/or several database entries per record (both strands,
  * translated searches): the reference's per-chunk schedule  frames x entries -> overflow lists re-run under every
  * frame  (src/algo/8/search_8.c:94-124, src/algo/16/search_16.c:92-113, src/algo/64/search_64.c:44-56), the bounded

@@ -264,6 +264,27 @@ class LibSSA:
         n = f(lens.ctypes.data, len(lens), out.ctypes.data)
         return out[:n]
 
+    def host_plan_passes(self, qlen, total_cols=80_000_000, longest_cols=5000, sms=148):
+        """[(G, R, rowbase)] of the packed tier's passes for a query of qlen rows (host-only)."""
+        import numpy as np
+        G = np.zeros(4096, dtype=np.int32); R = np.zeros(4096, dtype=np.int32); base = np.zeros(4096, dtype=np.uint64)
+        f = self.lib.ssa_b200_host_plan_passes
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        n = f(qlen, total_cols, longest_cols, sms, G.ctypes.data, R.ctypes.data, base.ctypes.data, 4096)
+        return [(int(G[i]), int(R[i]), int(base[i])) for i in range(min(n, 4096))]
+
+    def host_partition_batches(self, pair_col, first_pair, cols, groups, min_cols):
+        """first pair of every work batch over pair_col[npairs + 1] (host-only)."""
+        import numpy as np
+        pc = np.ascontiguousarray(pair_col, dtype=np.uint64)
+        out = np.zeros(max(len(pc), 1), dtype=np.uint32)
+        f = self.lib.ssa_b200_host_partition_batches
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
+        n = f(pc.ctypes.data, len(pc) - 1, first_pair, cols, groups, min_cols, out.ctypes.data, len(out))
+        return out[:n]
+
     def set_allgather(self, fn):
         """Register the collective that merges shard results: fn(send_ptr, recv_ptr, nbytes, cuda_stream_ptr)."""
         proto = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -426,6 +426,23 @@ void parallel_for( size_t n, size_t grain, const std::function<void( size_t, siz
 
 // Work batches of the packed tier: runs of whole pairs with at least `cols` columns, built on demand and cached.
 // Small batches balance the persistent grid's work queue, large ones amortise the G-1 fill/drain steps.
+// First pair of every work batch: whole pairs, at least `want` stream columns each (the last batch may be shorter), where
+// `want` = cols, or with groups > 0 min( cols, max( min_cols, columns left / (2 groups) ) ).  pair_col[npairs + 1].
+std::vector<uint32_t> partition_batches( const uint64_t * pair_col, size_t npairs, size_t first_pair, uint32_t cols, uint32_t groups,
+        uint32_t min_cols ) {
+    std::vector<uint32_t> first;
+    const uint64_t total = pair_col[npairs];
+    for( size_t p = first_pair; p < npairs; ) {
+        uint64_t want = cols;
+        if( groups > 0 ) want = std::min<uint64_t>( cols, std::max<uint64_t>( min_cols, ( total - pair_col[p] ) / ( 2ull * groups ) ) );
+        size_t q = p;
+        while( q < npairs && pair_col[q] - pair_col[p] < want ) q++;
+        first.push_back( (uint32_t) p );
+        p = q;
+    }
+    return first;
+}
+
 // Work batches of ~`cols` stream columns (whole pairs), starting at pair `first_pair`; cached per database.
 // The queue is consumed in table order by `groups` resident lane groups.  Towards the end of the table the batches shrink
 // (guided self-scheduling: at most 1/(2 groups) of the columns that are left, never below `min_cols`), so that the groups
@@ -438,21 +455,17 @@ PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0, uint
     auto it = db.batch_tables.find( key );
     if( it != db.batch_tables.end() ) return it->second;
     PackedDb::BatchTable & bt = db.batch_tables[key];
-    for( size_t p = first_pair; p < db.npairs; ) {
+    bt.pair0 = partition_batches( db.pair_col.data(), db.npairs, first_pair, cols, groups, min_cols );
+    for( size_t i = 0; i < bt.pair0.size(); i++ ) {
+        const size_t p = bt.pair0[i], q = i + 1 < bt.pair0.size() ? bt.pair0[i + 1] : db.npairs;
         Batch b;
         memset( &b, 0, sizeof( b ) );
         b.col0 = db.pair_col[p];
         b.bnd0 = db.pair_col[p];
         b.out0 = (uint32_t) p;
-        uint64_t want = cols;
-        if( groups > 0 ) want = std::min<uint64_t>( cols, std::max<uint64_t>( min_cols, ( db.total_cols - db.pair_col[p] ) / ( 2ull * groups ) ) );
-        size_t q = p;
-        while( q < db.npairs && db.pair_col[q] - db.pair_col[p] < want ) q++;
         if( db.pair_col[q] - db.pair_col[p] > 0x7fffffffull ) fatal( "libssa_b200: batch too long." );
         b.ncols = (uint32_t) ( db.pair_col[q] - db.pair_col[p] );
         bt.batches.push_back( b );
-        bt.pair0.push_back( (uint32_t) p );
-        p = q;
     }
     bt.d_batches.reserve( bt.batches.size() + 1 );
     if( !bt.batches.empty() )
@@ -1941,4 +1954,32 @@ __attribute__( ( visibility( "default" ) ) ) void ssa_b200_get_stats( ssa_b200_s
     if( out ) *out = ctx.stats;
 }
 __attribute__( ( visibility( "default" ) ) ) int ssa_b200_version( void ) { return 100; }
+// host-only: the packed tier's passes for a query of qlen rows (see plan_passes)
+__attribute__( ( visibility( "default" ) ) ) size_t ssa_b200_host_plan_passes( size_t qlen, uint64_t total_cols, uint64_t longest_cols, int sms,
+        int * G_out, int * R_out, size_t * rowbase_out, size_t max_passes ) {
+    if( qlen == 0 ) return 0;
+    const Plan pl = make_plan( qlen );
+    std::vector<PassLaunch> v;
+    if( pl.npass > 1 )
+        v = plan_passes( qlen, pl.R, pl.npass, total_cols, longest_cols, sms );
+    else {
+        PassLaunch ps;
+        ps.G = pl.G;
+        ps.R = pl.R;
+        v.push_back( ps );
+    }
+    for( size_t i = 0; i < v.size() && i < max_passes; i++ ) {
+        G_out[i] = v[i].G;
+        R_out[i] = v[i].R;
+        rowbase_out[i] = v[i].rowbase;
+    }
+    return v.size();
+}
+// host-only: the work-queue partition of a stream of pairs (see partition_batches / batch_table)
+__attribute__( ( visibility( "default" ) ) ) size_t ssa_b200_host_partition_batches( const uint64_t * pair_col, size_t npairs, size_t first_pair,
+        uint32_t cols, uint32_t groups, uint32_t min_cols, uint32_t * first_pair_out, size_t max_batches ) {
+    const std::vector<uint32_t> first = partition_batches( pair_col, npairs, first_pair, cols, groups, min_cols );
+    for( size_t i = 0; i < first.size() && i < max_batches; i++ ) first_pair_out[i] = first[i];
+    return first.size();
+}
 }

@@ -171,6 +171,55 @@ def test_replay_matches_oracle_with_ties(prod_host, port):
     assert prod_host.host_replay(np.zeros(0), np.zeros(0), 5) == []
 
 
+def test_pass_plan_covers_every_query_row(prod_host):
+    """packed tier: the passes tile the query rows without gaps; long queries = full 32 x 32 passes + one remainder pass"""
+    for qlen in list(range(1, 140)) + [255, 256, 257, 375, 511, 512, 513, 1000, 1023, 1024, 1025, 1030, 1100, 1500, 2005, 2047, 2048,
+                                        2049, 3100, 5119, 5120, 5121, 5147, 10000, 35213]:
+        passes = prod_host.host_plan_passes(qlen)
+        assert passes, qlen
+        row = 0
+        for i, (G, R, base) in enumerate(passes):
+            assert G in (4, 8, 16, 32) and R in (4, 8, 12, 16, 20, 24, 28, 32), (qlen, passes)
+            assert base == row, (qlen, passes)
+            if i + 1 < len(passes):
+                assert G == 32, (qlen, passes)          # only the last pass may run on narrow groups
+            row += G * R
+        assert row >= qlen, (qlen, passes)
+        assert row - passes[-1][0] * passes[-1][1] < qlen, (qlen, passes)     # no pass beyond the query
+        if qlen > 1024:
+            assert row - qlen < 128, (qlen, passes)   # at most a few padded rows (a uniform plan pads up to a whole lane block)
+    # the 5147-row benchmark query: 5 x (32 x 32) + a small remainder pass
+    p = prod_host.host_plan_passes(5147)
+    assert [x[:2] for x in p[:5]] == [(32, 32)] * 5 and len(p) == 6 and p[5][0] * p[5][1] >= 27
+    # a very long pair in the packed class keeps the remainder pass off the narrowest groups
+    wide = prod_host.host_plan_passes(5147, total_cols=2_000_000, longest_cols=400_000)
+    assert wide[-1][0] > p[-1][0]
+
+
+def test_work_batches_partition_the_stream(prod_host):
+    """work queue: whole pairs, contiguous, `cols` columns per batch, shrinking towards the end but never below min_cols"""
+    rng = np.random.default_rng(5)
+    lens = np.sort(rng.integers(30, 3000, size=20000))[::-1]
+    cols_of = (lens + 1) & ~1
+    pair_col = np.concatenate([[0], np.cumsum(cols_of)]).astype(np.uint64)
+    total = int(pair_col[-1])
+    for first_pair, cols, groups, min_cols in ((0, 4096, 0, 512), (0, 4096, 300, 512), (17, 2048, 1000, 128), (0, 256, 5000, 128)):
+        first = prod_host.host_partition_batches(pair_col, first_pair, cols, groups, min_cols)
+        assert first[0] == first_pair and (np.diff(first.astype(np.int64)) > 0).all()
+        bounds = np.concatenate([first, [len(lens)]])
+        size = (pair_col[bounds[1:]] - pair_col[bounds[:-1]]).astype(np.int64)
+        assert size.sum() == total - int(pair_col[first_pair])
+        left = total - pair_col[bounds[:-1]].astype(np.int64)
+        want = np.full(len(size), cols) if groups == 0 else np.minimum(cols, np.maximum(min_cols, left // (2 * groups)))
+        assert (size[:-1] >= want[:-1]).all()                                        # at least the wanted columns ...
+        assert (size[:-1] - cols_of[bounds[1:-1] - 1] < want[:-1]).all()             # ... and not a pair more than needed
+        if groups:
+            uniform = prod_host.host_partition_batches(pair_col, first_pair, cols, 0, min_cols)
+            assert len(first) >= len(uniform)
+            if total // cols > 4 * groups:
+                assert size[0] >= cols and size[-2] < cols                           # big batches first, small ones last
+
+
 def test_sharded_merge_two_ranks_gloo(tmp_path):
     """World-size-2 run of the shard/all-gather/replay logic on CPU (gloo): each rank scores its shard
     with the oracle standing in for the GPU kernels, the shard scores are all-gathered exactly as
