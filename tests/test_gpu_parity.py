@@ -42,11 +42,13 @@ def test_fixtures_through_c_abi(prod, entry):
 
 
 def test_live_reference_random_inputs(prod, ref, tmp_path):
+    """differential test against the compiled reference on random inputs; LIBSSA_B200_FUZZ_TRIALS=n runs a longer campaign"""
     from libssa_b200 import synth
-    rng = np.random.default_rng(2024)
-    for trial in range(6):
+    trials = int(os.environ.get("LIBSSA_B200_FUZZ_TRIALS", "8"))
+    rng = np.random.default_rng(2024 if trials == 8 else int(os.environ.get("LIBSSA_B200_FUZZ_SEED", "1")))
+    for trial in range(trials):
         n = int(rng.integers(1, 3000))
-        qlen = int(rng.choice([1, 2, 17, 33, 128, 129, 250, 700, 1300]))
+        qlen = int(rng.choice([1, 2, 17, 33, 128, 129, 250, 700, 1300, 2100]))
         q = synth.random_protein(rng, qlen)
         seqs = synth.protein_db(n, int(rng.integers(1, 1 << 30)), query=q, homolog_frac=0.03, n_dup=min(20, n // 3),
                                 mu=float(rng.choice([3.0, 5.0])), sigma=0.7, min_len=0, max_len=4000)
