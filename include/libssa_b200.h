@@ -83,6 +83,10 @@ size_t ssa_b200_host_arrival_order( const uint64_t * lens, size_t n, size_t chun
 size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
         uint64_t * ids_out, int64_t * scores_out );
 size_t ssa_b200_host_sorted_order( const uint64_t * lens, size_t n, uint32_t * sorted_out );
+/* the replay from the first `prefix` >= hitcount arrivals plus the later arrivals that beat the heap's root after them - what
+ * the library does on large databases so that only those records leave the device; equals ssa_b200_host_replay */
+size_t ssa_b200_host_replay_sparse( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
+        size_t prefix, uint64_t * ids_out, int64_t * scores_out );
 /*
  * Host-only pieces of the scoring schedule (no GPU involved), exposed so they can be tested on CPU.
  * ssa_b200_host_plan_passes: the passes of the packed tier for a query of qlen rows - pass i covers query rows

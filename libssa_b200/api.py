@@ -234,6 +234,18 @@ class LibSSA:
         n = f(sc.ctypes.data, order.ctypes.data, len(order), hitcount, ids.ctypes.data, out.ctypes.data)
         return [(int(out[i]), int(ids[i])) for i in range(n)]
 
+    def host_replay_sparse(self, scores_in_arrival_order, order, hitcount, prefix):
+        import numpy as np
+        sc = np.ascontiguousarray(scores_in_arrival_order, dtype=np.int32)
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        ids = np.zeros(max(hitcount, 1), dtype=np.uint64)
+        out = np.zeros(max(hitcount, 1), dtype=np.int64)
+        f = self.lib.ssa_b200_host_replay_sparse
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        n = f(sc.ctypes.data, order.ctypes.data, len(order), hitcount, prefix, ids.ctypes.data, out.ctypes.data)
+        return [(int(out[i]), int(ids[i])) for i in range(n)]
+
     def host_frames_replay(self, slot_lens, chunk_slots, bit_width, buffer_max, scores, hitcount, ovf8=None, ovf16=None):
         """Hit list [(score, slot, frame)] of a multi-frame search; scores/ovf8/ovf16 are [q_count][nslots]."""
         import numpy as np

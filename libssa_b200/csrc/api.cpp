@@ -237,6 +237,31 @@ API size_t ssa_b200_host_replay( const int32_t * scores_in_arrival_order, const 
     return hits.size();
 }
 
+// the sparse form of the same replay (replay_topk_sparse), candidates found by a host scan: must equal ssa_b200_host_replay
+API size_t ssa_b200_host_replay_sparse( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t hitcount,
+        size_t prefix, uint64_t * ids_out, int64_t * scores_out ) {
+    std::vector<Hit> hits;
+    const size_t m = std::min( prefix, n );
+    std::vector<int32_t> cs;
+    std::vector<uint32_t> ci;
+    auto fetch = [&]( int32_t thr, const int32_t ** s, const uint32_t ** i ) -> size_t {
+        for( size_t a = m; a < n; a++ )
+            if( scores_in_arrival_order[a] > thr ) {
+                cs.push_back( scores_in_arrival_order[a] );
+                ci.push_back( order[a] );
+            }
+        *s = cs.data();
+        *i = ci.data();
+        return cs.size();
+    };
+    replay_topk_sparse( scores_in_arrival_order, order, m, hitcount, fetch, hits );
+    for( size_t i = 0; i < hits.size(); i++ ) {
+        ids_out[i] = hits[i].db_id;
+        scores_out[i] = hits[i].score;
+    }
+    return hits.size();
+}
+
 API size_t ssa_b200_host_frames_replay( const uint64_t * slot_lens, size_t nslots, size_t chunk_slots, int bit_width, int q_count,
         int buffer_max, const int32_t * scores, const int32_t * ovf8, const int32_t * ovf16, size_t hitcount,
         uint32_t * slots_out, uint8_t * frames_out, int64_t * scores_out ) {

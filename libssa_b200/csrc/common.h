@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/libssa.h"
@@ -98,6 +99,10 @@ void arrival_order( const std::vector<uint64_t> & lens, const int64_t * ovf8, co
 // replays thread heap + merge heap + final sort (reference minheap.c, manager.c:141-172)
 void replay_topk( const int32_t * scores_in_arrival_order, const uint32_t * order, size_t n, size_t k,
         std::vector<Hit> & out );
+// the same result from the first m >= k arrivals plus the later arrivals that score above the heap's root after those m
+// (fetch( root, &scores, &ids ) returns them in arrival order): all other records are rejected by the reference's heap
+void replay_topk_sparse( const int32_t * prefix_scores, const uint32_t * prefix_ids, size_t m, size_t k,
+        const std::function<size_t( int32_t, const int32_t **, const uint32_t ** )> & fetch, std::vector<Hit> & out );
 // General form for searches with several query frames and/or several database entries per record (strands, 6-frame
 // translation).  `slots` = database entries in provider order (buffer_max per record, length 0 = absent);
 // scores/ovf8/ovf16 are indexed [frame][slot].  Produces the reference's final, sorted hit list.

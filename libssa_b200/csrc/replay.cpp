@@ -17,6 +17,7 @@
 #include "common.h"
 
 #include <algorithm>
+#include <functional>
 
 namespace {
 
@@ -154,6 +155,17 @@ void arrival_order( const std::vector<uint64_t> & lens, const int64_t * ovf8, co
     }
 }
 
+// manager.c:141-146: the thread heap is re-inserted in heap-array order, then both final sorts
+static void finish_replay( const Heap & thread_heap, size_t k, std::vector<Hit> & out ) {
+    Heap result( k );
+    for( const Hit & h : thread_heap.a ) result.add( h );
+    out = result.a;
+    std::sort( out.begin(), out.end(), []( const Hit & x, const Hit & y ) {
+        if( x.score != y.score ) return x.score > y.score;  // minheap.c:93-102, manager.c:68-77
+        return x.db_id > y.db_id;
+    } );
+}
+
 void replay_topk( const int32_t * scores, const uint32_t * order, size_t n, size_t k, std::vector<Hit> & out ) {
     Heap thread_heap( k );
     if( k > 0 ) {
@@ -164,13 +176,31 @@ void replay_topk( const int32_t * scores, const uint32_t * order, size_t n, size
         for( ; i < n; i++ )
             if( scores[i] > thread_heap.a[0].score ) thread_heap.add( Hit{ order[i], scores[i] } );
     }
-    Heap result( k );  // manager.c:141-146: thread heap re-inserted in heap-array order
-    for( const Hit & h : thread_heap.a ) result.add( h );
-    out = result.a;
-    std::sort( out.begin(), out.end(), []( const Hit & x, const Hit & y ) {
-        if( x.score != y.score ) return x.score > y.score;  // minheap.c:93-102, manager.c:68-77
-        return x.db_id > y.db_id;
-    } );
+    finish_replay( thread_heap, k, out );
+}
+
+// The same replay from the records that can touch the heap at all.  Once k records have arrived the root of the heap
+// is the k-th largest score so far and never decreases, so a record that arrives after the first m (m >= k) and does not
+// score above `threshold` = the root after those m is rejected whatever came in between: it need not be looked at.
+// prefix_*: the first m arrivals; cand_*: the later arrivals scoring above the threshold, in arrival order.
+// prefix_*: the first m arrivals; fetch( threshold, &scores, &ids ) supplies the later arrivals scoring above the threshold,
+// in arrival order.
+void replay_topk_sparse( const int32_t * prefix_scores, const uint32_t * prefix_ids, size_t m, size_t k,
+        const std::function<size_t( int32_t, const int32_t **, const uint32_t ** )> & fetch, std::vector<Hit> & out ) {
+    Heap thread_heap( k );
+    if( k > 0 && m > 0 ) {
+        size_t i = 0;
+        for( ; i < m && thread_heap.a.size() < k; i++ ) thread_heap.add( Hit{ prefix_ids[i], prefix_scores[i] } );
+        for( ; i < m; i++ )
+            if( prefix_scores[i] > thread_heap.a[0].score ) thread_heap.add( Hit{ prefix_ids[i], prefix_scores[i] } );
+        if( thread_heap.a.size() < k ) fatal( "libssa_b200: internal error: sparse replay with a prefix shorter than the hit list." );
+        const int32_t * cs = nullptr;
+        const uint32_t * ci = nullptr;
+        const size_t ncand = fetch( (int32_t) thread_heap.a[0].score, &cs, &ci );
+        for( size_t j = 0; j < ncand; j++ )
+            if( cs[j] > thread_heap.a[0].score ) thread_heap.add( Hit{ ci[j], cs[j] } );
+    }
+    finish_replay( thread_heap, k, out );
 }
 
 // Searches with several query frames and/or several database entries per record.  Per chunk the reference runs every

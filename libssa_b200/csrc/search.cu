@@ -155,7 +155,10 @@ struct Ctx {
     PinBuf<uint32_t> h_order;
     DevBuf<uint32_t> d_flag_list;
     PinBuf<uint32_t> h_profile[2], h_list;
-    PinBuf<int32_t> h_scores, h_first, h_pos;
+    PinBuf<int32_t> h_scores, h_first, h_pos, h_cand_score;
+    PinBuf<uint32_t> h_cand_pos, h_cand_id;
+    DevBuf<uint32_t> d_cand_pos, d_cand_id;
+    DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
     ssa_b200_stats_t stats;
 };
@@ -543,6 +546,22 @@ __global__ void count_ge_kernel( const int32_t * gathered, uint32_t stride, uint
 __global__ void count_set_kernel( const int32_t * p, uint32_t n, uint32_t * out ) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if( i < n && p[i] != 0x7fffffff ) atomicAdd( out, 1u );
+}
+
+// sparse heap replay: arrival positions >= first whose score exceeds thr (any order; few)
+__global__ void compact_greater_kernel( const int32_t * scores, uint32_t first, uint32_t n, int32_t thr, uint32_t * pos_out, int32_t * score_out,
+        uint32_t * counter ) {
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n && scores[i] > thr ) {
+        const uint32_t j = atomicAdd( counter, 1u );
+        pos_out[j] = i;
+        score_out[j] = scores[i];
+    }
+}
+
+__global__ void gather_u32_kernel( const uint32_t * table, const uint32_t * idx, uint32_t n, uint32_t * out ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n ) out[i] = table[idx[i]];
 }
 
 __global__ void fill_i32_kernel( int32_t * p, int32_t v, uint32_t n ) {
@@ -1198,8 +1217,10 @@ size_t gpu_arrival_order( int bit_width, size_t chunk, const int32_t * d_first_a
         a.pos_of_sorted = d_pos.p;
         arrival_kernel<<<ci.nchunks, 32, 0, ctx.stream>>>( a );
         ctx.stats.launches++;
-        CUDA_OK( cudaMemcpyAsync( h_order, ctx.d_order.p, ci.narr * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-        ctx.stats.d2h_bytes += ci.narr * sizeof( uint32_t );
+        if( h_order ) {  // nullptr: the caller fetches the part of ctx.d_order it needs
+            CUDA_OK( cudaMemcpyAsync( h_order, ctx.d_order.p, ci.narr * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            ctx.stats.d2h_bytes += ci.narr * sizeof( uint32_t );
+        }
     }
     return ci.narr;
 }
@@ -1463,6 +1484,12 @@ static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw ) {
 
 static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits );
 
+// sparse heap replay (replay_topk_sparse): the first m arrivals are replayed in full
+static size_t sparse_replay_prefix( size_t hitcount ) { return std::max<size_t>( 65536, 64 * hitcount ); }
+static bool sparse_replay_applies( size_t narr, size_t hitcount ) {
+    return narr > 4 * sparse_replay_prefix( hitcount ) && !getenv( "LIBSSA_B200_FULL_REPLAY" );
+}
+
 static void search_single( const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
     PackedDb & db = ctx.db;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
@@ -1622,8 +1649,9 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     }
     else if( use_gpu_arrival ) {
         ctx.h_order.reserve( nglob + 1 );
-        narr = gpu_arrival_order( req.bit_width, chunk, d_first_gathered, stride, ctx.d_pos_tmp, ctx.h_order.p );
-        order = ctx.h_order.p;   // complete once the stream is synchronised below
+        const bool sparse = sparse_replay_applies( chunk_info_for( chunk ).narr, req.hitcount );
+        narr = gpu_arrival_order( req.bit_width, chunk, d_first_gathered, stride, ctx.d_pos_tmp, sparse ? nullptr : ctx.h_order.p );
+        order = sparse ? nullptr : ctx.h_order.p;   // complete once the stream is synchronised below; sparse: stays in ctx.d_order
         d_pos = &ctx.d_pos_tmp;
     }
     else {
@@ -1643,11 +1671,69 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
                 (uint32_t) stride, (uint32_t) world, (uint32_t) nglob );
         ctx.stats.launches++;
         ctx.h_scores.reserve( narr + 1 );
-        CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-        CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        ctx.stats.d2h_bytes += narr * sizeof( int32_t );
-        replay_topk( ctx.h_scores.p, order, narr, req.hitcount, hits );
+        if( !sparse_replay_applies( narr, req.hitcount ) ) {
+            CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            ctx.stats.d2h_bytes += narr * sizeof( int32_t );
+            replay_topk( ctx.h_scores.p, order, narr, req.hitcount, hits );
+        }
+        else {
+            // Large databases: only the first m arrivals and the later arrivals that beat the heap's root after those m can
+            // touch the heap (replay.cpp: replay_topk_sparse) - 4 m bytes and a few hundred candidates cross PCIe instead of
+            // 4 bytes per record of the WHOLE database on every rank, and the host looks at m records instead of all.
+            const size_t m = sparse_replay_prefix( req.hitcount );
+            const uint32_t * d_order = order ? nullptr : ctx.d_order.p;   // arrival position -> provider index, where the host has no copy
+            CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, m * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            if( d_order ) CUDA_OK( cudaMemcpyAsync( ctx.h_order.p, d_order, m * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+            ctx.stats.d2h_bytes += m * sizeof( int32_t ) + ( d_order ? m * sizeof( uint32_t ) : 0 );
+            auto fetch = [&]( int32_t thr, const int32_t ** cand_scores, const uint32_t ** cand_ids ) -> size_t {
+                const size_t cap = narr - m;
+                ctx.d_cand_pos.reserve( cap + 1 );
+                ctx.d_cand_score.reserve( cap + 1 );
+                ctx.d_counter.reserve( 64 );
+                uint32_t * d_count = ctx.d_counter.p + 40;
+                CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx.stream ) );
+                compact_greater_kernel<<<(unsigned) ( ( cap + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_arrival_scores.p, (uint32_t) m, (uint32_t) narr, thr,
+                        ctx.d_cand_pos.p, ctx.d_cand_score.p, d_count );
+                ctx.stats.launches++;
+                uint32_t count = 0;
+                CUDA_OK( cudaMemcpyAsync( &count, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+                ctx.h_cand_pos.reserve( 2 * (size_t) count + 2 );   // [count] positions | [count] ids in arrival order
+                ctx.h_cand_score.reserve( 2 * (size_t) count + 2 ); // [count] scores as compacted | [count] in arrival order
+                ctx.h_cand_id.reserve( (size_t) count + 2 );
+                if( count > 0 ) {
+                    CUDA_OK( cudaMemcpyAsync( ctx.h_cand_pos.p, ctx.d_cand_pos.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                    CUDA_OK( cudaMemcpyAsync( ctx.h_cand_score.p, ctx.d_cand_score.p, count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                    if( d_order ) {
+                        ctx.d_cand_id.reserve( count + 1 );
+                        gather_u32_kernel<<<( count + 255 ) / 256, 256, 0, ctx.stream>>>( d_order, ctx.d_cand_pos.p, count, ctx.d_cand_id.p );
+                        ctx.stats.launches++;
+                        CUDA_OK( cudaMemcpyAsync( ctx.h_cand_id.p, ctx.d_cand_id.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                    }
+                }
+                CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+                ctx.stats.d2h_bytes += 4 + (size_t) count * ( d_order ? 12 : 8 );
+                // the compaction is unordered: back into arrival order
+                std::vector<uint32_t> perm( count );
+                std::iota( perm.begin(), perm.end(), 0u );
+                std::sort( perm.begin(), perm.end(), [&]( uint32_t x, uint32_t y ) { return ctx.h_cand_pos.p[x] < ctx.h_cand_pos.p[y]; } );
+                uint32_t * ids = ctx.h_cand_pos.p + count;
+                int32_t * sc = ctx.h_cand_score.p + count;
+                for( uint32_t j = 0; j < count; j++ ) {
+                    const uint32_t src = perm[j];
+                    sc[j] = ctx.h_cand_score.p[src];
+                    ids[j] = d_order ? ctx.h_cand_id.p[src] : order[ctx.h_cand_pos.p[src]];
+                }
+                *cand_scores = sc;
+                *cand_ids = ids;
+                return count;
+            };
+            replay_topk_sparse( ctx.h_scores.p, order ? order : ctx.h_order.p, m, req.hitcount, fetch, hits );
+        }
     }
     else {
         CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );

@@ -220,6 +220,22 @@ def test_work_batches_partition_the_stream(prod_host):
                 assert size[0] >= cols and size[-2] < cols                           # big batches first, small ones last
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_sparse_replay_equals_full_replay(prod_host, seed):
+    """large databases: only the first m arrivals and the later arrivals above the heap's root leave the device"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2000, 60000))
+    hi = int(rng.choice([3, 40, 100000]))                    # few distinct scores: ties everywhere, also at the cut-off
+    scores = rng.integers(0, hi, size=n).astype(np.int32)
+    if seed % 2:
+        scores = np.sort(scores)                              # worst case: every later record beats the root
+    order = rng.permutation(n).astype(np.uint32)
+    for k in (1, 7, 100):
+        full = prod_host.host_replay(scores, order, k)
+        for prefix in (k, k + 1, 500, 5000, n, n + 10):
+            assert prod_host.host_replay_sparse(scores, order, k, prefix) == full, (seed, k, prefix)
+
+
 def test_sharded_merge_two_ranks_gloo(tmp_path):
     """World-size-2 run of the shard/all-gather/replay logic on CPU (gloo): each rank scores its shard
     with the oracle standing in for the GPU kernels, the shard scores are all-gathered exactly as
