@@ -56,7 +56,16 @@ def test_live_reference_random_inputs(prod, ref, tmp_path):
         synth.write_fasta(str(path), seqs)
         scoring = ["blosum62", "blosum45", "pam30", [4, -3]][trial % 4]
         gaps = [[-11, -1], [-3, -1], [-5, -5], [0, -2]][trial % 4]
-        case = {"symtype": cases.AMINOACID, "scoring": scoring, "gaps": gaps, "db": str(path), "query_string": q,
+        symtype = cases.AMINOACID
+        if trial % 5 == 4:   # nucleotide searches (constant scoring, IUPAC codes in query and database)
+            symtype = cases.NUCLEOTIDE
+            q = synth.random_nucleotide(int(rng.integers(1, 1 << 30)), qlen, iupac_rate=0.03)
+            seqs = synth.nucleotide_db(min(n, 800), int(rng.integers(1, 1 << 30)), query=q, n_homologs=min(5, n), mu=float(rng.choice([4.0, 6.0])),
+                                       sigma=0.6, min_len=1, max_len=5000, iupac_rate=0.01)
+            synth.write_fasta(str(path), seqs)
+            scoring = [[5, -4], [2, -2], [1, -1]][trial % 3]
+            gaps = [[-4, -2], [-1, -1], [-10, -1]][(trial // 5) % 3]
+        case = {"symtype": symtype, "scoring": scoring, "gaps": gaps, "db": str(path), "query_string": q,
                 "chunk": [1000, 64][trial % 2],
                 "runs": [[m, w, 30, cases.COMPUTE_SCORE] for m in ("sw", "nw") for w in (64, 16, 8)]
                         + [["sw", 16, 6, cases.COMPUTE_ALIGNMENT], ["nw", 16, 6, cases.COMPUTE_ALIGNMENT]]}
