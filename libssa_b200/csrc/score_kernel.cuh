@@ -126,9 +126,6 @@ __device__ __forceinline__ uint4 lds128( uint32_t addr ) {
 // the other R - MR rows hold two scores per word (merged by PRMT).  The IMAD form pays where the ALU pipe throttles:
 // the shapes with 3-4 resident CTAs per SM (R <= 16: +5 % [B200]).  The 2-CTA shapes (R >= 24) are issue-bound at
 // 4 warps per scheduler and gain nothing from it (measured -1..+2 %), so they keep the smaller PRMT profile.
-#ifndef SSA_QUAD
-#define SSA_QUAD 0
-#endif
 #ifndef SSA_MR_HI
 #define SSA_MR_HI 0
 #endif
@@ -514,54 +511,6 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     S = A::max3( S, ta0, ta1 );
                     S = A::max3( S, tb0, tb1 );
                 };
-#if SSA_QUAD
-                // rows 4k .. 4k+3 of both columns: all four diagonal candidates of column A are formed from the OLD H registers first,
-                // so only one old value per quad (H of row 4k+3, the diagonal of the next quad) has to be copied aside
-                auto dp_quad = [&]( const int k, const uint32_t va0, const uint32_t va1, const uint32_t va2, const uint32_t va3,
-                                    const uint32_t vb0, const uint32_t vb1, const uint32_t vb2, const uint32_t vb3 ) {
-                    const T ta0 = A::add( hda, (T) va0 ), ta1 = A::add( Hp[4 * k], (T) va1 );
-                    const T ta2 = A::add( Hp[4 * k + 1], (T) va2 ), ta3 = A::add( Hp[4 * k + 2], (T) va3 );
-                    hda = Hp[4 * k + 3];
-                    auto row = [&]( const int r, const T ta, const uint32_t vb, T & tb_out ) {
-                        const T ha = NW ? A::max3( ta, E[r], fa ) : A::max3_relu( ta, E[r], fa );
-                        T hq = A::add( ha, QR );
-                        const T ea = A::addmax( E[r], RG, hq );
-                        fa = A::addmax( fa, RG, hq );
-                        const T tb = A::add( ha_prev, (T) vb );
-                        Hp[r] = NW ? A::max3( tb, ea, fb ) : A::max3_relu( tb, ea, fb );
-                        hq = A::add( Hp[r], QR );
-                        E[r] = A::addmax( ea, RG, hq );
-                        fb = A::addmax( fb, RG, hq );
-                        ha_prev = ha;
-                        tb_out = tb;
-                    };
-                    T tb0, tb1, tb2, tb3;
-                    row( 4 * k, ta0, vb0, tb0 );
-                    row( 4 * k + 1, ta1, vb1, tb1 );
-                    row( 4 * k + 2, ta2, vb2, tb2 );
-                    row( 4 * k + 3, ta3, vb3, tb3 );
-                    S = A::max3( S, ta0, ta1 );
-                    S = A::max3( S, ta2, ta3 );
-                    S = A::max3( S, tb0, tb1 );
-                    S = A::max3( S, tb2, tb3 );
-                };
-#pragma unroll
-                for( int q = 0; q < MR / 4; q++ ) {
-                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lba = lds128( prof_base + ( rb << 9 ) + q * 16384 );
-                    const uint4 lab = lds128( prof_base + ( sa << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
-                    dp_quad( q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w,
-                            lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
-                }
-#pragma unroll
-                for( int q = 0; q < NQ16; q++ ) {
-                    const uint2 laa = lds64( prof_base16 + ( ra << 8 ) + q * 8192 ), lba = lds64( prof_base16 + ( rb << 8 ) + q * 8192 );
-                    const uint2 lab = lds64( prof_base16 + ( sa << 8 ) + q * 8192 ), lbb = lds64( prof_base16 + ( sb << 8 ) + q * 8192 );
-                    dp_quad( MR / 4 + q, __byte_perm( lba.x, laa.x, 0x5410 ), __byte_perm( lba.x, laa.x, 0x7632 ),
-                            __byte_perm( lba.y, laa.y, 0x5410 ), __byte_perm( lba.y, laa.y, 0x7632 ),
-                            __byte_perm( lbb.x, lab.x, 0x5410 ), __byte_perm( lbb.x, lab.x, 0x7632 ),
-                            __byte_perm( lbb.y, lab.y, 0x5410 ), __byte_perm( lbb.y, lab.y, 0x7632 ) );
-                }
-#else
                 // one shared load per sequence and column fetches the scores of four query rows
 #pragma unroll
                 for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
@@ -579,7 +528,6 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     dp_pair( MR / 2 + 2 * q + 1, __byte_perm( lba.y, laa.y, 0x5410 ), __byte_perm( lba.y, laa.y, 0x7632 ),
                             __byte_perm( lbb.y, lab.y, 0x5410 ), __byte_perm( lbb.y, lab.y, 0x7632 ) );
                 }
-#endif
                 ha_last = ha_prev;
                 fa_last = fa;
                 hb_last = Hp[R - 1];
