@@ -12,3 +12,27 @@ int launch_score_packed( int R, bool nw, bool multi, const ScoreArgs & args, cud
 int packed_blocks_per_sm( int R, bool nw, bool multi );
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & args, cudaStream_t stream );
 }  // namespace ssa
+
+#include <map>
+#include <utility>
+
+namespace ssa {
+// Multiprocessors of the current device and resident CTAs per multiprocessor of `kernel` with `smem_bytes` of dynamic shared
+// memory; sets the kernel's shared-memory limit.  Cached per (device, kernel): the runtime queries cost more host time per
+// launch than everything else a search enqueues.
+template<typename K> inline std::pair<int, int> kernel_limits( K kernel, int smem_bytes ) {
+    static std::map<std::pair<int, const void *>, std::pair<int, int>> cache;
+    int dev = 0;
+    cudaGetDevice( &dev );
+    const std::pair<int, const void *> key( dev, (const void *) kernel );
+    auto it = cache.find( key );
+    if( it != cache.end() ) return it->second;
+    int sms = 0, per_sm = 0;
+    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
+    if( per_sm < 1 ) per_sm = 1;
+    return cache[key] = std::make_pair( sms, per_sm );
+}
+}  // namespace ssa
+

@@ -7,14 +7,8 @@
 namespace ssa {
 
 template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArgs & args, cudaStream_t stream ) {
-    static thread_local int cached_dev = -1;
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice( &dev );
-    (void) cached_dev;
-    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
-    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
-    if( per_sm < 1 ) per_sm = 1;
+    const std::pair<int, int> lim = kernel_limits( kernel, smem_bytes );
+    const int sms = lim.first, per_sm = lim.second;
     // persistent grid: a whole number of CTAs per SM; every warp pulls batches from the work queue
     const long groups_per_cta = ( SCORE_THREADS / 32 ) * ( 32 / args.group );
     long want = ( (long) args.nbatches + groups_per_cta - 1 ) / groups_per_cta;  // never more groups than batches
@@ -34,12 +28,7 @@ template<int R> static int pick( bool nw, bool multi, const ScoreArgs & a, cudaS
                  : launch( score_kernel<true, R, false, 0, false>, smem, a, s );
 }
 
-template<typename K> static int occupancy( K kernel, int smem_bytes ) {
-    int per_sm = 0;
-    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
-    return per_sm < 1 ? 1 : per_sm;
-}
+template<typename K> static int occupancy( K kernel, int smem_bytes ) { return kernel_limits( kernel, smem_bytes ).second; }
 
 template<int R> static int occ_pick( bool nw, bool multi ) {
     const int smem = profile_words<true, R>() * 4;

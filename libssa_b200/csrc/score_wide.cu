@@ -9,12 +9,9 @@
 namespace ssa {
 
 template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArgs & args, cudaStream_t stream ) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice( &dev );
-    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
-    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
-    if( per_sm < 1 ) per_sm = 1;
+    const std::pair<int, int> lim = kernel_limits( kernel, smem_bytes );
+    const int sms = lim.first, per_sm = lim.second;
+    // persistent grid: a whole number of CTAs per SM; every warp pulls batches from the work queue
     const long groups_per_cta = ( SCORE_THREADS / 32 ) * ( 32 / args.group );
     long want = ( (long) args.nbatches + groups_per_cta - 1 ) / groups_per_cta;
     int grid = sms * per_sm;

@@ -1516,7 +1516,6 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     const size_t chunk = g_chunk_size * (size_t) db.buffer_max;
     const bool use_gpu_arrival = chunk <= (size_t) ARRIVAL_MAX_CHUNK;
-    const bool fast_done = false;
     hits.clear();
 
     // ---- which records would the reference have pushed through its overflow cascade? (SW only) ----
@@ -1527,7 +1526,7 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     bool have_overflow = false;
     const int32_t * d_first_gathered = nullptr;
     uint32_t n_flagged = 0;
-    if( !fast_done && !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+    if( !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const int32_t thr = req.bit_width == 8 ? 255 : 65535;
         const uint32_t total = (uint32_t) ( stride * world );
         ctx.d_flag_list.reserve( total + 2 );
@@ -1591,7 +1590,7 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     // ---- NW entered at 8 or 16 bit: which records overflow the reference's saturating tiers, and where ----
     // (only for the records static bounds cannot clear: usually none at 16 bit, everything at 8 bit)
     uint32_t * d_nw_counts = nullptr;
-    if( !fast_done && nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
+    if( nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( qlen, 8 ) ) : 0;
         const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( qlen, 16 ) );
         // every rank takes the same branch: whether any shard needs the emulation follows from the GLOBAL longest record
@@ -1638,10 +1637,7 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     const uint32_t * order = nullptr;
     size_t narr = 0;
     DevBuf<int32_t> * d_pos = nullptr;
-    if( fast_done ) {
-        // nothing to replay
-    }
-    else if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
+    if( !have_overflow ) {  // a function of the database alone: cached per (bit width, chunk size)
         PackedDb::Arrival & ar = arrival_for( req.bit_width, chunk, use_gpu_arrival );
         order = ar.order.data();
         narr = ar.order.size();
@@ -1661,10 +1657,7 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
         narr = ctx.order_tmp.size();
         d_pos = &ctx.d_pos_tmp;
     }
-    if( fast_done ) {
-        // nothing to replay
-    }
-    else if( narr > 0 && nglob > 0 ) {
+    if( narr > 0 && nglob > 0 ) {
         ctx.d_arrival_scores.reserve( narr + 1 );
         const uint32_t total = (uint32_t) ( stride * world );
         scatter_arrival_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, d_pos->p, ctx.d_arrival_scores.p,
