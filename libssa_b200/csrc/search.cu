@@ -1485,7 +1485,11 @@ static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw ) {
 static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits );
 
 // sparse heap replay (replay_topk_sparse): the first m arrivals are replayed in full
-static size_t sparse_replay_prefix( size_t hitcount ) { return std::max<size_t>( 65536, 64 * hitcount ); }
+static size_t sparse_replay_prefix( size_t hitcount ) {
+    size_t floor = 65536;
+    if( const char * e = getenv( "LIBSSA_B200_REPLAY_PREFIX" ) ) floor = std::max<size_t>( 1, (size_t) atol( e ) );   // tests: small databases too
+    return std::max<size_t>( floor, 64 * hitcount );
+}
 static bool sparse_replay_applies( size_t narr, size_t hitcount ) {
     return narr > 4 * sparse_replay_prefix( hitcount ) && !getenv( "LIBSSA_B200_FULL_REPLAY" );
 }
@@ -1679,6 +1683,7 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
             const uint32_t * d_order = order ? nullptr : ctx.d_order.p;   // arrival position -> provider index, where the host has no copy
             CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, m * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
             if( d_order ) CUDA_OK( cudaMemcpyAsync( ctx.h_order.p, d_order, m * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );   // (recorded again behind the candidate fetch)
             CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
             ctx.stats.d2h_bytes += m * sizeof( int32_t ) + ( d_order ? m * sizeof( uint32_t ) : 0 );
             auto fetch = [&]( int32_t thr, const int32_t ** cand_scores, const uint32_t ** cand_ids ) -> size_t {

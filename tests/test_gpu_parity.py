@@ -221,6 +221,23 @@ def test_full_size_properties(prod, port, big_db, tmp_path):
     order = prod.host_arrival_order(lens, 1000, 64)
     assert lists[64] == prod.host_replay(sw[order], order, 100)
     assert prod.stats().overflow_8 == int((sw >= 255).sum())          # counted during the bw = 8 search above
+    # (4b) ties AT the cut-off force the arrival-order replay; its sparse form (first m arrivals + later records above the
+    # heap's root, what databases beyond 262 144 records use) must return the same lists as the full form
+    desc = np.sort(sw)[::-1]
+    k_tie = next(k for k in range(60, 5000) if desc[k - 1] == desc[k])
+    for k in (k_tie, 1, 0):
+        full = {bw: [(h.score, h.db_id) for h in prod.sw_align(q, k, bw, cases.COMPUTE_SCORE)] for bw in (64, 16, 8)}
+        assert full[64] == prod.host_replay(sw[order], order, k)
+        d2h_full = prod.stats().d2h_bytes
+        os.environ["LIBSSA_B200_REPLAY_PREFIX"] = "300"
+        try:
+            sparse = {bw: [(h.score, h.db_id) for h in prod.sw_align(q, k, bw, cases.COMPUTE_SCORE)] for bw in (64, 16, 8)}
+            d2h_sparse = prod.stats().d2h_bytes
+        finally:
+            del os.environ["LIBSSA_B200_REPLAY_PREFIX"]
+        assert sparse == full, k
+        if k == k_tie:
+            assert d2h_sparse < d2h_full / 4, (d2h_sparse, d2h_full)      # the sparse replay really ran
     # (5) permutation invariance: the same records in another provider order get the same scores
     perm = rng.permutation(len(seqs))
     from libssa_b200 import synth
