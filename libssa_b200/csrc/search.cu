@@ -532,16 +532,6 @@ __global__ void iota_kernel( uint32_t * p, uint32_t first, uint32_t n ) {
     if( i < n ) p[i] = first + i;
 }
 
-// records scoring >= thr8 / >= thr16 over the gathered score vector (the reference's overflow counters)
-__global__ void count_ge_kernel( const int32_t * gathered, uint32_t stride, uint32_t world, uint32_t nglobal, int32_t thr8, int32_t thr16, uint32_t * out ) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if( i >= stride * world ) return;
-    uint32_t r = i / stride, sl = i % stride;
-    if( (uint64_t) sl * world + r >= nglobal ) return;
-    if( gathered[i] >= thr8 ) atomicAdd( out, 1u );
-    if( gathered[i] >= thr16 ) atomicAdd( out + 1, 1u );
-}
-
 // counts the entries that are not INT_MAX (records that overflow a tier)
 __global__ void count_set_kernel( const int32_t * p, uint32_t n, uint32_t * out ) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1405,7 +1395,10 @@ static void enqueue_topk( const int32_t * d_all, PackedDb::Arrival & base, size_
     const size_t nglob = db.sorted_all.size();
     const size_t world = (size_t) ctx.world;
     const size_t stride = ( nglob + world - 1 ) / world;
-    ctx.d_select.reserve( 1 );
+    if( ctx.d_select.cap == 0 ) {   // the passes keep the state's histogram, ticket and accumulators zero from here on
+        ctx.d_select.reserve( 1 );
+        CUDA_OK( cudaMemsetAsync( ctx.d_select.p, 0, sizeof( SelectState ), ctx.stream ) );
+    }
     ctx.h_select[slot].reserve( 1 );
     SelectArgs sa;
     sa.scores = d_all;
@@ -1416,35 +1409,23 @@ static void enqueue_topk( const int32_t * d_all, PackedDb::Arrival & base, size_
     sa.state = ctx.d_select.p;
     const uint32_t total = (uint32_t) ( stride * world );
     const unsigned grid = std::min<unsigned>( ( total + 255 ) / 256, 148 * 8 );
-    select_init_kernel<<<1, 256, 0, ctx.stream>>>( ctx.d_select.p, (uint32_t) k );
     const int shifts[3] = { 21, 10, 0 };
     const uint32_t masks[3] = { 0x7ff, 0x7ff, 0x3ff };
-    for( int p = 0; p < 3; p++ ) {
-        select_hist_kernel<<<grid, 256, 0, ctx.stream>>>( sa, shifts[p], masks[p] );
-        select_pick_kernel<<<1, 1024, 0, ctx.stream>>>( ctx.d_select.p, shifts[p], masks[p], p == 2 );
-    }
+    for( int p = 0; p < 3; p++ ) select_pass_kernel<<<grid, 256, 0, ctx.stream>>>( sa, p, shifts[p], masks[p], (uint32_t) k, p == 2 );
     ctx.d_topk_scores.reserve( k + 1 );
     ctx.d_topk_ids.reserve( k + 1 );
     select_compact_kernel<<<grid, 256, 0, ctx.stream>>>( sa, db.d_sorted_all.p, ctx.d_topk_scores.p, ctx.d_topk_ids.p, (uint32_t) k );
-    ctx.stats.launches += 8;
+    ctx.stats.launches += 4;
     ctx.h_topk_scores[slot].reserve( k + 1 );
     ctx.h_topk_ids[slot].reserve( k + 1 );
     ctx.h_counts[slot].reserve( 2 );
-    ctx.h_counts[slot].p[0] = ctx.h_counts[slot].p[1] = 0;
-    if( count_overflow ) {  // the reference's overflow counters (informational, manager.c:157-160)
-        ctx.d_counter.reserve( 64 );
-        uint32_t * d_c = ctx.d_counter.p + 40;
-        CUDA_OK( cudaMemsetAsync( d_c, 0, 8, ctx.stream ) );
-        count_ge_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world, (uint32_t) nglob, 255, 65535, d_c );
-        ctx.stats.launches++;
-        CUDA_OK( cudaMemcpyAsync( ctx.h_counts[slot].p, d_c, 8, cudaMemcpyDeviceToHost, ctx.stream ) );
-    }
-    CUDA_OK( cudaMemcpyAsync( ctx.h_select[slot].p, ctx.d_select.p, 32, cudaMemcpyDeviceToHost, ctx.stream ) );
+    ctx.h_counts[slot].p[0] = count_overflow ? 1 : 0;   // whether the reference's overflow counters apply (manager.c:157-160)
+    CUDA_OK( cudaMemcpyAsync( ctx.h_select[slot].p, ctx.d_select.p, SELECT_HEADER_BYTES, cudaMemcpyDeviceToHost, ctx.stream ) );
     CUDA_OK( cudaMemcpyAsync( ctx.h_topk_scores[slot].p, ctx.d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
     CUDA_OK( cudaMemcpyAsync( ctx.h_topk_ids[slot].p, ctx.d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
     CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
     CUDA_OK( cudaEventRecord( ctx.ev_topk[slot], ctx.stream ) );
-    ctx.stats.d2h_bytes += 40 + k * 8;
+    ctx.stats.d2h_bytes += SELECT_HEADER_BYTES + k * 8;
 }
 
 // waits for the slot's results; true (and the sorted hit list) if the set does not depend on the arrival order
@@ -1460,8 +1441,9 @@ static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & 
         if( x.score != y.score ) return x.score > y.score;
         return x.db_id > y.db_id;
     } );
-    if( bit_width == 8 ) ctx.stats.overflow_8 = ctx.h_counts[slot].p[0];
-    if( bit_width == 8 || bit_width == 16 ) ctx.stats.overflow_16 = ctx.h_counts[slot].p[1];
+    const bool counted = ctx.h_counts[slot].p[0] != 0;
+    if( bit_width == 8 ) ctx.stats.overflow_8 = counted ? st.ge8 : 0;
+    if( bit_width == 8 || bit_width == 16 ) ctx.stats.overflow_16 = counted ? st.ge16 : 0;
     return true;
 }
 
