@@ -292,6 +292,10 @@ def run_ours(steps, warmup, n_gpus):
             "roofline": {
                 "bound": "int_alu", "kernel": "ssa::score_kernel<PACKED,...> (SW, s16x2)", "achieved": round(achieved, 1),
                 "peak": round(peak, 1), "unit": "GCUPS", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_note": "ncu dram bytes per launch of the dominant kernel = one 32 x 32-row pass of the 5147-aa query over the whole "
+                                "database (profiles/prof_r01_top.md): 0.16 GB of column stream, the rest are the pass-boundary rows it reads "
+                                "from the previous pass and writes for the next one (8 B per column each way; a single-pass launch moves "
+                                "0.17 GB) - about 48 GB/s, HBM is not the bound",
                 "peak_formula": "SMs x f_clk x L x c / I = %d x %.0f MHz x %d lane-ops/clk/SM x %d cells/word / %.1f ALU-pipe ops/word"
                                 % (SM_COUNT, sm_mhz, LANE_OPS_PER_CLK_PER_SM, CELLS_PER_WORD, ALU_OPS_PER_WORD),
                 "peak_source": "L measured on this pool (profiles/pipes_r01.md); f_clk = median SM clock sampled during the timed region",
