@@ -65,6 +65,31 @@ def kernel_report(rep, title, cells_per_launch, note):
     open(os.path.join(P, rep.replace(".ncu-rep", ".md")), "w").write("\n".join(out) + "\n")
     return res
 
+def stall_breakdown(rep):
+    """appends the warp-state samples by reason and by opcode (ncu --page source) of the first captured launch to the summary"""
+    raw = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, data = rows[1], []
+    for r in rows[2:]:
+        if r and r[0] == "Kernel Name": break
+        if len(r) < 10 or r[0] == "Address": continue
+        data.append(r)
+    ia, ie = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
+    sc = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    tot, exe = sum(int(r[ia]) for r in data), sum(int(r[ie]) for r in data)
+    reasons = sorted(((sum(int(r[i] or 0) for r in data), hdr[i]) for i in sc), reverse=True)
+    agg = collections.defaultdict(lambda: [0, 0])
+    for r in data:
+        t = r[1].split(); op = t[1] if t[0].startswith("@") else t[0]
+        agg[op][0] += int(r[ia]); agg[op][1] += int(r[ie])
+    out = ["", "## warp-state samples by reason and by opcode (first launch above; `ncu --page source`, %d samples, %d SASS instructions, "
+           "%.2f G warp instructions executed)" % (tot, len(data), exe / 1e9), "", "| reason | share |", "|---|---|"]
+    out += ["| %s | %.1f %% |" % (n, 100.0 * v / tot) for v, n in reasons if v * 1000 >= tot]
+    out += ["", "| opcode | share of samples | share of executed instructions |", "|---|---|---|"]
+    out += ["| `%s` | %.1f %% | %.1f %% |" % (op, 100.0 * sv / tot, 100.0 * ev / exe) for op, (sv, ev) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]]
+    open(os.path.join(P, rep.replace(".ncu-rep", ".md")), "a").write("\n".join(out) + "\n")
+
+
 if __name__ == "__main__":
     share = launches()
     meta = json.load(open(os.path.join(G, "bench_%s.json" % tag)))
@@ -74,6 +99,7 @@ if __name__ == "__main__":
                         res_per_gpu * 1024.0,
                         "`ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:score_kernel<.bool.1, .int.32, .bool.0, .int.1' -s 5 -c 2 "
                         "python tools/profile_target.py P33450 sw 500000` (same 500 000-record database shape as bench.py; the capture follows a plain run of the same command that exited 0).")
+    stall_breakdown("prof_%s_top.ncu-rep" % tag)
     json.dump({"kernel": top[-1]["kernel"], "dram_bytes_per_launch": top[-1]["dram_bytes"], "seconds_under_ncu": top[-1]["seconds"],
                "algorithmic_cells_per_launch": res_per_gpu * 1024.0, "algorithmic_bytes_per_launch": res_per_gpu * 1.0 + 4.0 * meta["config"]["db_records"] / meta["n_gpus"],
                "score_kernel_share_of_step": share, "source": "profiles/prof_%s_top.md" % tag}, open(os.path.join(P, "roofline_%s.json" % tag), "w"), indent=1)
