@@ -36,34 +36,57 @@ __attribute__( ( weak, visibility( "default" ) ) ) int ssa_db_init( const char *
         print_error( "Cannot open database file: %s", db_name );
         return -1;
     }
-    std::vector<char> buf( 1 << 20 );
+    // Line by line over 4 MB blocks (a partial last line is carried into the next block): a line that starts with '>' opens a
+    // record, every other line of a record is appended without its line break, carriage returns, blanks and tabs.
+    std::vector<char> buf( 4u << 20 );
     std::vector<size_t> lens;
-    bool in_header = false, in_record = false, line_start = true;
-    size_t got;
-    while( ( got = fread( buf.data(), 1, buf.size(), fp ) ) > 0 ) {
-        for( size_t i = 0; i < got; i++ ) {
-            char c = buf[i];
-            if( in_header ) {
-                if( c == '\n' ) {
-                    in_header = false;
-                    line_start = true;
-                }
-                continue;
+    if( fseek( fp, 0, SEEK_END ) == 0 ) {   // the residues cannot outgrow the file: one allocation instead of repeated growth
+        const long bytes = ftell( fp );
+        if( bytes > 0 ) store.text.reserve( (size_t) bytes + 1 );
+        rewind( fp );
+    }
+    bool in_record = false;
+    size_t have = 0;   // bytes in buf: [0, have)
+    auto take_line = [&]( const char * p, size_t n ) {
+        if( n > 0 && p[0] == '>' ) {
+            if( in_record ) {
+                lens.push_back( store.text.size() - store.offset.back() );
+                store.text.push_back( 0 );
             }
-            if( line_start && c == '>' ) {
-                if( in_record ) {
-                    lens.push_back( store.text.size() - store.offset.back() );
-                    store.text.push_back( 0 );
-                }
-                store.offset.push_back( store.text.size() );
-                in_record = true;
-                in_header = true;
-                continue;
-            }
-            line_start = ( c == '\n' );
-            if( !in_record || c == '\n' || c == '\r' || c == ' ' || c == '\t' ) continue;
-            store.text.push_back( c );
+            store.offset.push_back( store.text.size() );
+            in_record = true;
+            return;
         }
+        if( !in_record || n == 0 ) return;
+        const size_t at = store.text.size();
+        store.text.resize( at + n );
+        char * out = store.text.data() + at;
+        size_t m = 0;
+        for( size_t i = 0; i < n; i++ ) {
+            const char c = p[i];
+            out[m] = c;
+            m += ( c != '\r' && c != ' ' && c != '\t' );
+        }
+        store.text.resize( at + m );
+    };
+    while( true ) {
+        if( have == buf.size() ) buf.resize( 2 * buf.size() );   // a line longer than the block
+        const size_t got = fread( buf.data() + have, 1, buf.size() - have, fp );
+        have += got;
+        const bool eof = got == 0;
+        size_t pos = 0;
+        while( pos < have ) {
+            const char * nl = (const char *) memchr( buf.data() + pos, '\n', have - pos );
+            if( !nl ) break;
+            take_line( buf.data() + pos, (size_t) ( nl - ( buf.data() + pos ) ) );
+            pos = (size_t) ( nl - buf.data() ) + 1;
+        }
+        if( eof ) {
+            if( pos < have ) take_line( buf.data() + pos, have - pos );   // last line without a line break
+            break;
+        }
+        memmove( buf.data(), buf.data() + pos, have - pos );
+        have -= pos;
     }
     fclose( fp );
     if( in_record ) {
