@@ -126,6 +126,8 @@ __device__ __forceinline__ uint4 lds128( uint32_t addr ) {
 // the other R - MR rows hold two scores per word (merged by PRMT).  The IMAD form pays where the ALU pipe throttles:
 // the shapes with 3-4 resident CTAs per SM (R <= 16: +5 % [B200]).  The 2-CTA shapes (R >= 24) are issue-bound at
 // 4 warps per scheduler and gain nothing from it (measured -1..+2 %), so they keep the smaller PRMT profile.
+// (SSA_MR_FULL / SSA_MR_HI: build-time knobs of that measurement - `make EXTRA=-DSSA_MR_FULL=24 OUT=... OBJDIR=...` builds a
+// variant library that LIBSSA_B200_LIB selects at run time; profiles/prof_r01_shapes.md.)
 #ifndef SSA_MR_HI
 #define SSA_MR_HI 0
 #endif
