@@ -2,7 +2,7 @@
 // reference citations).  One warp per chunk of the provider order; the lanes play the SIMD channels of the
 // reference scheduler (32 for the 8-bit tier, 16 for the 16-bit tier): every iteration the channel with the
 // smallest (finish block, channel index) key emits its record and is refilled with the chunk's next record -
-// found with one warp-wide REDUX.  Records that overflow a tier are collected in emission order and run through
+// found with warp-wide REDUX reductions over a 64-bit key.  Records that overflow a tier are collected in emission order and run through
 // the next tier, exactly like search_8_chunk / search_16_chunk (reference src/algo/8/search_8.c:94-124,
 // src/algo/16/search_16.c:92-114).  The overflow positions come straight from the tracking kernel's output, so
 // nothing but the final order has to cross PCIe.
@@ -78,14 +78,21 @@ __global__ void __launch_bounds__( 32 ) arrival_kernel( const ArrivalArgs a ) {
             blk_a[i] = b;
         }
         __syncwarp();
-        // channel state: key = finish block * 64 + channel (unique per lane), UINT_MAX = idle
-        uint32_t rec = lane, key = 0xffffffffu;
-        if( lane < channels && (uint32_t) lane < m ) key = ( blk_a[lane] << 6 ) | (uint32_t) lane;
+        // channel state: the block after which the channel's record finishes (64 bit: a chunk of 2048 records of up to 2^22
+        // blocks each can accumulate more than 2^32 blocks in one channel); the reference's scan finds the channel with
+        // the smallest (finish block, channel index) first (replay.cpp: simd_emission uses the same 64-bit key)
+        uint32_t rec = lane;
+        uint64_t fin = 0;
+        bool active = lane < channels && (uint32_t) lane < m;
+        if( active ) fin = blk_a[lane];
         uint32_t next = min( (uint32_t) channels, m ), nb = 0;
         for( uint32_t e = 0; e < m; e++ ) {
-            const uint32_t kmin = __reduce_min_sync( FULL, key );
+            const uint32_t hi = (uint32_t) ( fin >> 32 ), lo = (uint32_t) fin;
+            const uint32_t hmin = __reduce_min_sync( FULL, active ? hi : 0xffffffffu );
+            const uint32_t lmin = __reduce_min_sync( FULL, ( active && hi == hmin ) ? lo : 0xffffffffu );
+            const unsigned tied = __ballot_sync( FULL, active && hi == hmin && lo == lmin );
             bool to_b = false;
-            if( key == kmin ) {  // exactly one lane: the channel the reference's scan finds finished first
+            if( lane == __ffs( tied ) - 1 ) {  // exactly one lane: the channel the reference's scan finds finished first
                 const uint32_t id = list_a[rec];
                 to_b = overflow_block( id, tier ) >= 0;
                 if( to_b )
@@ -94,10 +101,10 @@ __global__ void __launch_bounds__( 32 ) arrival_kernel( const ArrivalArgs a ) {
                     emit_final( id, out );
                 if( next < m ) {
                     rec = next;
-                    key = ( ( ( kmin >> 6 ) + blk_a[next] ) << 6 ) | (uint32_t) lane;
+                    fin += blk_a[next];
                 }
                 else {
-                    key = 0xffffffffu;
+                    active = false;
                 }
             }
             if( __ballot_sync( FULL, to_b ) )

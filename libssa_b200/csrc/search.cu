@@ -219,6 +219,7 @@ void build_db() {
     const bool general = bm > 1 || translate_db;  // entries are materialised as code strings first
     db.buffer_max = bm;
 
+    for( auto & kv : db.arrival ) kv.second.d_pos_of_sorted.release();
     db.arrival.clear();
     db.lens_all.clear();
     std::vector<const char *> text;
@@ -1333,6 +1334,12 @@ void gpu_release() {
     ctx.h_scores.release();
     ctx.h_first.release();
     ctx.h_pos.release();
+    ctx.d_cand_pos.release();
+    ctx.d_cand_id.release();
+    ctx.d_cand_score.release();
+    ctx.h_cand_pos.release();
+    ctx.h_cand_id.release();
+    ctx.h_cand_score.release();
     traceback_release();
     cudaEventDestroy( ctx.ev_begin );
     cudaEventDestroy( ctx.ev_k0 );

@@ -580,9 +580,20 @@ void traceback_hits( cudaStream_t stream, const uint8_t * query, size_t qlen, bo
     CUDA_OK( cudaStreamSynchronize( stream ) );
     stats->d2h_bytes += download_bytes;
 
+    bool matrix_symmetric = true;
+    for( int x = 0; x < SCORE_MATRIX_DIM && matrix_symmetric; x++ )
+        for( int y = 0; y < x; y++ )
+            if( g_matrix.m[( x << 5 ) + y] != g_matrix.m[( y << 5 ) + x] ) {
+                matrix_symmetric = false;
+                break;
+            }
     for( int k = 0; k < n; k++ ) {
         const int32_t * r = (const int32_t *) stage + 8 * k;
-        if( scored_sequence && !nw && r[0] != (int32_t) hits[k].hit.score )
+        // The search scores with M[(db << 5) + query], the region passes read M[query][db] like the reference's align.c:
+        // with an asymmetric user matrix the two scores legitimately differ, and the reference returns the alignment of
+        // its own forward score (align.c:39-131).  The cross-check is therefore an internal assertion for symmetric
+        // matrices only.
+        if( scored_sequence && !nw && matrix_symmetric && r[0] != (int32_t) hits[k].hit.score )
             fatal( "libssa_b200: internal error: alignment score %d differs from search score %ld for sequence %ld", r[0],
                     (long) hits[k].hit.score, (long) hits[k].hit.db_id );
         if( !r[5] ) fatal( "Internal error in align function." );  // align.c:131

@@ -371,3 +371,39 @@ def test_batched_queries_multi_frame_fallback(prod, tmp_path):
         for q in qs:
             prod.free_sequence(q)
         prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+
+
+def test_asymmetric_matrix_alignment_matches_reference(prod, ref, tmp_path):
+    """A user matrix read from a string need not be symmetric.  The search scores with M[db][query], the region passes of the
+    alignment read M[query][db] (reference src/algo/align.c:39-131), so the alignment's own forward score differs from the
+    search score - the reference returns the alignment of ITS forward score, and so must the library (it used to abort)."""
+    from libssa_b200 import synth
+    rng = np.random.default_rng(77)
+    letters = "ARNDCQEGHILKMFPSTWYV"
+    vals = rng.integers(-4, 3, size=(20, 20))
+    for i in range(20):
+        vals[i, i] = int(rng.integers(4, 9))
+    assert (vals != vals.T).any()
+    text = "   " + "  ".join(letters) + "\n" + "".join(
+        "%s %s\n" % (letters[i], " ".join("%2d" % v for v in vals[i])) for i in range(20))
+    q = synth.random_protein(rng, 180)
+    seqs = synth.protein_db(400, 78, query=q, homolog_frac=0.05, n_dup=4, mu=5.0, sigma=0.5, min_len=5, max_len=900)
+    path = tmp_path / "asym.fas"
+    synth.write_fasta(str(path), seqs)
+    results = []
+    for lib in (ref, prod):
+        lib.set_output_mode(0)
+        lib.set_thread_count(1)
+        lib.set_chunk_size(1000)
+        lib.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+        lib.init_score_matrix(cases.READ_FROM_STRING, text)
+        lib.init_gap_penalties(-7, -1)
+        lib.init_db(str(path))
+        qh = lib.init_sequence_fasta(cases.READ_FROM_STRING, q)
+        out = []
+        for mode, bw in (("sw", 16), ("sw", 8), ("nw", 16), ("sw", 64)):
+            hits = (lib.sw_align if mode == "sw" else lib.nw_align)(qh, 8, bw, cases.COMPUTE_ALIGNMENT)
+            out.append([(h.score, h.db_id, h.cigar, h.q_start, h.q_end, h.d_start, h.d_end) for h in hits])
+        lib.free_sequence(qh)
+        results.append(out)
+    assert results[0] == results[1]
