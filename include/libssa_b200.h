@@ -24,7 +24,7 @@ extern "C" {
 typedef struct {
     uint64_t n_seqs;          /* non-empty database records (all shards) */
     uint64_t n_residues;      /* their total length */
-    uint64_t local_seqs;      /* records held by this process' shard */
+    uint64_t local_seqs;      /* records held by this process (its shard; all its GPUs' shards in single-process mode) */
     uint64_t local_residues;
     uint64_t cells;           /* query length x local_residues: real DP cells of the last search */
     uint64_t overflow_8;      /* records the reference would have re-aligned at 16 bit (manager.c:157-160) */
@@ -45,17 +45,29 @@ typedef struct {
 void ssa_b200_set_device( int device );
 
 /*
- * Shard the database over `world_size` processes (one per GPU): the records are sorted by length
- * and dealt round-robin, so every shard holds the same residue count to within one record
- * (SURVEY.md 8e).  Each process scores its shard only.
+ * ONE process, SEVERAL GPUs - the drop-in for a plain C host (the counterpart of the reference's thread fan-out inside
+ * the library, reference src/algo/manager.c:120-146): the database is sharded by residue count over devices 0 .. n-1, one
+ * host thread per device enqueues its shard's kernels, the shard scores are merged with ncclAllGather over NVLink/NVSwitch
+ * (ncclCommInitAll inside the library, libnccl.so.2 loaded on demand), hit selection and traceback run on device 0.
+ * Without this call the environment variable LIBSSA_B200_GPUS (a number or "all") decides; default 1 - so an unchanged
+ * libssa.h program uses 8 GPUs with `LIBSSA_B200_GPUS=8 ./program`.  Call before the first search.
  */
-void ssa_b200_set_shard( int rank, int world_size );
+void ssa_b200_set_device_count( int n );
+int ssa_b200_get_device_count( void );
 
 /*
- * Collective used to merge shard results: all-gather `bytes` bytes from every rank's DEVICE buffer
- * `d_send` into `d_recv` (world_size * bytes, rank order), ordered on CUDA stream `stream`.
- * The host language supplies it (torch.distributed/NCCL in bench.py and the tests; ncclAllGather in C).
+ * ONE process PER GPU (torchrun / MPI): shard the database over `world_size` processes.  The records are sorted by length
+ * and dealt round-robin, so every shard holds the same residue count to within one record.  Each process
+ * scores its shard only; the shard scores are merged by a collective, either
+ *   (a) inside the library: rank 0 calls ssa_b200_nccl_unique_id, the host program carries the 128 bytes to the other
+ *       ranks over any channel it has, every rank calls ssa_b200_nccl_init( id, rank, world_size ) (which implies
+ *       ssa_b200_set_shard) - the library then issues ncclAllGather on its own CUDA stream; or
+ *   (b) supplied by the host: ssa_b200_set_shard + ssa_b200_set_allgather( fn ) with fn all-gathering `bytes` bytes from
+ *       every rank's DEVICE buffer `d_send` into `d_recv` (world_size * bytes, rank order), ordered on CUDA stream `stream`.
  */
+void ssa_b200_set_shard( int rank, int world_size );
+void ssa_b200_nccl_unique_id( void * out_128_bytes );
+void ssa_b200_nccl_init( const void * id_128_bytes, int rank, int world_size );
 typedef void (*ssa_b200_allgather_fn)( void * ctx, const void * d_send, void * d_recv, size_t bytes, void * stream );
 void ssa_b200_set_allgather( ssa_b200_allgather_fn fn, void * ctx );
 
@@ -66,7 +78,7 @@ void ssa_b200_get_stats( ssa_b200_stats_t * out );
 
 /*
  * Exact score of every local database record against the query, without hit selection:
- * writes `local_seqs` entries, index = position in this shard's record list; ids[] receives the
+ * writes `local_seqs` entries in provider order (the records this process holds); ids[] receives the
  * provider IDs.  Either pointer may be NULL.  nw = 0 Smith-Waterman, 1 Needleman-Wunsch.
  * Returns local_seqs.
  */

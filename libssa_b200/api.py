@@ -178,6 +178,31 @@ class LibSSA:
     # ---- libssa_b200.h ----
     def set_device(self, device): self.lib.ssa_b200_set_device(device)
     def set_shard(self, rank, world_size): self.lib.ssa_b200_set_shard(rank, world_size)
+
+    def set_device_count(self, n):
+        """One process, n GPUs: shards over devices 0..n-1, merged with NCCL inside the library."""
+        self.lib.ssa_b200_set_device_count.argtypes = [C.c_int]
+        self.lib.ssa_b200_set_device_count.restype = None
+        self.lib.ssa_b200_set_device_count(n)
+
+    def device_count(self):
+        self.lib.ssa_b200_get_device_count.restype = C.c_int
+        return self.lib.ssa_b200_get_device_count()
+
+    def nccl_unique_id(self):
+        """128 bytes identifying a new NCCL communicator (rank 0 creates it, the host carries it to the other ranks)."""
+        buf = C.create_string_buffer(128)
+        self.lib.ssa_b200_nccl_unique_id.argtypes = [C.c_void_p]
+        self.lib.ssa_b200_nccl_unique_id.restype = None
+        self.lib.ssa_b200_nccl_unique_id(buf)
+        return buf.raw
+
+    def nccl_init(self, unique_id, rank, world_size):
+        """Joins the communicator: from now on the library all-gathers shard scores itself (ncclAllGather on its stream)."""
+        assert len(unique_id) == 128
+        self.lib.ssa_b200_nccl_init.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        self.lib.ssa_b200_nccl_init.restype = None
+        self.lib.ssa_b200_nccl_init(unique_id, rank, world_size)
     def prepare_db(self): self.lib.ssa_b200_prepare_db()
 
     def stats(self):

@@ -13,26 +13,34 @@ int packed_blocks_per_sm( int R, bool nw, bool multi );
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & args, cudaStream_t stream );
 }  // namespace ssa
 
+#include <cstdio>
+#include <cstdlib>
 #include <map>
+#include <mutex>
 #include <utility>
 
 namespace ssa {
 // Multiprocessors of the current device and resident CTAs per multiprocessor of `kernel` with `smem_bytes` of dynamic shared
 // memory; sets the kernel's shared-memory limit.  Cached per (device, kernel): the runtime queries cost more host time per
-// launch than everything else a search enqueues.
+// launch than everything else a search enqueues.  Called from one host thread per GPU, hence the lock.
 template<typename K> inline std::pair<int, int> kernel_limits( K kernel, int smem_bytes ) {
     static std::map<std::pair<int, const void *>, std::pair<int, int>> cache;
+    static std::mutex lock;
     int dev = 0;
     cudaGetDevice( &dev );
     const std::pair<int, const void *> key( dev, (const void *) kernel );
+    std::lock_guard<std::mutex> guard( lock );
     auto it = cache.find( key );
     if( it != cache.end() ) return it->second;
     int sms = 0, per_sm = 0;
-    cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
-    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
+    cudaError_t e = cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes );
+    if( e == cudaSuccess ) e = cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+    if( e == cudaSuccess ) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, kernel, SCORE_THREADS, smem_bytes );
+    if( e != cudaSuccess ) {
+        fprintf( stderr, "libssa_b200: cannot configure a scoring kernel (%d bytes of shared memory): %s\n", smem_bytes, cudaGetErrorString( e ) );
+        exit( 1 );
+    }
     if( per_sm < 1 ) per_sm = 1;
     return cache[key] = std::make_pair( sms, per_sm );
 }
 }  // namespace ssa
-

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <functional>
 #include <climits>
 #include <cstdio>
@@ -18,8 +19,13 @@
 #include <cstring>
 #include <array>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <thread>
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace ssa;
 
@@ -120,12 +126,12 @@ struct PackedDb {
     std::map<std::pair<int, size_t>, Arrival> arrival;
 };
 
+// One context per GPU this process drives.  Multi-process mode (torchrun): one context, rank / world from ssa_b200_set_shard or
+// ssa_b200_nccl_init.  Single-process mode (LIBSSA_B200_GPUS / ssa_b200_set_device_count): one context per device, rank = index.
 struct Ctx {
-    bool init = false;
     int device = -1;
     int rank = 0, world = 1;
-    ssa_b200_allgather_fn allgather = nullptr;
-    void * allgather_ctx = nullptr;
+    ncclComm_t comm = nullptr;          // in-library collective (NCCL over NVLink / NVSwitch), nullptr = none
     cudaStream_t stream = nullptr, stream_aux = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     PackedDb db;
@@ -161,36 +167,208 @@ struct Ctx {
     DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
     ssa_b200_stats_t stats;
+    bool scored = false;                  // score_shard launched kernels in the current call (ev_k0 / ev_k1 are valid)
 };
 
-Ctx ctx;
+// ---- process-wide configuration (set before the first search creates the contexts) ----
+struct Config {
+    int device = -1;                      // ssa_b200_set_device: the (primary) device, -1 = $LOCAL_RANK or 0
+    int rank = 0, world = 1;              // ssa_b200_set_shard / ssa_b200_nccl_init: this process' shard
+    int ndev = 0;                         // ssa_b200_set_device_count: devices of this process, 0 = $LIBSSA_B200_GPUS or 1
+    ssa_b200_allgather_fn allgather = nullptr;   // host-supplied collective (alternative to the in-library NCCL)
+    void * allgather_ctx = nullptr;
+} g_cfg;
 
-void ensure_ctx() {
-    if( ctx.init ) return;
-    int dev = ctx.device;
-    if( dev < 0 ) {
-        const char * lr = getenv( "LOCAL_RANK" );
-        dev = lr ? atoi( lr ) : 0;
-        int count = 0;
-        cudaError_t e = cudaGetDeviceCount( &count );
-        if( e != cudaSuccess || count == 0 )
-            fatal( "libssa_b200: no CUDA device available (%s). This library has no CPU fallback.",
-                    e != cudaSuccess ? cudaGetErrorString( e ) : "device count is 0" );
-        dev %= count;
+std::vector<Ctx *> g_devs;                // contexts of this process, [0] = primary (hit selection, traceback, host results)
+thread_local Ctx * t_ctx = nullptr;       // the context the calling thread works on
+int g_stage_slot = 0;                     // which of the two pinned staging buffer sets the call in flight uses (gpu_search_batch)
+
+inline Ctx & ctx() { return *( t_ctx ? t_ctx : g_devs[0] ); }
+inline bool is_primary() { return &ctx() == g_devs[0]; }
+
+// RAII: work on another context (and its device) from the calling thread
+struct Activate {
+    Ctx * prev;
+    explicit Activate( Ctx * c ) : prev( t_ctx ) {
+        t_ctx = c;
+        CUDA_OK( cudaSetDevice( c->device ) );
     }
-    CUDA_OK( cudaSetDevice( dev ) );
-    ctx.device = dev;
-    CUDA_OK( cudaStreamCreateWithFlags( &ctx.stream, cudaStreamNonBlocking ) );
-    CUDA_OK( cudaStreamCreateWithFlags( &ctx.stream_aux, cudaStreamNonBlocking ) );
-    CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_fork, cudaEventDisableTiming ) );
-    CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_join, cudaEventDisableTiming ) );
-    CUDA_OK( cudaEventCreate( &ctx.ev_begin ) );
-    CUDA_OK( cudaEventCreate( &ctx.ev_k0 ) );
-    CUDA_OK( cudaEventCreate( &ctx.ev_k1 ) );
-    CUDA_OK( cudaEventCreate( &ctx.ev_end ) );
-    for( int i = 0; i < 2; i++ ) CUDA_OK( cudaEventCreateWithFlags( &ctx.ev_topk[i], cudaEventDisableTiming ) );
-    memset( &ctx.stats, 0, sizeof( ctx.stats ) );
-    ctx.init = true;
+    ~Activate() {
+        t_ctx = prev;
+        if( prev ) cudaSetDevice( prev->device );
+    }
+};
+
+// ---- NCCL, loaded on demand: a single-GPU process never needs it ----
+struct NcclApi {
+    void * handle = nullptr;
+    ncclResult_t ( *GetUniqueId )( ncclUniqueId * ) = nullptr;
+    ncclResult_t ( *CommInitRank )( ncclComm_t *, int, ncclUniqueId, int ) = nullptr;
+    ncclResult_t ( *CommInitAll )( ncclComm_t *, int, const int * ) = nullptr;
+    ncclResult_t ( *CommDestroy )( ncclComm_t ) = nullptr;
+    ncclResult_t ( *AllGather )( const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t ) = nullptr;
+    const char * ( *GetErrorString )( ncclResult_t ) = nullptr;
+} g_nccl;
+
+#define NCCL_OK( call )                                                                                        \
+    do {                                                                                                       \
+        ncclResult_t r_ = ( call );                                                                            \
+        if( r_ != ncclSuccess ) fatal( "NCCL error %s at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString( r_ ) ); \
+    } while( 0 )
+
+void load_nccl() {
+    if( g_nccl.handle ) return;
+    const char * names[] = { getenv( "LIBSSA_B200_NCCL" ), "libnccl.so.2", "libnccl.so" };
+    for( const char * n : names ) {
+        if( !n || !*n ) continue;
+        g_nccl.handle = dlopen( n, RTLD_NOW | RTLD_GLOBAL );
+        if( g_nccl.handle ) break;
+    }
+    if( !g_nccl.handle ) fatal( "libssa_b200: several GPUs need NCCL, but libnccl.so.2 could not be loaded: %s", dlerror() );
+    auto sym = [&]( const char * name ) {
+        void * p = dlsym( g_nccl.handle, name );
+        if( !p ) fatal( "libssa_b200: %s not found in the NCCL library", name );
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype( g_nccl.GetUniqueId )) sym( "ncclGetUniqueId" );
+    g_nccl.CommInitRank = (decltype( g_nccl.CommInitRank )) sym( "ncclCommInitRank" );
+    g_nccl.CommInitAll = (decltype( g_nccl.CommInitAll )) sym( "ncclCommInitAll" );
+    g_nccl.CommDestroy = (decltype( g_nccl.CommDestroy )) sym( "ncclCommDestroy" );
+    g_nccl.AllGather = (decltype( g_nccl.AllGather )) sym( "ncclAllGather" );
+    g_nccl.GetErrorString = (decltype( g_nccl.GetErrorString )) sym( "ncclGetErrorString" );
+}
+
+// ---- one host thread per additional device (the counterpart of the reference's pthread pool, src/util/thread_pool.c:50-86:
+// there one thread per CPU core, here one per GPU; the calling thread drives the primary device itself) ----
+struct Workers {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    const std::function<void()> * job = nullptr;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+};
+// never destroyed: a host program may exit without ssa_exit() while the device threads wait for work, and a joinable
+// std::thread must not meet its destructor
+Workers & g_workers = *new Workers;
+
+void worker_main( int index ) {
+    t_ctx = g_devs[index];
+    CUDA_OK( cudaSetDevice( t_ctx->device ) );
+    uint64_t seen = 0;
+    for( ;; ) {
+        const std::function<void()> * job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk( g_workers.m );
+            g_workers.cv_go.wait( lk, [&] { return g_workers.stop || g_workers.generation != seen; } );
+            if( g_workers.stop ) return;
+            seen = g_workers.generation;
+            job = g_workers.job;
+        }
+        ( *job )();
+        {
+            std::lock_guard<std::mutex> lk( g_workers.m );
+            if( --g_workers.pending == 0 ) g_workers.cv_done.notify_one();
+        }
+    }
+}
+
+// runs fn once per context of this process, each on its own host thread with ctx() bound to that context; returns when
+// every one has ENQUEUED its work (the GPUs keep running)
+void run_on_all( const std::function<void()> & fn ) {
+    if( g_devs.size() == 1 ) {
+        fn();
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk( g_workers.m );
+        g_workers.job = &fn;
+        g_workers.pending = (int) g_devs.size() - 1;
+        g_workers.generation++;
+    }
+    g_workers.cv_go.notify_all();
+    fn();
+    std::unique_lock<std::mutex> lk( g_workers.m );
+    g_workers.cv_done.wait( lk, [&] { return g_workers.pending == 0; } );
+}
+
+void init_ctx( Ctx * c, int device, int rank, int world ) {
+    c->device = device;
+    c->rank = rank;
+    c->world = world;
+    CUDA_OK( cudaSetDevice( device ) );
+    CUDA_OK( cudaStreamCreateWithFlags( &c->stream, cudaStreamNonBlocking ) );
+    CUDA_OK( cudaStreamCreateWithFlags( &c->stream_aux, cudaStreamNonBlocking ) );
+    CUDA_OK( cudaEventCreateWithFlags( &c->ev_fork, cudaEventDisableTiming ) );
+    CUDA_OK( cudaEventCreateWithFlags( &c->ev_join, cudaEventDisableTiming ) );
+    CUDA_OK( cudaEventCreate( &c->ev_begin ) );
+    CUDA_OK( cudaEventCreate( &c->ev_k0 ) );
+    CUDA_OK( cudaEventCreate( &c->ev_k1 ) );
+    CUDA_OK( cudaEventCreate( &c->ev_end ) );
+    for( int i = 0; i < 2; i++ ) CUDA_OK( cudaEventCreateWithFlags( &c->ev_topk[i], cudaEventDisableTiming ) );
+    memset( &c->stats, 0, sizeof( c->stats ) );
+}
+
+// Creates the contexts at the first use; afterwards binds the calling thread to the primary context and its device.
+void ensure_ctx() {
+    if( !g_devs.empty() ) {
+        if( !t_ctx ) {
+            t_ctx = g_devs[0];
+            CUDA_OK( cudaSetDevice( t_ctx->device ) );
+        }
+        return;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount( &count );
+    if( e != cudaSuccess || count == 0 )
+        fatal( "libssa_b200: no CUDA device available (%s). This library has no CPU fallback.",
+                e != cudaSuccess ? cudaGetErrorString( e ) : "device count is 0" );
+    int ndev = g_cfg.ndev;
+    if( ndev <= 0 ) {
+        ndev = 1;
+        if( const char * env = getenv( "LIBSSA_B200_GPUS" ) ) ndev = strcmp( env, "all" ) == 0 ? count : atoi( env );
+        if( ndev < 1 ) ndev = 1;
+    }
+    if( ndev > count ) fatal( "libssa_b200: %d GPUs requested, %d visible.", ndev, count );
+    if( ndev > 1 && g_cfg.world > 1 )
+        fatal( "libssa_b200: several GPUs per process (LIBSSA_B200_GPUS / ssa_b200_set_device_count) cannot be combined with "
+               "several processes (ssa_b200_set_shard / ssa_b200_nccl_init): use one or the other." );
+    if( ndev == 1 ) {
+        int dev = g_cfg.device;
+        if( dev < 0 ) {
+            const char * lr = getenv( "LOCAL_RANK" );
+            dev = ( lr ? atoi( lr ) : 0 ) % count;
+        }
+        Ctx * c = new Ctx;
+        init_ctx( c, dev, g_cfg.rank, g_cfg.world );
+        g_devs.push_back( c );
+    }
+    else {
+        // single process, several GPUs: the database is sharded over devices 0 .. ndev-1, one host thread per device, the
+        // shard scores are all-gathered with NCCL (ncclCommInitAll) exactly as between processes
+        std::vector<int> devlist( ndev );
+        for( int i = 0; i < ndev; i++ ) {
+            devlist[i] = i;
+            Ctx * c = new Ctx;
+            init_ctx( c, i, i, ndev );
+            g_devs.push_back( c );
+        }
+        load_nccl();
+        std::vector<ncclComm_t> comms( ndev );
+        NCCL_OK( g_nccl.CommInitAll( comms.data(), ndev, devlist.data() ) );
+        for( int i = 0; i < ndev; i++ ) g_devs[i]->comm = comms[i];
+        g_workers.stop = false;
+        for( int i = 1; i < ndev; i++ ) g_workers.threads.emplace_back( worker_main, i );
+    }
+    t_ctx = g_devs[0];
+    CUDA_OK( cudaSetDevice( t_ctx->device ) );
+}
+
+uint64_t process_residues() {
+    uint64_t n = 0;
+    for( Ctx * c : g_devs ) n += c->db.local_residues;
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -199,58 +377,92 @@ void ensure_ctx() {
 
 void parallel_for( size_t n, size_t grain, const std::function<void( size_t, size_t )> & fn );
 
-void build_db() {
-    ensure_ctx();
-    PackedDb & db = ctx.db;
+// Provider-wide part of the database build, shared by the shards of all contexts of this process: the provider walk, the
+// entries (strands / reading frames) as code strings, and the global length-sorted order that defines the shards.
+struct GlobalDb {
+    int symtype = -1, strands_key = -1, gencode_key = -1;
+    int buffer_max = 1;
+    bool general = false;                  // entries are materialised as code strings (several entries per record / translation)
+    const signed char * map = nullptr;
+    std::vector<const char *> text;        // provider-owned record texts
+    std::vector<uint64_t> rec_len;
+    std::vector<uint64_t> lens_all;        // entry lengths, provider order (0 = skipped)
+    std::vector<uint8_t> entry_codes;
+    std::vector<uint64_t> entry_off;
+    std::vector<uint32_t> sorted;          // provider index by global sorted position
+    std::vector<int32_t> sorted_pos_of_id;
+    uint64_t n_seqs = 0, n_residues = 0;
+    size_t unknown_mapped = 0;
+    double ms = 0;
+    void release() {
+        std::vector<const char *>().swap( text );
+        std::vector<uint64_t>().swap( rec_len );
+        std::vector<uint64_t>().swap( lens_all );
+        std::vector<uint8_t>().swap( entry_codes );
+        std::vector<uint64_t>().swap( entry_off );
+        std::vector<uint32_t>().swap( sorted );
+        std::vector<int32_t>().swap( sorted_pos_of_id );
+    }
+} g_gdb;
+
+bool shard_is_current( const Ctx & c ) {
     const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
     const int gencode_key = translate_db ? g_db_gencode : 0;
     const int strands_key = ( g_symtype == NUCLEOTIDE || translate_db ) ? g_query_strands : 0;
-    if( db.valid && db.epoch == g_db_epoch && db.symtype == g_symtype && db.rank == ctx.rank && db.world == ctx.world &&
-            db.strands == strands_key && db.db_gencode == gencode_key )
-        return;
+    const PackedDb & db = c.db;
+    return db.valid && db.epoch == g_db_epoch && db.symtype == g_symtype && db.rank == c.rank && db.world == c.world &&
+           db.strands == strands_key && db.db_gencode == gencode_key;
+}
 
+void build_global() {
+    GlobalDb & g = g_gdb;
     const double t0 = wall_ms();
-    const signed char * map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
+    const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
+    g.symtype = g_symtype;
+    g.gencode_key = translate_db ? g_db_gencode : 0;
+    g.strands_key = ( g_symtype == NUCLEOTIDE || translate_db ) ? g_query_strands : 0;
+    g.map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
+    const signed char * map = g.map;
     int bm = 1;  // reference adp_init, src/db_adapter.c:118-139
     if( g_symtype == NUCLEOTIDE )
         bm = ( g_query_strands & COMPLEMENTARY_STRAND ) ? 2 : 1;
     else if( translate_db )
         bm = ( g_query_strands ^ BOTH_STRANDS ) ? 3 : 6;
-    const bool general = bm > 1 || translate_db;  // entries are materialised as code strings first
-    db.buffer_max = bm;
+    g.general = bm > 1 || translate_db;
+    g.buffer_max = bm;
 
-    for( auto & kv : db.arrival ) kv.second.d_pos_of_sorted.release();
-    db.arrival.clear();
-    db.lens_all.clear();
-    std::vector<const char *> text;
-    std::vector<uint64_t> rec_len;
+    g.text.clear();
+    g.rec_len.clear();
+    g.lens_all.clear();
+    g.entry_codes.clear();
+    g.entry_off.clear();
+    g.unknown_mapped = 0;
+    std::vector<const char *> & text = g.text;
+    std::vector<uint64_t> & rec_len = g.rec_len;
     for( size_t i = 0;; i++ ) {  // the reference walks ids until the provider returns NULL (db_adapter.c:224-229)
         p_seqinfo rec = ssa_db_get_sequence( i );
         if( !rec ) break;
         rec_len.push_back( rec->seqlen );
         text.push_back( rec->seq );
     }
-    std::vector<uint8_t> entry_codes;
-    std::vector<uint64_t> entry_off;
-    size_t unknown_mapped = 0;
-    if( !general ) {
-        db.lens_all = rec_len;
+    if( !g.general ) {
+        g.lens_all = rec_len;
     }
     else {
         // entries of record r: nucleotide = forward, reverse complement; translated = frames 0-2 of one strand or of
         // both (db_adapter.c:46-107).  Entries that come out empty are skipped like empty records.
         const size_t nrec = rec_len.size();
         if( nrec * (size_t) bm > 0xfffffff0ull ) fatal( "libssa_b200: more than 2^32 database entries are not supported." );
-        db.lens_all.assign( nrec * bm, 0 );
-        entry_off.assign( nrec * bm + 1, 0 );
+        g.lens_all.assign( nrec * bm, 0 );
+        g.entry_off.assign( nrec * bm + 1, 0 );
         for( size_t r = 0; r < nrec; r++ )
             for( int b = 0; b < bm; b++ ) {
                 uint64_t len = rec_len[r];
                 if( translate_db ) len = len >= (uint64_t) ( b % 3 ) ? ( len - ( b % 3 ) ) / 3 : 0;
-                db.lens_all[r * bm + b] = len;
-                entry_off[r * bm + b + 1] = entry_off[r * bm + b] + len;
+                g.lens_all[r * bm + b] = len;
+                g.entry_off[r * bm + b + 1] = g.entry_off[r * bm + b] + len;
             }
-        entry_codes.resize( entry_off.back() + 1 );
+        g.entry_codes.resize( g.entry_off.back() + 1 );
         std::vector<size_t> unknown_per( ( nrec + 255 ) / 256 + 1, 0 );
         parallel_for( nrec, 256, [&]( size_t r0, size_t r1 ) {
             std::vector<uint8_t> nt, tmp;
@@ -260,7 +472,7 @@ void build_db() {
                 nt.resize( rec_len[r] + 1 );
                 unknown += map_db_sequence( text[r], rec_len[r], nt.data(), map );
                 for( int b = 0; b < bm; b++ ) {
-                    uint8_t * dst = entry_codes.data() + entry_off[r * bm + b];
+                    uint8_t * dst = g.entry_codes.data() + g.entry_off[r * bm + b];
                     if( !translate_db ) {
                         if( b == 0 )
                             memcpy( dst, nt.data(), rec_len[r] );
@@ -270,39 +482,61 @@ void build_db() {
                     else {
                         const int strand = ( bm == 6 ) ? b / 3 : g_query_strands - 1;
                         translate_codes( true, nt.data(), rec_len[r], strand, b % 3, tmp );
-                        if( tmp.size() != db.lens_all[r * bm + b] ) fatal( "libssa_b200: internal error: translated length." );
+                        if( tmp.size() != g.lens_all[r * bm + b] ) fatal( "libssa_b200: internal error: translated length." );
                         if( !tmp.empty() ) memcpy( dst, tmp.data(), tmp.size() );
                     }
                 }
             }
             unknown_per[r0 / 256] = unknown;
         } );
-        unknown_mapped = std::accumulate( unknown_per.begin(), unknown_per.end(), (size_t) 0 );
+        g.unknown_mapped = std::accumulate( unknown_per.begin(), unknown_per.end(), (size_t) 0 );
     }
-    const size_t nall = db.lens_all.size();
+    const size_t nall = g.lens_all.size();
     if( nall > 0xfffffff0ull ) fatal( "libssa_b200: more than 2^32 database records are not supported." );
 
-    std::vector<uint32_t> sorted;
+    std::vector<uint32_t> & sorted = g.sorted;
+    sorted.clear();
     sorted.reserve( nall );
-    db.n_residues = 0;
+    g.n_residues = 0;
     for( size_t i = 0; i < nall; i++ )
-        if( db.lens_all[i] > 0 ) {
+        if( g.lens_all[i] > 0 ) {
             sorted.push_back( (uint32_t) i );
-            db.n_residues += db.lens_all[i];
-            if( db.lens_all[i] > 0x7fffffffull ) fatal( "libssa_b200: database record %ld is too long.", (long) i );
+            g.n_residues += g.lens_all[i];
+            if( g.lens_all[i] > 0x7fffffffull ) fatal( "libssa_b200: database record %ld is too long.", (long) i );
         }
-    db.n_seqs = sorted.size();
-    std::stable_sort( sorted.begin(), sorted.end(),
-            [&]( uint32_t a, uint32_t b ) { return db.lens_all[a] > db.lens_all[b]; } );
+    g.n_seqs = sorted.size();
+    std::stable_sort( sorted.begin(), sorted.end(), [&]( uint32_t a, uint32_t b ) { return g.lens_all[a] > g.lens_all[b]; } );
+    g.sorted_pos_of_id.assign( nall, -1 );
+    for( size_t i = 0; i < sorted.size(); i++ ) g.sorted_pos_of_id[sorted[i]] = (int32_t) i;
+    g.ms = wall_ms() - t0;
+}
+
+// Packs and uploads the shard of the calling thread's context from g_gdb.  Returns the number of unknown symbols it mapped to 0.
+size_t build_shard() {
+    PackedDb & db = ctx().db;
+    const GlobalDb & g = g_gdb;
+    const double t0 = wall_ms();
+    const signed char * map = g.map;
+    const bool general = g.general;
+    db.buffer_max = g.buffer_max;
+    for( auto & kv : db.arrival ) kv.second.d_pos_of_sorted.release();
+    db.arrival.clear();
+    db.lens_all = g.lens_all;
+    db.n_residues = g.n_residues;
+    db.n_seqs = g.n_seqs;
+    const size_t nall = db.lens_all.size();
+    const std::vector<uint32_t> & sorted = g.sorted;
+    const std::vector<const char *> & text = g.text;
+    const std::vector<uint8_t> & entry_codes = g.entry_codes;
+    const std::vector<uint64_t> & entry_off = g.entry_off;
 
     // shard: deal the length-sorted records round-robin
     db.sorted_all = sorted;
-    db.sorted_pos_of_id.assign( nall, -1 );
-    for( size_t g = 0; g < sorted.size(); g++ ) db.sorted_pos_of_id[sorted[g]] = (int32_t) g;
+    db.sorted_pos_of_id = g.sorted_pos_of_id;
     db.sorted_id.clear();
     db.sorted_len.clear();
     db.local_residues = 0;
-    for( size_t s = (size_t) ctx.rank; s < sorted.size(); s += (size_t) ctx.world ) {
+    for( size_t s = (size_t) ctx().rank; s < sorted.size(); s += (size_t) ctx().world ) {
         db.sorted_id.push_back( sorted[s] );
         db.sorted_len.push_back( (uint32_t) db.lens_all[sorted[s]] );
         db.local_residues += db.lens_all[sorted[s]];
@@ -355,8 +589,7 @@ void build_db() {
         }
         unknown_per_chunk[p0 / 1024] = unknown;
     } );
-    size_t unknown = unknown_mapped + std::accumulate( unknown_per_chunk.begin(), unknown_per_chunk.end(), (size_t) 0 );
-    if( unknown > 0 ) print_warning( "%ld unknown symbols found and set to zero", (long) unknown );
+    const size_t unknown = std::accumulate( unknown_per_chunk.begin(), unknown_per_chunk.end(), (size_t) 0 );
     for( size_t i = db.total_cols; i < db.total_cols + 64; i++ ) h_stream.p[i] = 0;
 
     for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
@@ -366,7 +599,7 @@ void build_db() {
     const double t1 = wall_ms();
     db.d_stream.reserve( db.total_cols + 64 );
     CUDA_OK( cudaMemcpyAsync( db.d_stream.p, h_stream.p, ( db.total_cols + 64 ) * sizeof( uint16_t ), cudaMemcpyHostToDevice,
-            ctx.stream ) );
+            ctx().stream ) );
     {
         std::vector<uint32_t> lens32( nall );
         for( size_t i = 0; i < nall; i++ ) lens32[i] = (uint32_t) db.lens_all[i];
@@ -385,26 +618,60 @@ void build_db() {
         for( auto & kv : db.chunk_info ) kv.second.d_chunk_base.release();
         db.chunk_info.clear();
     }
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     h_stream.release();
     db.upload_ms = wall_ms() - t1;
 
     db.epoch = g_db_epoch;
-    db.symtype = g_symtype;
-    db.strands = strands_key;
-    db.db_gencode = gencode_key;
-    db.rank = ctx.rank;
-    db.world = ctx.world;
+    db.symtype = g.symtype;
+    db.strands = g.strands_key;
+    db.db_gencode = g.gencode_key;
+    db.rank = ctx().rank;
+    db.world = ctx().world;
     db.valid = true;
-    ctx.stats.n_seqs = db.n_seqs;
-    ctx.stats.n_residues = db.n_residues;
-    ctx.stats.local_seqs = nloc;
-    ctx.stats.local_residues = db.local_residues;
-    ctx.stats.pack_ms = db.pack_ms;
-    ctx.stats.upload_ms = db.upload_ms;
-    ctx.stats.db_device_bytes = ( db.total_cols + 64 ) * sizeof( uint16_t );
-    print_info( "GPU database: %ld sequences, %ld residues, %ld columns in %ld pairs, packed in %.1f ms, uploaded in %.1f ms\n",
-            (long) nloc, (long) db.local_residues, (long) db.total_cols, (long) db.npairs, db.pack_ms, db.upload_ms );
+    ctx().stats.n_seqs = db.n_seqs;
+    ctx().stats.n_residues = db.n_residues;
+    ctx().stats.local_seqs = nloc;
+    ctx().stats.local_residues = db.local_residues;
+    ctx().stats.pack_ms = db.pack_ms;
+    ctx().stats.upload_ms = db.upload_ms;
+    ctx().stats.db_device_bytes = ( db.total_cols + 64 ) * sizeof( uint16_t );
+    print_info( "GPU %d database: %ld sequences, %ld residues, %ld columns in %ld pairs, packed in %.1f ms, uploaded in %.1f ms\n",
+            ctx().device, (long) nloc, (long) db.local_residues, (long) db.total_cols, (long) db.npairs, db.pack_ms, db.upload_ms );
+    return unknown;
+}
+
+// Builds (once per init_db / init_symbol_translation / shard change) the device-resident shard of every context.
+void build_db() {
+    ensure_ctx();
+    bool current = true;
+    for( Ctx * c : g_devs ) current = current && shard_is_current( *c );
+    if( current ) return;
+    const double t0 = wall_ms();
+    build_global();
+    std::atomic<size_t> unknown( g_gdb.unknown_mapped );
+    run_on_all( [&]() { unknown += build_shard(); } );   // the provider is no longer touched: shards pack side by side
+    if( unknown > 0 ) print_warning( "%ld unknown symbols found and set to zero", (long) unknown.load() );
+    g_gdb.release();
+    // the primary's record describes the whole process: shard sizes summed, wall clock of the whole build
+    ssa_b200_stats_t & st = g_devs[0]->stats;
+    if( g_devs.size() > 1 ) {
+        st.local_seqs = 0;
+        st.local_residues = 0;
+        st.db_device_bytes = 0;
+        double upload = 0;
+        for( Ctx * c : g_devs ) {
+            st.local_seqs += c->db.sorted_id.size();
+            st.local_residues += c->db.local_residues;
+            st.db_device_bytes += ( c->db.total_cols + 64 ) * sizeof( uint16_t );
+            upload = std::max( upload, c->db.upload_ms );
+        }
+        st.upload_ms = upload;
+        st.pack_ms = wall_ms() - t0 - upload;
+    }
+    else {
+        st.pack_ms += g_gdb.ms;
+    }
 }
 
 void parallel_for( size_t n, size_t grain, const std::function<void( size_t, size_t )> & fn ) {
@@ -453,7 +720,7 @@ std::vector<uint32_t> partition_batches( const uint64_t * pair_col, size_t npair
 // finish within a small batch of each other instead of a full one - with ~8 batches per group the idle tail of a launch
 // drops from ~6 % to < 1 % of its duration, for a few more wavefront fills.  groups = 0: uniform batches.
 PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0, uint32_t groups = 0, uint32_t min_cols = 512 ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     if( getenv( "LIBSSA_B200_NO_TAPER" ) ) groups = 0;
     const std::array<uint32_t, 4> key = { cols, first_pair, groups, min_cols };
     auto it = db.batch_tables.find( key );
@@ -473,8 +740,8 @@ PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0, uint
     }
     bt.d_batches.reserve( bt.batches.size() + 1 );
     if( !bt.batches.empty() )
-        CUDA_OK( cudaMemcpyAsync( bt.d_batches.p, bt.batches.data(), bt.batches.size() * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream ) );
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        CUDA_OK( cudaMemcpyAsync( bt.d_batches.p, bt.batches.data(), bt.batches.size() * sizeof( Batch ), cudaMemcpyHostToDevice, ctx().stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     return bt;
 }
 
@@ -697,13 +964,13 @@ int32_t nw_offset_for( const Plan & pl, int qrows, int64_t dmax ) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// scoring of the whole shard: scores by sorted position in ctx.d_scores
+// scoring of the whole shard: scores by sorted position in ctx().d_scores
 // ------------------------------------------------------------------------------------------------
 
 void launch_fill( int32_t * p, int32_t v, size_t n ) {
     if( n == 0 ) return;
-    fill_i32_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx.stream>>>( p, v, (uint32_t) n );
-    ctx.stats.launches++;
+    fill_i32_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx().stream>>>( p, v, (uint32_t) n );
+    ctx().stats.launches++;
 }
 
 // runs the wide tier over `items` (slots = sorted positions); optional first-crossing tracking
@@ -711,10 +978,10 @@ void launch_fill( int32_t * p, int32_t v, size_t n ) {
 // one search never overwrites pinned memory an earlier asynchronous copy has not consumed yet
 void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t qlen, const Plan & pl, bool nw, bool track,
         int32_t * d_first8, int32_t * d_first16, int slot, cudaStream_t stream ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     if( slots.empty() ) return;
     const size_t n = slots.size();
-    ctx.h_wide_batches[ctx.ss][slot].reserve( n );
+    ctx().h_wide_batches[g_stage_slot][slot].reserve( n );
     uint64_t bnd = 0;
     for( size_t i = 0; i < n; i++ ) {
         Batch b;
@@ -726,29 +993,29 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         b.out0 = s;
         b.half = s & 1;
         bnd += b.ncols;
-        ctx.h_wide_batches[ctx.ss][slot].p[i] = b;
+        ctx().h_wide_batches[g_stage_slot][slot].p[i] = b;
     }
-    ctx.d_wide_batches[slot].reserve( n );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_wide_batches[slot].p, ctx.h_wide_batches[ctx.ss][slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
-    ctx.stats.h2d_bytes += n * sizeof( Batch );
+    ctx().d_wide_batches[slot].reserve( n );
+    CUDA_OK( cudaMemcpyAsync( ctx().d_wide_batches[slot].p, ctx().h_wide_batches[g_stage_slot][slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
+    ctx().stats.h2d_bytes += n * sizeof( Batch );
     const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
-    ctx.h_profile_wide[ctx.ss][slot].reserve( words * npass );
-    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx.h_profile_wide[ctx.ss][slot].p + p * words, q, qlen, pl, p );
-    ctx.d_profile_wide[slot].reserve( words * npass );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_profile_wide[slot].p, ctx.h_profile_wide[ctx.ss][slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
-    ctx.stats.h2d_bytes += words * npass * 4;
-    if( npass > 1 ) ctx.d_bnd_wide.reserve( 4 * bnd + 256 );
-    ctx.d_counter.reserve( 64 );
+    ctx().h_profile_wide[g_stage_slot][slot].reserve( words * npass );
+    for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx().h_profile_wide[g_stage_slot][slot].p + p * words, q, qlen, pl, p );
+    ctx().d_profile_wide[slot].reserve( words * npass );
+    CUDA_OK( cudaMemcpyAsync( ctx().d_profile_wide[slot].p, ctx().h_profile_wide[g_stage_slot][slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
+    ctx().stats.h2d_bytes += words * npass * 4;
+    if( npass > 1 ) ctx().d_bnd_wide.reserve( 4 * bnd + 256 );
+    ctx().d_counter.reserve( 64 );
     for( int p = 0; p < npass; p++ ) {
-        CUDA_OK( cudaMemsetAsync( ( ctx.d_counter.p + 16 + 8 * slot ), 0, 4, stream ) );
+        CUDA_OK( cudaMemsetAsync( ( ctx().d_counter.p + 16 + 8 * slot ), 0, 4, stream ) );
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
         a.stream = db.d_stream.p;
-        a.batches = ctx.d_wide_batches[slot].p;
+        a.batches = ctx().d_wide_batches[slot].p;
         a.nbatches = (uint32_t) n;
-        a.counter = ( ctx.d_counter.p + 16 + 8 * slot );
-        a.profile = ctx.d_profile_wide[slot].p + p * words;
+        a.counter = ( ctx().d_counter.p + 16 + 8 * slot );
+        a.profile = ctx().d_profile_wide[slot].p + p * words;
         a.group = (uint32_t) G;
         a.k65536 = 65536u;
         a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
@@ -765,13 +1032,13 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
             a.cap_row = (int) ( ( qlen - 1 - a.rowbase ) % R );
         }
         a.first_pass = ( p == 0 );
-        a.out = ctx.d_scores.p;
+        a.out = ctx().d_scores.p;
         a.first8 = d_first8;
         a.first16 = d_first16;
         a.thr8 = 255;
         a.thr16 = 65535;
         if( npass > 1 ) {
-            uint32_t * base = ctx.d_bnd_wide.p;
+            uint32_t * base = ctx().d_bnd_wide.p;
             uint32_t * h0 = base, * f0 = base + bnd, * h1 = base + 2 * bnd, * f1 = base + 3 * bnd;
             a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
             a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
@@ -779,9 +1046,9 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
         launch_score_wide( R, nw, npass > 1, track, a, stream );
-        ctx.stats.launches++;
+        ctx().stats.launches++;
     }
-    ctx.stats.wide_tier_seqs += n;
+    ctx().stats.wide_tier_seqs += n;
 }
 
 // One pass of the packed tier: G lanes x R rows from query row `rowbase` on, over its own list of work batches (the boundary
@@ -796,7 +1063,7 @@ struct PassLaunch {
 // The packed tier over one class of pairs: all passes of the query, one launch each.
 void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, const std::vector<PassLaunch> & passes,
         uint32_t * d_counter, DevBuf<uint32_t> & d_profile_buf, PinBuf<uint32_t> & h_profile_buf, int32_t offset ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const int npass = (int) passes.size();
     const bool multi = npass > 1 || getenv( "LIBSSA_B200_FORCE_MULTI" ) != nullptr;
     size_t words_total = 0;
@@ -810,7 +1077,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         w0 += packed_profile_words( ps.R );
     }
     CUDA_OK( cudaMemcpyAsync( d_profile, h_profile, words_total * 4, cudaMemcpyHostToDevice, stream ) );
-    ctx.stats.h2d_bytes += words_total * 4;
+    ctx().stats.h2d_bytes += words_total * 4;
     w0 = 0;
     for( int p = 0; p < npass; p++ ) {
         const PassLaunch & ps = passes[p];
@@ -838,10 +1105,10 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
             a.cap_row = (int) ( ( qlen - 1 - ps.rowbase ) % ps.R );
         }
         a.first_pass = ( p == 0 );
-        a.out = ctx.d_out_packed.p;
+        a.out = ctx().d_out_packed.p;
         a.guard = nullptr;
         if( npass > 1 ) {
-            uint32_t * base = ctx.d_bnd.p;
+            uint32_t * base = ctx().d_bnd.p;
             const uint64_t n = db.total_cols;
             uint32_t * h0 = base, * f0 = base + n, * h1 = base + 2 * n, * f1 = base + 3 * n;
             a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
@@ -850,7 +1117,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
             a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
         }
         launch_score_packed( ps.R, nw, multi, a, stream );
-        ctx.stats.launches++;
+        ctx().stats.launches++;
     }
 }
 
@@ -909,7 +1176,7 @@ std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_unifo
 
 // first pair (pairs are sorted by descending length of their longer sequence) whose length is <= len
 size_t first_pair_not_longer( int64_t len ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     size_t lo = 0, hi = db.npairs;
     while( lo < hi ) {
         size_t mid = ( lo + hi ) / 2;
@@ -922,16 +1189,16 @@ size_t first_pair_not_longer( int64_t len ) {
 }
 
 void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t nloc = db.sorted_id.size();
-    ctx.d_scores.reserve( ( db.sorted_all.size() + ctx.world - 1 ) / ctx.world + 2 );
+    ctx().d_scores.reserve( ( db.sorted_all.size() + ctx().world - 1 ) / ctx().world + 2 );
     if( nloc == 0 ) return;
     if( qlen == 0 ) fatal( "libssa_b200: empty query." );
     if( qlen > ( 1u << 24 ) || ( qlen + db.sorted_len[0] ) > ( 1ull << 24 ) )
         fatal( "libssa_b200: query/database sequences beyond 2^24 symbols are not supported by the 32-bit tier." );
     Plan pl = make_plan( qlen );
     int sms = 148;
-    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx.device );
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx().device );
     if( db.batch_tables.size() >= 24 ) {  // bound the cache: a table's first pair depends on the query and the score matrix
         CUDA_OK( cudaDeviceSynchronize() );
         for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
@@ -995,23 +1262,24 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     const size_t wide_pairs = long_pair0;                                        // wide tier = pairs [0, long_pair0)
     if( nw && wide_pairs < db.npairs ) offset = nw_offset_for( pl, qrows_max, db.sorted_len[2 * wide_pairs] );
 
-    CUDA_OK( cudaEventRecord( ctx.ev_k0, ctx.stream ) );
-    ctx.d_out_packed.reserve( db.npairs + 1 );
-    ctx.d_counter.reserve( 64 );
+    CUDA_OK( cudaEventRecord( ctx().ev_k0, ctx().stream ) );
+    ctx().scored = true;
+    ctx().d_out_packed.reserve( db.npairs + 1 );
+    ctx().d_counter.reserve( 64 );
     // ---- auxiliary stream: the few sequences of the wide tier and the long class overlap the bulk launch ----
     const size_t n_long = bulk_pair0 - long_pair0;
     const bool use_aux = n_long > 0 || wide_pairs > 0;
     if( use_aux ) {
-        CUDA_OK( cudaEventRecord( ctx.ev_fork, ctx.stream ) );
-        CUDA_OK( cudaStreamWaitEvent( ctx.stream_aux, ctx.ev_fork, 0 ) );
+        CUDA_OK( cudaEventRecord( ctx().ev_fork, ctx().stream ) );
+        CUDA_OK( cudaStreamWaitEvent( ctx().stream_aux, ctx().ev_fork, 0 ) );
     }
     if( wide_pairs > 0 ) {  // pairs beyond the packed tier's guaranteed range: exact int32 tier
         std::vector<uint32_t> slots;
         for( size_t s = 0; s < std::min( nloc, 2 * wide_pairs ); s++ ) slots.push_back( (uint32_t) s );
-        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0, ctx.stream_aux );
+        run_wide( slots, q, qlen, pl, nw, false, nullptr, nullptr, 0, ctx().stream_aux );
     }
     if( n_long > 0 ) {
-        ctx.h_long_batches[ctx.ss].reserve( n_long );
+        ctx().h_long_batches[g_stage_slot].reserve( n_long );
         for( size_t i = 0; i < n_long; i++ ) {
             Batch b;
             memset( &b, 0, sizeof( b ) );
@@ -1020,25 +1288,25 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             b.bnd0 = db.pair_col[p];
             b.ncols = (uint32_t) ( db.pair_col[p + 1] - db.pair_col[p] );
             b.out0 = (uint32_t) p;
-            ctx.h_long_batches[ctx.ss].p[i] = b;
+            ctx().h_long_batches[g_stage_slot].p[i] = b;
         }
-        ctx.d_long_batches.reserve( n_long );
-        CUDA_OK( cudaMemcpyAsync( ctx.d_long_batches.p, ctx.h_long_batches[ctx.ss].p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx.stream_aux ) );
-        ctx.stats.h2d_bytes += n_long * sizeof( Batch );
+        ctx().d_long_batches.reserve( n_long );
+        CUDA_OK( cudaMemcpyAsync( ctx().d_long_batches.p, ctx().h_long_batches[g_stage_slot].p, n_long * sizeof( Batch ), cudaMemcpyHostToDevice, ctx().stream_aux ) );
+        ctx().stats.h2d_bytes += n_long * sizeof( Batch );
         PassLaunch lp;
         lp.G = 32;
         lp.R = long_R;
-        lp.d_batches = ctx.d_long_batches.p;
+        lp.d_batches = ctx().d_long_batches.p;
         lp.nbatches = (uint32_t) n_long;
-        launch_packed_class( ctx.stream_aux, q, qlen, nw, pl, { lp }, ctx.d_counter.p + 8, ctx.d_profile_long, ctx.h_profile_long[ctx.ss], offset );
+        launch_packed_class( ctx().stream_aux, q, qlen, nw, pl, { lp }, ctx().d_counter.p + 8, ctx().d_profile_long, ctx().h_profile_long[g_stage_slot], offset );
     }
-    if( use_aux ) CUDA_OK( cudaEventRecord( ctx.ev_join, ctx.stream_aux ) );
+    if( use_aux ) CUDA_OK( cudaEventRecord( ctx().ev_join, ctx().stream_aux ) );
     // ---- bulk class ----
     if( b0 < bt.batches.size() ) {
         std::vector<PassLaunch> passes;
         if( npass > 1 ) {
             passes = plan_passes( qlen, R, npass, db.total_cols - db.pair_col[bulk_pair0], db.sorted_len[2 * bulk_pair0], sms );
-            ctx.d_bnd.reserve( 4 * db.total_cols + 256 );
+            ctx().d_bnd.reserve( 4 * db.total_cols + 256 );
         }
         else {
             PassLaunch ps;
@@ -1060,16 +1328,16 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             ps.d_batches = pt.d_batches.p;
             ps.nbatches = (uint32_t) pt.batches.size();
         }
-        launch_packed_class( ctx.stream, q, qlen, nw, pl, passes, ctx.d_counter.p, ctx.d_profile, ctx.h_profile[ctx.ss], offset );
+        launch_packed_class( ctx().stream, q, qlen, nw, pl, passes, ctx().d_counter.p, ctx().d_profile, ctx().h_profile[g_stage_slot], offset );
     }
-    if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx.stream, ctx.ev_join, 0 ) );
+    if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx().stream, ctx().ev_join, 0 ) );
     if( wide_pairs < db.npairs ) {
         const uint32_t np = (uint32_t) ( db.npairs - wide_pairs );
-        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_out_packed.p, ctx.d_scores.p, (uint32_t) wide_pairs,
+        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx().stream>>>( ctx().d_out_packed.p, ctx().d_scores.p, (uint32_t) wide_pairs,
                 (uint32_t) db.npairs, (uint32_t) nloc, offset );
-        ctx.stats.launches++;
+        ctx().stats.launches++;
     }
-    CUDA_OK( cudaEventRecord( ctx.ev_k1, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_k1, ctx().stream ) );
 }
 
 // ---- order emulation of the reference's narrow NW tiers (nw_sat.cuh) ----
@@ -1104,7 +1372,7 @@ int64_t nw_tier_safe_len( size_t qlen, int bits ) {
 
 // number of leading local sorted positions (longest sequences first) whose length exceeds `len`
 size_t sorted_prefix_longer_than( int64_t len ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     size_t lo = 0, hi = db.sorted_len.size();
     while( lo < hi ) {
         size_t mid = ( lo + hi ) / 2;
@@ -1119,48 +1387,48 @@ size_t sorted_prefix_longer_than( int64_t len ) {
 // emulates the `bits`-wide saturating NW kernel for the first `count` local sorted positions; first_col[s] receives
 // 4 * (overflow block) for the records that overflow
 void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t * d_first_col ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     if( count == 0 ) return;
-    if( ctx.matrix32_version != g_matrix.version ) {
+    if( ctx().matrix32_version != g_matrix.version ) {
         int32_t m32[1024];
         for( int i = 0; i < 1024; i++ ) m32[i] = (int32_t) g_matrix.m[i];
-        ctx.d_matrix32.reserve( 1024 );
-        CUDA_OK( cudaMemcpy( ctx.d_matrix32.p, m32, sizeof( m32 ), cudaMemcpyHostToDevice ) );
-        ctx.matrix32_version = g_matrix.version;
+        ctx().d_matrix32.reserve( 1024 );
+        CUDA_OK( cudaMemcpy( ctx().d_matrix32.p, m32, sizeof( m32 ), cudaMemcpyHostToDevice ) );
+        ctx().matrix32_version = g_matrix.version;
     }
-    ctx.d_query.reserve( qlen + 1 );
-    CUDA_OK( cudaMemcpyAsync( ctx.d_query.p, q, qlen, cudaMemcpyHostToDevice, ctx.stream ) );
-    ctx.stats.h2d_bytes += qlen;
+    ctx().d_query.reserve( qlen + 1 );
+    CUDA_OK( cudaMemcpyAsync( ctx().d_query.p, q, qlen, cudaMemcpyHostToDevice, ctx().stream ) );
+    ctx().stats.h2d_bytes += qlen;
     const size_t wave = std::max<size_t>( 4096, ( 256u << 20 ) / ( 4 * qlen ) );
-    ctx.d_nw_scratch.reserve( 2 * qlen * std::min( wave, count ) + 16 );
-    ctx.d_wave_list.reserve( std::min( wave, count ) + 1 );
+    ctx().d_nw_scratch.reserve( 2 * qlen * std::min( wave, count ) + 16 );
+    ctx().d_wave_list.reserve( std::min( wave, count ) + 1 );
     for( size_t first = 0; first < count; first += wave ) {
         const size_t n = std::min( wave, count - first );
-        iota_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_wave_list.p, (uint32_t) first, (uint32_t) n );
+        iota_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, ctx().stream>>>( ctx().d_wave_list.p, (uint32_t) first, (uint32_t) n );
         NwSatArgs a;
         a.stream = db.d_stream.p;
         a.pair_col = db.d_pair_col.p;
         a.sorted_len = db.d_sorted_len.p;
-        a.list = ctx.d_wave_list.p;
+        a.list = ctx().d_wave_list.p;
         a.count = (uint32_t) n;
-        a.query = ctx.d_query.p;
+        a.query = ctx().d_query.p;
         a.qlen = (uint32_t) qlen;
-        a.matrix = ctx.d_matrix32.p;
+        a.matrix = ctx().d_matrix32.p;
         a.gap_open = g_gapO;
         a.gap_extend = g_gapE;
         a.bits = bits;
-        a.scratch_h = ctx.d_nw_scratch.p;
-        a.scratch_e = ctx.d_nw_scratch.p + qlen * n;
+        a.scratch_h = ctx().d_nw_scratch.p;
+        a.scratch_e = ctx().d_nw_scratch.p + qlen * n;
         a.first_col = d_first_col;
-        nw_sat_kernel<<<(unsigned) ( ( n + 127 ) / 128 ), 128, 0, ctx.stream>>>( a );
-        ctx.stats.launches += 2;
+        nw_sat_kernel<<<(unsigned) ( ( n + 127 ) / 128 ), 128, 0, ctx().stream>>>( a );
+        ctx().stats.launches += 2;
     }
 }
 
 // where each chunk of `chunk` provider records starts in arrival order (the reference stops at the first chunk
 // without a non-empty record, src/algo/16/search_16.c:123)
 PackedDb::ChunkInfo & chunk_info_for( size_t chunk ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     auto it = db.chunk_info.find( chunk );
     if( it != db.chunk_info.end() ) return it->second;
     PackedDb::ChunkInfo & ci = db.chunk_info[chunk];
@@ -1186,12 +1454,12 @@ PackedDb::ChunkInfo & chunk_info_for( size_t chunk ) {
 // columns of the tracking kernel or nullptr.  Returns the number of records in arrival order.
 size_t gpu_arrival_order( int bit_width, size_t chunk, const int32_t * d_first_all, size_t stride, DevBuf<int32_t> & d_pos,
         uint32_t * h_order ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     PackedDb::ChunkInfo & ci = chunk_info_for( chunk );
     const size_t nglob = db.sorted_all.size();
     d_pos.reserve( nglob + 1 );
-    ctx.d_order.reserve( ci.narr + 1 );
-    CUDA_OK( cudaMemsetAsync( d_pos.p, 0xff, ( nglob + 1 ) * sizeof( int32_t ), ctx.stream ) );
+    ctx().d_order.reserve( ci.narr + 1 );
+    CUDA_OK( cudaMemsetAsync( d_pos.p, 0xff, ( nglob + 1 ) * sizeof( int32_t ), ctx().stream ) );
     if( ci.nchunks > 0 ) {
         ArrivalArgs a;
         a.lens = db.d_lens_all.p;
@@ -1203,14 +1471,14 @@ size_t gpu_arrival_order( int bit_width, size_t chunk, const int32_t * d_first_a
         a.sorted_pos_of_id = db.d_sorted_pos_of_id.p;
         a.first_all = d_first_all;
         a.stride = (uint32_t) stride;
-        a.world = (uint32_t) ctx.world;
-        a.order = ctx.d_order.p;
+        a.world = (uint32_t) ctx().world;
+        a.order = ctx().d_order.p;
         a.pos_of_sorted = d_pos.p;
-        arrival_kernel<<<ci.nchunks, 32, 0, ctx.stream>>>( a );
-        ctx.stats.launches++;
-        if( h_order ) {  // nullptr: the caller fetches the part of ctx.d_order it needs
-            CUDA_OK( cudaMemcpyAsync( h_order, ctx.d_order.p, ci.narr * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            ctx.stats.d2h_bytes += ci.narr * sizeof( uint32_t );
+        arrival_kernel<<<ci.nchunks, 32, 0, ctx().stream>>>( a );
+        ctx().stats.launches++;
+        if( h_order ) {  // nullptr: the caller fetches the part of ctx().d_order it needs
+            CUDA_OK( cudaMemcpyAsync( h_order, ctx().d_order.p, ci.narr * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+            ctx().stats.d2h_bytes += ci.narr * sizeof( uint32_t );
         }
     }
     return ci.narr;
@@ -1218,29 +1486,29 @@ size_t gpu_arrival_order( int bit_width, size_t chunk, const int32_t * d_first_a
 
 PackedDb::Arrival & arrival_for( int bit_width, size_t chunk, bool on_gpu );
 void upload_positions( const std::vector<uint32_t> & order, DevBuf<int32_t> & d_pos ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t nglob = db.sorted_all.size();
-    ctx.h_pos.reserve( nglob + 1 );
-    int32_t * pos = ctx.h_pos.p;
+    ctx().h_pos.reserve( nglob + 1 );
+    int32_t * pos = ctx().h_pos.p;
     if( order.size() != nglob ) std::fill( pos, pos + nglob, -1 );  // records the reference never reaches
     for( size_t a = 0; a < order.size(); a++ ) pos[db.sorted_pos_of_id[order[a]]] = (int32_t) a;
     d_pos.reserve( nglob + 1 );
-    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos, nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx.stream ) );
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-    ctx.stats.h2d_bytes += nglob * sizeof( int32_t );
+    CUDA_OK( cudaMemcpyAsync( d_pos.p, pos, nglob * sizeof( int32_t ), cudaMemcpyHostToDevice, ctx().stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+    ctx().stats.h2d_bytes += nglob * sizeof( int32_t );
 }
 
 PackedDb::Arrival & arrival_for( int bit_width, size_t chunk, bool on_gpu ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     auto key = std::make_pair( bit_width, chunk );
     auto it = db.arrival.find( key );
     if( it != db.arrival.end() ) return it->second;
     PackedDb::Arrival & ar = db.arrival[key];
     if( on_gpu ) {
-        ctx.h_order.reserve( db.sorted_all.size() + 1 );
-        const size_t n = gpu_arrival_order( bit_width, chunk, nullptr, 1, ar.d_pos_of_sorted, ctx.h_order.p );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        ar.order.assign( ctx.h_order.p, ctx.h_order.p + n );
+        ctx().h_order.reserve( db.sorted_all.size() + 1 );
+        const size_t n = gpu_arrival_order( bit_width, chunk, nullptr, 1, ar.d_pos_of_sorted, ctx().h_order.p );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+        ar.order.assign( ctx().h_order.p, ctx().h_order.p + n );
     }
     else {
         arrival_order( db.lens_all, nullptr, nullptr, chunk, bit_width, ar.order );
@@ -1250,17 +1518,24 @@ PackedDb::Arrival & arrival_for( int bit_width, size_t chunk, bool on_gpu ) {
     return ar;
 }
 
-// all-gather `count` int32 per rank from d_send into d_recv (rank-major); world = 1: plain copy
+// all-gather `count` int32 per rank from d_send into d_recv (rank-major) on the calling context's stream; world = 1: plain copy.
+// The collective runs INSIDE the library: ncclAllGather on the communicator of ssa_b200_nccl_init (one process per GPU) or
+// of ncclCommInitAll (one process, several GPUs: every context's host thread calls it for its own rank).  A host-supplied
+// callback (ssa_b200_set_allgather) is the alternative for hosts that bring their own collective.
 void gather_i32( const int32_t * d_send, int32_t * d_recv, size_t count ) {
-    if( ctx.world == 1 ) {
+    if( ctx().world == 1 ) {
         if( d_send != d_recv )
-            CUDA_OK( cudaMemcpyAsync( d_recv, d_send, count * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx.stream ) );
+            CUDA_OK( cudaMemcpyAsync( d_recv, d_send, count * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx().stream ) );
         return;
     }
-    if( !ctx.allgather )
-        fatal( "libssa_b200: the database is sharded over %d processes but no all-gather collective was registered "
-               "(ssa_b200_set_allgather).", ctx.world );
-    ctx.allgather( ctx.allgather_ctx, d_send, d_recv, count * sizeof( int32_t ), (void *) ctx.stream );
+    if( ctx().comm ) {
+        NCCL_OK( g_nccl.AllGather( d_send, d_recv, count, ncclInt32, ctx().comm, ctx().stream ) );
+        return;
+    }
+    if( !g_cfg.allgather )
+        fatal( "libssa_b200: the database is sharded over %d processes but no collective is available "
+               "(ssa_b200_nccl_init or ssa_b200_set_allgather).", ctx().world );
+    g_cfg.allgather( g_cfg.allgather_ctx, d_send, d_recv, count * sizeof( int32_t ), (void *) ctx().stream );
 }
 
 }  // namespace
@@ -1271,122 +1546,181 @@ void gather_i32( const int32_t * d_send, int32_t * d_recv, size_t count ) {
 
 void gpu_prepare_db() { build_db(); }
 
-void gpu_release() {
-    if( !ctx.init ) return;
-    cudaStreamSynchronize( ctx.stream );
-    ctx.db.d_stream.release();
-    ctx.db.d_lens_all.release();
-    ctx.db.d_pair_col.release();
-    ctx.db.d_sorted_all.release();
-    ctx.db.d_sorted_len.release();
-    ctx.db.d_sorted_pos_of_id.release();
-    for( auto & kv : ctx.db.chunk_info ) kv.second.d_chunk_base.release();
-    ctx.db.chunk_info.clear();
-    for( auto & kv : ctx.db.batch_tables ) kv.second.d_batches.release();
-    ctx.db.batch_tables.clear();
-    for( auto & kv : ctx.db.arrival ) kv.second.d_pos_of_sorted.release();
-    ctx.db.arrival.clear();
-    ctx.db.valid = false;
-    ctx.d_profile.release();
-    ctx.d_out_packed.release();
-    ctx.d_counter.release();
-    ctx.d_bnd.release();
-    ctx.d_bnd_wide.release();
-    ctx.d_scores.release();
-    ctx.d_all_slot[0].release();
-    ctx.d_all_slot[1].release();
-    ctx.d_arrival_scores.release();
-    ctx.d_first.release();
-    ctx.d_first_compact.release();
-    ctx.d_gathered.release();
-    ctx.d_pos_tmp.release();
-    ctx.d_guard.release();
+static void release_ctx( Ctx & c ) {
+    cudaSetDevice( c.device );
+    cudaDeviceSynchronize();
+    PackedDb & db = c.db;
+    db.d_stream.release();
+    db.d_lens_all.release();
+    db.d_pair_col.release();
+    db.d_sorted_all.release();
+    db.d_sorted_len.release();
+    db.d_sorted_pos_of_id.release();
+    for( auto & kv : db.chunk_info ) kv.second.d_chunk_base.release();
+    db.chunk_info.clear();
+    for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
+    db.batch_tables.clear();
+    for( auto & kv : db.arrival ) kv.second.d_pos_of_sorted.release();
+    db.arrival.clear();
+    db.valid = false;
+    c.d_profile.release();
+    c.d_profile_long.release();
+    c.d_out_packed.release();
+    c.d_counter.release();
+    c.d_bnd.release();
+    c.d_bnd_wide.release();
+    c.d_long_batches.release();
+    c.d_first_compact.release();
+    c.d_scores.release();
+    c.d_gathered.release();
+    c.d_arrival_scores.release();
+    c.d_first.release();
+    c.d_guard.release();
+    c.d_pos_tmp.release();
+    c.d_order.release();
+    c.d_wave_list.release();
+    c.d_topk_ids.release();
+    c.d_topk_scores.release();
+    c.d_select.release();
+    c.d_nw_scratch.release();
+    c.d_query.release();
+    c.d_matrix32.release();
+    c.matrix32_version = ~0ull;
+    c.d_flag_list.release();
+    c.d_cand_pos.release();
+    c.d_cand_id.release();
+    c.d_cand_score.release();
+    c.h_order.release();
+    c.h_list.release();
+    c.h_scores.release();
+    c.h_first.release();
+    c.h_pos.release();
+    c.h_cand_pos.release();
+    c.h_cand_id.release();
+    c.h_cand_score.release();
     for( int i = 0; i < 2; i++ ) {
-        ctx.d_wide_batches[i].release();
-        ctx.d_profile_wide[i].release();
+        c.d_all_slot[i].release();
+        c.d_wide_batches[i].release();
+        c.d_profile_wide[i].release();
         for( int j = 0; j < 2; j++ ) {
-            ctx.h_wide_batches[i][j].release();
-            ctx.h_profile_wide[i][j].release();
+            c.h_wide_batches[i][j].release();
+            c.h_profile_wide[i][j].release();
         }
-        ctx.h_long_batches[i].release();
-        ctx.h_profile_long[i].release();
-        ctx.h_profile[i].release();
-        ctx.h_select[i].release();
-        ctx.h_topk_ids[i].release();
-        ctx.h_topk_scores[i].release();
-        ctx.h_counts[i].release();
-        if( ctx.ev_topk[i] ) cudaEventDestroy( ctx.ev_topk[i] );
-        ctx.ev_topk[i] = nullptr;
+        c.h_long_batches[i].release();
+        c.h_profile_long[i].release();
+        c.h_profile[i].release();
+        c.h_select[i].release();
+        c.h_topk_ids[i].release();
+        c.h_topk_scores[i].release();
+        c.h_counts[i].release();
+        if( c.ev_topk[i] ) cudaEventDestroy( c.ev_topk[i] );
+        c.ev_topk[i] = nullptr;
     }
-    ctx.d_order.release();
-    ctx.d_topk_ids.release();
-    ctx.d_topk_scores.release();
-    ctx.d_select.release();
-    ctx.d_wave_list.release();
-    ctx.d_nw_scratch.release();
-    ctx.d_query.release();
-    ctx.d_matrix32.release();
-    ctx.matrix32_version = ~0ull;
-    ctx.h_order.release();
-    ctx.d_flag_list.release();
-    ctx.h_profile[ctx.ss].release();
-    ctx.h_list.release();
-    ctx.h_scores.release();
-    ctx.h_first.release();
-    ctx.h_pos.release();
-    ctx.d_cand_pos.release();
-    ctx.d_cand_id.release();
-    ctx.d_cand_score.release();
-    ctx.h_cand_pos.release();
-    ctx.h_cand_id.release();
-    ctx.h_cand_score.release();
-    traceback_release();
-    cudaEventDestroy( ctx.ev_begin );
-    cudaEventDestroy( ctx.ev_k0 );
-    cudaEventDestroy( ctx.ev_k1 );
-    cudaEventDestroy( ctx.ev_end );
-    cudaEventDestroy( ctx.ev_fork );
-    cudaEventDestroy( ctx.ev_join );
-    cudaStreamDestroy( ctx.stream_aux );
-    cudaStreamDestroy( ctx.stream );
-    ctx.d_profile_long.release();
-    ctx.d_long_batches.release();
-    ctx.h_long_batches[ctx.ss].release();
-    ctx.h_profile_long[ctx.ss].release();
-    ctx.init = false;
+    cudaEventDestroy( c.ev_begin );
+    cudaEventDestroy( c.ev_k0 );
+    cudaEventDestroy( c.ev_k1 );
+    cudaEventDestroy( c.ev_end );
+    cudaEventDestroy( c.ev_fork );
+    cudaEventDestroy( c.ev_join );
+    cudaStreamDestroy( c.stream_aux );
+    cudaStreamDestroy( c.stream );
 }
 
+void gpu_release() {
+    if( g_devs.empty() ) return;
+    if( !g_workers.threads.empty() ) {
+        {
+            std::lock_guard<std::mutex> lk( g_workers.m );
+            g_workers.stop = true;
+        }
+        g_workers.cv_go.notify_all();
+        for( std::thread & th : g_workers.threads ) th.join();
+        g_workers.threads.clear();
+        g_workers.stop = false;
+    }
+    for( Ctx * c : g_devs ) {
+        cudaSetDevice( c->device );
+        cudaDeviceSynchronize();
+    }
+    for( Ctx * c : g_devs )
+        if( c->comm ) {
+            g_nccl.CommDestroy( c->comm );
+            c->comm = nullptr;
+        }
+    cudaSetDevice( g_devs[0]->device );
+    traceback_release();
+    for( Ctx * c : g_devs ) {
+        release_ctx( *c );
+        delete c;
+    }
+    g_devs.clear();
+    t_ctx = nullptr;
+    g_gdb.release();
+}
+
+// per-call counters of every context -> zero; the primary's record is what ssa_b200_get_stats returns
+static void reset_call_stats() {
+    for( Ctx * c : g_devs ) {
+        c->stats.launches = 0;
+        c->stats.h2d_bytes = c->stats.d2h_bytes = 0;
+        c->stats.wide_tier_seqs = 0;
+        c->stats.overflow_8 = c->stats.overflow_16 = 0;
+        c->scored = false;
+    }
+}
+
+// sums the other contexts' counters into the primary's record; score kernel time = the slowest device's
+static void merge_call_stats() {
+    ssa_b200_stats_t & st = g_devs[0]->stats;
+    float kernel_ms = 0;
+    for( Ctx * c : g_devs ) {
+        if( c != g_devs[0] ) {
+            st.launches += c->stats.launches;
+            st.h2d_bytes += c->stats.h2d_bytes;
+            st.d2h_bytes += c->stats.d2h_bytes;
+            st.wide_tier_seqs += c->stats.wide_tier_seqs;
+            c->stats.launches = 0;
+            c->stats.h2d_bytes = c->stats.d2h_bytes = 0;
+            c->stats.wide_tier_seqs = 0;
+        }
+        if( c->scored ) {
+            float ms = 0;
+            if( cudaEventElapsedTime( &ms, c->ev_k0, c->ev_k1 ) == cudaSuccess ) kernel_ms = std::max( kernel_ms, ms );
+        }
+    }
+    cudaGetLastError();   // an event of another device may not have completed yet: not an error
+    st.score_kernel_ms = kernel_ms;
+}
+
+// Exact scores of every record this PROCESS holds (all its contexts' shards), provider order.
 size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64_t * scores, uint64_t * ids ) {
     build_db();
-    PackedDb & db = ctx.db;
-    const size_t nloc = db.sorted_id.size();
-    ctx.stats.launches = 0;
-    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
-    ctx.stats.wide_tier_seqs = 0;
-    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
-    score_shard( query, qlen, search_type == NEEDLEMAN_WUNSCH );
-    ctx.h_scores.reserve( nloc + 1 );
-    if( nloc ) CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_scores.p, nloc * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-    ctx.stats.d2h_bytes += nloc * sizeof( int32_t );
+    reset_call_stats();
+    CUDA_OK( cudaEventRecord( ctx().ev_begin, ctx().stream ) );
+    run_on_all( [&]() {
+        PackedDb & db = ctx().db;
+        const size_t nloc = db.sorted_id.size();
+        score_shard( query, qlen, search_type == NEEDLEMAN_WUNSCH );
+        ctx().h_scores.reserve( nloc + 1 );
+        if( nloc ) CUDA_OK( cudaMemcpyAsync( ctx().h_scores.p, ctx().d_scores.p, nloc * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+        if( is_primary() ) CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+        ctx().stats.d2h_bytes += nloc * sizeof( int32_t );
+    } );
+    merge_call_stats();
     float ms = 0;
-    if( nloc ) {
-        cudaEventElapsedTime( &ms, ctx.ev_k0, ctx.ev_k1 );
-        ctx.stats.score_kernel_ms = ms;
+    cudaEventElapsedTime( &ms, ctx().ev_begin, ctx().ev_end );
+    ctx().stats.device_ms = ms;
+    ctx().stats.cells = (uint64_t) qlen * process_residues();
+    std::vector<std::pair<uint32_t, int32_t>> all;   // (provider index, score)
+    for( Ctx * c : g_devs )
+        for( size_t i = 0; i < c->db.sorted_id.size(); i++ ) all.emplace_back( c->db.sorted_id[i], c->h_scores.p[i] );
+    std::sort( all.begin(), all.end() );
+    for( size_t i = 0; i < all.size(); i++ ) {
+        if( scores ) scores[i] = all[i].second;
+        if( ids ) ids[i] = all[i].first;
     }
-    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
-    ctx.stats.device_ms = ms;
-    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
-    // provider order of this shard
-    std::vector<uint32_t> by_id( nloc );
-    std::iota( by_id.begin(), by_id.end(), 0u );
-    std::sort( by_id.begin(), by_id.end(), [&]( uint32_t a, uint32_t b ) { return db.sorted_id[a] < db.sorted_id[b]; } );
-    for( size_t i = 0; i < nloc; i++ ) {
-        if( scores ) scores[i] = ctx.h_scores.p[by_id[i]];
-        if( ids ) ids[i] = db.sorted_id[by_id[i]];
-    }
-    return nloc;
+    return all.size();
 }
 
 // ---- top-k on the device ----
@@ -1395,62 +1729,62 @@ size_t gpu_score_all( const uint8_t * query, size_t qlen, int search_type, int64
 // crosses PCIe.  Only when the tie at T straddles the cut-off does the reference's tie behaviour matter; then the
 // arrival-order replay of search_single runs.  Split in two so that a batch of queries can keep the GPU busy with the
 // next query while the host picks up the results of this one.
-static bool topk_applicable( PackedDb::Arrival & base, size_t k ) { return k > 0 && k < base.order.size() && !ctx.db.sorted_all.empty(); }
+static bool topk_applicable( PackedDb::Arrival & base, size_t k ) { return k > 0 && k < base.order.size() && !ctx().db.sorted_all.empty(); }
 
 static void enqueue_topk( const int32_t * d_all, PackedDb::Arrival & base, size_t k, bool count_overflow, int slot ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t nglob = db.sorted_all.size();
-    const size_t world = (size_t) ctx.world;
+    const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;
-    if( ctx.d_select.cap == 0 ) {   // the passes keep the state's histogram, ticket and accumulators zero from here on
-        ctx.d_select.reserve( 1 );
-        CUDA_OK( cudaMemsetAsync( ctx.d_select.p, 0, sizeof( SelectState ), ctx.stream ) );
+    if( ctx().d_select.cap == 0 ) {   // the passes keep the state's histogram, ticket and accumulators zero from here on
+        ctx().d_select.reserve( 1 );
+        CUDA_OK( cudaMemsetAsync( ctx().d_select.p, 0, sizeof( SelectState ), ctx().stream ) );
     }
-    ctx.h_select[slot].reserve( 1 );
+    ctx().h_select[slot].reserve( 1 );
     SelectArgs sa;
     sa.scores = d_all;
     sa.pos = base.d_pos_of_sorted.p;
     sa.stride = (uint32_t) stride;
     sa.world = (uint32_t) world;
     sa.nglobal = (uint32_t) nglob;
-    sa.state = ctx.d_select.p;
+    sa.state = ctx().d_select.p;
     const uint32_t total = (uint32_t) ( stride * world );
     const unsigned grid = std::min<unsigned>( ( total + 255 ) / 256, 148 * 8 );
     const int shifts[3] = { 21, 10, 0 };
     const uint32_t masks[3] = { 0x7ff, 0x7ff, 0x3ff };
-    for( int p = 0; p < 3; p++ ) select_pass_kernel<<<grid, 256, 0, ctx.stream>>>( sa, p, shifts[p], masks[p], (uint32_t) k, p == 2 );
-    ctx.d_topk_scores.reserve( k + 1 );
-    ctx.d_topk_ids.reserve( k + 1 );
-    select_compact_kernel<<<grid, 256, 0, ctx.stream>>>( sa, db.d_sorted_all.p, ctx.d_topk_scores.p, ctx.d_topk_ids.p, (uint32_t) k );
-    ctx.stats.launches += 4;
-    ctx.h_topk_scores[slot].reserve( k + 1 );
-    ctx.h_topk_ids[slot].reserve( k + 1 );
-    ctx.h_counts[slot].reserve( 2 );
-    ctx.h_counts[slot].p[0] = count_overflow ? 1 : 0;   // whether the reference's overflow counters apply (manager.c:157-160)
-    CUDA_OK( cudaMemcpyAsync( ctx.h_select[slot].p, ctx.d_select.p, SELECT_HEADER_BYTES, cudaMemcpyDeviceToHost, ctx.stream ) );
-    CUDA_OK( cudaMemcpyAsync( ctx.h_topk_scores[slot].p, ctx.d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-    CUDA_OK( cudaMemcpyAsync( ctx.h_topk_ids[slot].p, ctx.d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-    CUDA_OK( cudaEventRecord( ctx.ev_topk[slot], ctx.stream ) );
-    ctx.stats.d2h_bytes += SELECT_HEADER_BYTES + k * 8;
+    for( int p = 0; p < 3; p++ ) select_pass_kernel<<<grid, 256, 0, ctx().stream>>>( sa, p, shifts[p], masks[p], (uint32_t) k, p == 2 );
+    ctx().d_topk_scores.reserve( k + 1 );
+    ctx().d_topk_ids.reserve( k + 1 );
+    select_compact_kernel<<<grid, 256, 0, ctx().stream>>>( sa, db.d_sorted_all.p, ctx().d_topk_scores.p, ctx().d_topk_ids.p, (uint32_t) k );
+    ctx().stats.launches += 4;
+    ctx().h_topk_scores[slot].reserve( k + 1 );
+    ctx().h_topk_ids[slot].reserve( k + 1 );
+    ctx().h_counts[slot].reserve( 2 );
+    ctx().h_counts[slot].p[0] = count_overflow ? 1 : 0;   // whether the reference's overflow counters apply (manager.c:157-160)
+    CUDA_OK( cudaMemcpyAsync( ctx().h_select[slot].p, ctx().d_select.p, SELECT_HEADER_BYTES, cudaMemcpyDeviceToHost, ctx().stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx().h_topk_scores[slot].p, ctx().d_topk_scores.p, k * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+    CUDA_OK( cudaMemcpyAsync( ctx().h_topk_ids[slot].p, ctx().d_topk_ids.p, k * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_topk[slot], ctx().stream ) );
+    ctx().stats.d2h_bytes += SELECT_HEADER_BYTES + k * 8;
 }
 
 // waits for the slot's results; true (and the sorted hit list) if the set does not depend on the arrival order
 static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & hits ) {
-    CUDA_OK( cudaEventSynchronize( ctx.ev_topk[slot] ) );
-    const SelectState & st = *ctx.h_select[slot].p;
+    CUDA_OK( cudaEventSynchronize( ctx().ev_topk[slot] ) );
+    const SelectState & st = *ctx().h_select[slot].p;
     hits.clear();
     if( (size_t) st.count_gt + st.count_eq > k ) return false;
     const size_t n = (size_t) st.count_gt + st.count_eq;
     hits.resize( n );
-    for( size_t i = 0; i < n; i++ ) hits[i] = Hit{ ctx.h_topk_ids[slot].p[i], ctx.h_topk_scores[slot].p[i] };
+    for( size_t i = 0; i < n; i++ ) hits[i] = Hit{ ctx().h_topk_ids[slot].p[i], ctx().h_topk_scores[slot].p[i] };
     std::sort( hits.begin(), hits.end(), []( const Hit & x, const Hit & y ) {
         if( x.score != y.score ) return x.score > y.score;
         return x.db_id > y.db_id;
     } );
-    const bool counted = ctx.h_counts[slot].p[0] != 0;
-    if( bit_width == 8 ) ctx.stats.overflow_8 = counted ? st.ge8 : 0;
-    if( bit_width == 8 || bit_width == 16 ) ctx.stats.overflow_16 = counted ? st.ge16 : 0;
+    const bool counted = ctx().h_counts[slot].p[0] != 0;
+    if( bit_width == 8 ) ctx().stats.overflow_8 = counted ? st.ge8 : 0;
+    if( bit_width == 8 || bit_width == 16 ) ctx().stats.overflow_16 = counted ? st.ge16 : 0;
     return true;
 }
 
@@ -1458,17 +1792,19 @@ static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & 
 // (slot) indices.  Every key (score, id) is distinct, so the final order does not depend on the sort algorithm.
 // scores of this shard's entries -> every rank; returns the gathered score vector (rank-major blocks of `stride`)
 static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw ) {
-    PackedDb & db = ctx.db;
-    const size_t nglob = db.sorted_all.size();
-    const size_t world = (size_t) ctx.world;
+    const size_t nglob = ctx().db.sorted_all.size();
+    const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;  // local positions per rank, padded
-    ctx.d_scores.reserve( stride + 2 );
-    score_shard( query, qlen, nw );
-    // ---- shard results -> every rank (NCCL all-gather over NVLink, supplied by the host language) ----
-    if( world == 1 ) return ctx.d_scores.p;
-    ctx.d_gathered.reserve( stride * world + 2 );
-    gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
-    return ctx.d_gathered.p;
+    run_on_all( [&]() {
+        ctx().d_scores.reserve( stride + 2 );
+        score_shard( query, qlen, nw );
+        // ---- shard results -> every rank (ncclAllGather over NVLink / NVSwitch, on this context's stream) ----
+        if( world > 1 ) {
+            ctx().d_gathered.reserve( stride * world + 2 );
+            gather_i32( ctx().d_scores.p, ctx().d_gathered.p, stride );
+        }
+    } );
+    return world == 1 ? ctx().d_scores.p : ctx().d_gathered.p;
 }
 
 static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits );
@@ -1484,9 +1820,9 @@ static bool sparse_replay_applies( size_t narr, size_t hitcount ) {
 }
 
 static void search_single( const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
-    ctx.stats.cells = (uint64_t) qlen * db.local_residues;
+    ctx().stats.cells = (uint64_t) qlen * process_residues();
     const int32_t * d_all = score_query( query, qlen, nw );
     // ---- top-k on the device (see enqueue_topk) ----
     const size_t chunk = g_chunk_size * (size_t) db.buffer_max;  // entries per reference chunk (db_adapter.c:196)
@@ -1502,9 +1838,9 @@ static void search_single( const uint8_t * query, size_t qlen, const SearchReque
 // The reference's tie behaviour in full: which records overflow a narrow tier and where, the heap-arrival order of the
 // emulated one-thread run, and the heap replay (used when ties straddle the cut-off of the hit list).
 static void select_replay( const int32_t * d_all, const uint8_t * query, size_t qlen, const SearchRequest & req, std::vector<Hit> & hits ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t nglob = db.sorted_all.size();
-    const size_t world = (size_t) ctx.world;
+    const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     const size_t chunk = g_chunk_size * (size_t) db.buffer_max;
@@ -1522,60 +1858,60 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     if( !nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
         const int32_t thr = req.bit_width == 8 ? 255 : 65535;
         const uint32_t total = (uint32_t) ( stride * world );
-        ctx.d_flag_list.reserve( total + 2 );
-        uint32_t * d_count = ctx.d_flag_list.p + total;
-        CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx.stream ) );
-        flag_overflow_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, (uint32_t) stride, (uint32_t) world,
-                (uint32_t) nglob, thr, ctx.d_flag_list.p, d_count, total );
-        ctx.stats.launches++;
-        ctx.h_list.reserve( total + 2 );
-        CUDA_OK( cudaMemcpyAsync( ctx.h_list.p + total, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        const uint32_t count = ctx.h_list.p[total];
-        ctx.stats.d2h_bytes += 4;
+        ctx().d_flag_list.reserve( total + 2 );
+        uint32_t * d_count = ctx().d_flag_list.p + total;
+        CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx().stream ) );
+        flag_overflow_kernel<<<( total + 255 ) / 256, 256, 0, ctx().stream>>>( d_all, (uint32_t) stride, (uint32_t) world,
+                (uint32_t) nglob, thr, ctx().d_flag_list.p, d_count, total );
+        ctx().stats.launches++;
+        ctx().h_list.reserve( total + 2 );
+        CUDA_OK( cudaMemcpyAsync( ctx().h_list.p + total, d_count, 4, cudaMemcpyDeviceToHost, ctx().stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+        const uint32_t count = ctx().h_list.p[total];
+        ctx().stats.d2h_bytes += 4;
         if( count > 0 ) {  // every rank sees the same gathered scores, so every rank takes this branch together
             have_overflow = true;
-            CUDA_OK( cudaMemcpyAsync( ctx.h_list.p, ctx.d_flag_list.p, count * 4, cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += count * 4;
-            std::vector<uint32_t> flagged( ctx.h_list.p, ctx.h_list.p + count );  // gathered indices r*stride + s
+            CUDA_OK( cudaMemcpyAsync( ctx().h_list.p, ctx().d_flag_list.p, count * 4, cudaMemcpyDeviceToHost, ctx().stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+            ctx().stats.d2h_bytes += count * 4;
+            std::vector<uint32_t> flagged( ctx().h_list.p, ctx().h_list.p + count );  // gathered indices r*stride + s
             std::sort( flagged.begin(), flagged.end() );
-            std::vector<uint32_t> slots;  // this rank's own flagged local positions
-            for( uint32_t i : flagged )
-                if( i / stride == (uint32_t) ctx.rank ) slots.push_back( (uint32_t) ( i % stride ) );
-            // first columns at which the running maximum reaches 255 / 65535, via the tracking wide kernel
-            ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
-            int32_t * d_f = ctx.d_first.p;  // [stride] first8 | [stride] first16
-            launch_fill( d_f, INT_MAX, 2 * stride );
-            Plan pl = make_plan( qlen );
-            run_wide( slots, query, qlen, pl, false, true, d_f, d_f + stride, 1, ctx.stream );  // rewrites the same exact scores
-            int32_t * d_f_all = d_f;
-            if( world > 1 ) {
-                d_f_all = ctx.d_first.p + 2 * stride;
-                gather_i32( d_f, d_f_all, 2 * stride );
-            }
+            // first columns at which the running maximum reaches 255 / 65535, via the tracking wide kernel: every context
+            // re-runs its own flagged records, the columns are all-gathered like the scores
+            const Plan pl = make_plan( qlen );
+            run_on_all( [&]() {
+                std::vector<uint32_t> slots;  // this rank's own flagged local positions
+                for( uint32_t i : flagged )
+                    if( i / stride == (uint32_t) ctx().rank ) slots.push_back( (uint32_t) ( i % stride ) );
+                ctx().d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+                int32_t * d_f = ctx().d_first.p;  // [stride] first8 | [stride] first16
+                launch_fill( d_f, INT_MAX, 2 * stride );
+                run_wide( slots, query, qlen, pl, false, true, d_f, d_f + stride, 1, ctx().stream );  // rewrites the same exact scores
+                if( world > 1 ) gather_i32( d_f, ctx().d_first.p + 2 * stride, 2 * stride );
+            } );
+            int32_t * d_f_all = world > 1 ? ctx().d_first.p + 2 * stride : ctx().d_first.p;
             d_first_gathered = d_f_all;
             // overflow counters (the reference prints them at OUTPUT_INFO) and, for the host fallback, the columns
-            ctx.d_first_compact.reserve( 2 * (size_t) count + 2 );
-            gather_first_kernel<<<( count + 255 ) / 256, 256, 0, ctx.stream>>>( ctx.d_flag_list.p, count, d_f_all, (uint32_t) stride,
-                    ctx.d_first_compact.p );
-            ctx.stats.launches++;
-            ctx.h_first.reserve( 2 * (size_t) count + 2 );
-            CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, ctx.d_first_compact.p, 2 * (size_t) count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+            ctx().d_first_compact.reserve( 2 * (size_t) count + 2 );
+            gather_first_kernel<<<( count + 255 ) / 256, 256, 0, ctx().stream>>>( ctx().d_flag_list.p, count, d_f_all, (uint32_t) stride,
+                    ctx().d_first_compact.p );
+            ctx().stats.launches++;
+            ctx().h_first.reserve( 2 * (size_t) count + 2 );
+            CUDA_OK( cudaMemcpyAsync( ctx().h_first.p, ctx().d_first_compact.p, 2 * (size_t) count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
             if( !use_gpu_arrival ) {
-                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
                 ovf8.assign( db.lens_all.size(), -1 );
                 ovf16.assign( db.lens_all.size(), -1 );
-                for( uint32_t k = 0; k < count; k++ ) {   // ctx.h_list still holds the (unsorted) device list order
-                    const uint32_t i = ctx.h_list.p[k];
+                for( uint32_t k = 0; k < count; k++ ) {   // ctx().h_list still holds the (unsorted) device list order
+                    const uint32_t i = ctx().h_list.p[k];
                     const size_t r = i / stride, sl = i % stride;
                     const uint32_t id = db.sorted_all[sl * world + r];
-                    const int32_t c8 = ctx.h_first.p[k], c16 = ctx.h_first.p[count + k];
+                    const int32_t c8 = ctx().h_first.p[k], c16 = ctx().h_first.p[count + k];
                     if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[id] = c8 / 4;
                     if( c16 != INT_MAX ) ovf16[id] = c16 / 4;
                 }
             }
-            ctx.stats.d2h_bytes += 2 * (size_t) count * sizeof( int32_t );
+            ctx().stats.d2h_bytes += 2 * (size_t) count * sizeof( int32_t );
             n_flagged = count;
         }
     }
@@ -1584,41 +1920,43 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
     // (only for the records static bounds cannot clear: usually none at 16 bit, everything at 8 bit)
     uint32_t * d_nw_counts = nullptr;
     if( nw && nglob > 0 && ( req.bit_width == 8 || req.bit_width == 16 ) ) {
-        const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( qlen, 8 ) ) : 0;
-        const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( qlen, 16 ) );
         // every rank takes the same branch: whether any shard needs the emulation follows from the GLOBAL longest record
         const int64_t longest = nglob ? (int64_t) db.lens_all[db.sorted_all[0]] : 0;
         const bool need8 = req.bit_width == 8 && longest > nw_tier_safe_len( qlen, 8 );
         const bool need16 = longest > nw_tier_safe_len( qlen, 16 );
         if( need8 || need16 ) {
             have_overflow = true;
-            ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
-            int32_t * d_f = ctx.d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier
-            launch_fill( d_f, INT_MAX, 2 * stride );
-            if( n8 ) run_nw_sat( query, qlen, 8, n8, d_f );
-            if( n16 ) run_nw_sat( query, qlen, 16, n16, d_f + stride );
-            ctx.d_counter.reserve( 64 );
-            d_nw_counts = ctx.d_counter.p + 32;
-            CUDA_OK( cudaMemsetAsync( d_nw_counts, 0, 8, ctx.stream ) );
-            count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx.stream>>>( d_f, (uint32_t) stride, d_nw_counts );
-            count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx.stream>>>( d_f + stride, (uint32_t) stride, d_nw_counts + 1 );
-            ctx.stats.launches += 2;
-            d_first_gathered = d_f;
-            if( world > 1 ) {
-                int32_t * d_f_all = ctx.d_first.p + 2 * stride;
-                gather_i32( d_f, d_f_all, 2 * stride );
-                d_first_gathered = d_f_all;
+            run_on_all( [&]() {
+                const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( qlen, 8 ) ) : 0;
+                const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( qlen, 16 ) );
+                ctx().d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+                int32_t * d_f = ctx().d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier
+                launch_fill( d_f, INT_MAX, 2 * stride );
+                if( n8 ) run_nw_sat( query, qlen, 8, n8, d_f );
+                if( n16 ) run_nw_sat( query, qlen, 16, n16, d_f + stride );
+                if( world > 1 ) gather_i32( d_f, ctx().d_first.p + 2 * stride, 2 * stride );
+            } );
+            // overflow counters of this process' records, counted on the primary from the (gathered) columns
+            d_first_gathered = world > 1 ? ctx().d_first.p + 2 * stride : ctx().d_first.p;
+            ctx().d_counter.reserve( 64 );
+            d_nw_counts = ctx().d_counter.p + 32;
+            CUDA_OK( cudaMemsetAsync( d_nw_counts, 0, 8, ctx().stream ) );
+            for( Ctx * c : g_devs ) {
+                const int32_t * d_f = d_first_gathered + ( world > 1 ? (size_t) c->rank * 2 * stride : 0 );
+                count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx().stream>>>( d_f, (uint32_t) stride, d_nw_counts );
+                count_set_kernel<<<(unsigned) ( ( stride + 255 ) / 256 ), 256, 0, ctx().stream>>>( d_f + stride, (uint32_t) stride, d_nw_counts + 1 );
+                ctx().stats.launches += 2;
             }
             if( !use_gpu_arrival ) {  // chunk sizes the arrival kernel does not cover: overflow blocks to the host emulation
-                ctx.h_first.reserve( 2 * stride * world + 2 );
-                CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_first_gathered, 2 * stride * world * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-                ctx.stats.d2h_bytes += 2 * stride * world * sizeof( int32_t );
+                ctx().h_first.reserve( 2 * stride * world + 2 );
+                CUDA_OK( cudaMemcpyAsync( ctx().h_first.p, d_first_gathered, 2 * stride * world * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+                ctx().stats.d2h_bytes += 2 * stride * world * sizeof( int32_t );
                 ovf8.assign( db.lens_all.size(), -1 );
                 ovf16.assign( db.lens_all.size(), -1 );
                 for( size_t g = 0; g < nglob; g++ ) {
                     const size_t r = g % world, sl = g / world;
-                    const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
+                    const int32_t c8 = ctx().h_first.p[r * 2 * stride + sl], c16 = ctx().h_first.p[r * 2 * stride + stride + sl];
                     if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[db.sorted_all[g]] = c8 / 4;
                     if( c16 != INT_MAX ) ovf16[db.sorted_all[g]] = c16 / 4;
                 }
@@ -1637,105 +1975,105 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
         d_pos = &ar.d_pos_of_sorted;
     }
     else if( use_gpu_arrival ) {
-        ctx.h_order.reserve( nglob + 1 );
+        ctx().h_order.reserve( nglob + 1 );
         const bool sparse = sparse_replay_applies( chunk_info_for( chunk ).narr, req.hitcount );
-        narr = gpu_arrival_order( req.bit_width, chunk, d_first_gathered, stride, ctx.d_pos_tmp, sparse ? nullptr : ctx.h_order.p );
-        order = sparse ? nullptr : ctx.h_order.p;   // complete once the stream is synchronised below; sparse: stays in ctx.d_order
-        d_pos = &ctx.d_pos_tmp;
+        narr = gpu_arrival_order( req.bit_width, chunk, d_first_gathered, stride, ctx().d_pos_tmp, sparse ? nullptr : ctx().h_order.p );
+        order = sparse ? nullptr : ctx().h_order.p;   // complete once the stream is synchronised below; sparse: stays in ctx().d_order
+        d_pos = &ctx().d_pos_tmp;
     }
     else {
-        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), chunk, req.bit_width, ctx.order_tmp );
-        upload_positions( ctx.order_tmp, ctx.d_pos_tmp );
-        order = ctx.order_tmp.data();
-        narr = ctx.order_tmp.size();
-        d_pos = &ctx.d_pos_tmp;
+        arrival_order( db.lens_all, ovf8.data(), ovf16.data(), chunk, req.bit_width, ctx().order_tmp );
+        upload_positions( ctx().order_tmp, ctx().d_pos_tmp );
+        order = ctx().order_tmp.data();
+        narr = ctx().order_tmp.size();
+        d_pos = &ctx().d_pos_tmp;
     }
     if( narr > 0 && nglob > 0 ) {
-        ctx.d_arrival_scores.reserve( narr + 1 );
+        ctx().d_arrival_scores.reserve( narr + 1 );
         const uint32_t total = (uint32_t) ( stride * world );
-        scatter_arrival_kernel<<<( total + 255 ) / 256, 256, 0, ctx.stream>>>( d_all, d_pos->p, ctx.d_arrival_scores.p,
+        scatter_arrival_kernel<<<( total + 255 ) / 256, 256, 0, ctx().stream>>>( d_all, d_pos->p, ctx().d_arrival_scores.p,
                 (uint32_t) stride, (uint32_t) world, (uint32_t) nglob );
-        ctx.stats.launches++;
-        ctx.h_scores.reserve( narr + 1 );
+        ctx().stats.launches++;
+        ctx().h_scores.reserve( narr + 1 );
         if( !sparse_replay_applies( narr, req.hitcount ) ) {
-            CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += narr * sizeof( int32_t );
-            replay_topk( ctx.h_scores.p, order, narr, req.hitcount, hits );
+            CUDA_OK( cudaMemcpyAsync( ctx().h_scores.p, ctx().d_arrival_scores.p, narr * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+            CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+            CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+            ctx().stats.d2h_bytes += narr * sizeof( int32_t );
+            replay_topk( ctx().h_scores.p, order, narr, req.hitcount, hits );
         }
         else {
             // Large databases: only the first m arrivals and the later arrivals that beat the heap's root after those m can
             // touch the heap (replay.cpp: replay_topk_sparse) - 4 m bytes and a few hundred candidates cross PCIe instead of
             // 4 bytes per record of the WHOLE database on every rank, and the host looks at m records instead of all.
             const size_t m = sparse_replay_prefix( req.hitcount );
-            const uint32_t * d_order = order ? nullptr : ctx.d_order.p;   // arrival position -> provider index, where the host has no copy
-            CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, ctx.d_arrival_scores.p, m * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            if( d_order ) CUDA_OK( cudaMemcpyAsync( ctx.h_order.p, d_order, m * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-            CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );   // (recorded again behind the candidate fetch)
-            CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-            ctx.stats.d2h_bytes += m * sizeof( int32_t ) + ( d_order ? m * sizeof( uint32_t ) : 0 );
+            const uint32_t * d_order = order ? nullptr : ctx().d_order.p;   // arrival position -> provider index, where the host has no copy
+            CUDA_OK( cudaMemcpyAsync( ctx().h_scores.p, ctx().d_arrival_scores.p, m * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+            if( d_order ) CUDA_OK( cudaMemcpyAsync( ctx().h_order.p, d_order, m * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+            CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );   // (recorded again behind the candidate fetch)
+            CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+            ctx().stats.d2h_bytes += m * sizeof( int32_t ) + ( d_order ? m * sizeof( uint32_t ) : 0 );
             auto fetch = [&]( int32_t thr, const int32_t ** cand_scores, const uint32_t ** cand_ids ) -> size_t {
                 const size_t cap = narr - m;
-                ctx.d_cand_pos.reserve( cap + 1 );
-                ctx.d_cand_score.reserve( cap + 1 );
-                ctx.d_counter.reserve( 64 );
-                uint32_t * d_count = ctx.d_counter.p + 40;
-                CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx.stream ) );
-                compact_greater_kernel<<<(unsigned) ( ( cap + 255 ) / 256 ), 256, 0, ctx.stream>>>( ctx.d_arrival_scores.p, (uint32_t) m, (uint32_t) narr, thr,
-                        ctx.d_cand_pos.p, ctx.d_cand_score.p, d_count );
-                ctx.stats.launches++;
+                ctx().d_cand_pos.reserve( cap + 1 );
+                ctx().d_cand_score.reserve( cap + 1 );
+                ctx().d_counter.reserve( 64 );
+                uint32_t * d_count = ctx().d_counter.p + 40;
+                CUDA_OK( cudaMemsetAsync( d_count, 0, 4, ctx().stream ) );
+                compact_greater_kernel<<<(unsigned) ( ( cap + 255 ) / 256 ), 256, 0, ctx().stream>>>( ctx().d_arrival_scores.p, (uint32_t) m, (uint32_t) narr, thr,
+                        ctx().d_cand_pos.p, ctx().d_cand_score.p, d_count );
+                ctx().stats.launches++;
                 uint32_t count = 0;
-                CUDA_OK( cudaMemcpyAsync( &count, d_count, 4, cudaMemcpyDeviceToHost, ctx.stream ) );
-                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-                ctx.h_cand_pos.reserve( 2 * (size_t) count + 2 );   // [count] positions | [count] ids in arrival order
-                ctx.h_cand_score.reserve( 2 * (size_t) count + 2 ); // [count] scores as compacted | [count] in arrival order
-                ctx.h_cand_id.reserve( (size_t) count + 2 );
+                CUDA_OK( cudaMemcpyAsync( &count, d_count, 4, cudaMemcpyDeviceToHost, ctx().stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+                ctx().h_cand_pos.reserve( 2 * (size_t) count + 2 );   // [count] positions | [count] ids in arrival order
+                ctx().h_cand_score.reserve( 2 * (size_t) count + 2 ); // [count] scores as compacted | [count] in arrival order
+                ctx().h_cand_id.reserve( (size_t) count + 2 );
                 if( count > 0 ) {
-                    CUDA_OK( cudaMemcpyAsync( ctx.h_cand_pos.p, ctx.d_cand_pos.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-                    CUDA_OK( cudaMemcpyAsync( ctx.h_cand_score.p, ctx.d_cand_score.p, count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                    CUDA_OK( cudaMemcpyAsync( ctx().h_cand_pos.p, ctx().d_cand_pos.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+                    CUDA_OK( cudaMemcpyAsync( ctx().h_cand_score.p, ctx().d_cand_score.p, count * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
                     if( d_order ) {
-                        ctx.d_cand_id.reserve( count + 1 );
-                        gather_u32_kernel<<<( count + 255 ) / 256, 256, 0, ctx.stream>>>( d_order, ctx.d_cand_pos.p, count, ctx.d_cand_id.p );
-                        ctx.stats.launches++;
-                        CUDA_OK( cudaMemcpyAsync( ctx.h_cand_id.p, ctx.d_cand_id.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
+                        ctx().d_cand_id.reserve( count + 1 );
+                        gather_u32_kernel<<<( count + 255 ) / 256, 256, 0, ctx().stream>>>( d_order, ctx().d_cand_pos.p, count, ctx().d_cand_id.p );
+                        ctx().stats.launches++;
+                        CUDA_OK( cudaMemcpyAsync( ctx().h_cand_id.p, ctx().d_cand_id.p, count * sizeof( uint32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
                     }
                 }
-                CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-                CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-                ctx.stats.d2h_bytes += 4 + (size_t) count * ( d_order ? 12 : 8 );
+                CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+                CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+                ctx().stats.d2h_bytes += 4 + (size_t) count * ( d_order ? 12 : 8 );
                 // the compaction is unordered: back into arrival order
                 std::vector<uint32_t> perm( count );
                 std::iota( perm.begin(), perm.end(), 0u );
-                std::sort( perm.begin(), perm.end(), [&]( uint32_t x, uint32_t y ) { return ctx.h_cand_pos.p[x] < ctx.h_cand_pos.p[y]; } );
-                uint32_t * ids = ctx.h_cand_pos.p + count;
-                int32_t * sc = ctx.h_cand_score.p + count;
+                std::sort( perm.begin(), perm.end(), [&]( uint32_t x, uint32_t y ) { return ctx().h_cand_pos.p[x] < ctx().h_cand_pos.p[y]; } );
+                uint32_t * ids = ctx().h_cand_pos.p + count;
+                int32_t * sc = ctx().h_cand_score.p + count;
                 for( uint32_t j = 0; j < count; j++ ) {
                     const uint32_t src = perm[j];
-                    sc[j] = ctx.h_cand_score.p[src];
-                    ids[j] = d_order ? ctx.h_cand_id.p[src] : order[ctx.h_cand_pos.p[src]];
+                    sc[j] = ctx().h_cand_score.p[src];
+                    ids[j] = d_order ? ctx().h_cand_id.p[src] : order[ctx().h_cand_pos.p[src]];
                 }
                 *cand_scores = sc;
                 *cand_ids = ids;
                 return count;
             };
-            replay_topk_sparse( ctx.h_scores.p, order ? order : ctx.h_order.p, m, req.hitcount, fetch, hits );
+            replay_topk_sparse( ctx().h_scores.p, order ? order : ctx().h_order.p, m, req.hitcount, fetch, hits );
         }
     }
     else {
-        CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+        CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     }
 
     if( d_nw_counts ) {  // records of this shard the reference would have re-aligned (NW tiers)
         uint32_t c[2] = { 0, 0 };
         CUDA_OK( cudaMemcpy( c, d_nw_counts, 8, cudaMemcpyDeviceToHost ) );
-        if( req.bit_width == 8 ) ctx.stats.overflow_8 = c[0];
-        ctx.stats.overflow_16 = c[1];
+        if( req.bit_width == 8 ) ctx().stats.overflow_8 = c[0];
+        ctx().stats.overflow_16 = c[1];
     }
     for( uint32_t k = 0; k < n_flagged; k++ ) {  // valid after the synchronisation above
-        if( req.bit_width == 8 && ctx.h_first.p[k] != INT_MAX ) ctx.stats.overflow_8++;
-        if( ctx.h_first.p[n_flagged + k] != INT_MAX ) ctx.stats.overflow_16++;
+        if( req.bit_width == 8 && ctx().h_first.p[k] != INT_MAX ) ctx().stats.overflow_8++;
+        if( ctx().h_first.p[n_flagged + k] != INT_MAX ) ctx().stats.overflow_16++;
     }
 }
 
@@ -1743,10 +2081,10 @@ static void select_replay( const int32_t * d_all, const uint8_t * query, size_t 
 // GPU, the scores (and, for 8/16-bit entry, the overflow blocks) come back to the host, and the reference's chunk /
 // frame / overflow-list schedule is replayed there (replay.cpp: general_search_order).
 static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh ) {
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t nloc = db.sorted_id.size();
     const size_t nglob = db.sorted_all.size();
-    const size_t world = (size_t) ctx.world;
+    const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;
     const size_t total = stride * world;
     const size_t nslots = db.lens_all.size();
@@ -1754,79 +2092,78 @@ static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh
     const int Q = (int) req.frames.size();
     const bool tiers = req.bit_width == 8 || req.bit_width == 16;
     std::vector<std::vector<int32_t>> scores( Q ), ovf8( Q ), ovf16( Q );
-    ctx.stats.cells = 0;
+    ctx().stats.cells = 0;
     for( int q = 0; q < Q; q++ ) {
         const QueryFrame & f = req.frames[q];
         scores[q].assign( nslots, 0 );
-        ctx.stats.cells += (uint64_t) f.len * db.local_residues;
+        ctx().stats.cells += (uint64_t) f.len * process_residues();
         if( nglob == 0 ) continue;
-        ctx.d_scores.reserve( stride + 2 );
-        score_shard( f.seq, f.len, nw );
-        int32_t * d_all = ctx.d_scores.p;
-        if( world > 1 ) {
-            ctx.d_gathered.reserve( total + 2 );
-            gather_i32( ctx.d_scores.p, ctx.d_gathered.p, stride );
-            d_all = ctx.d_gathered.p;
-        }
-        ctx.h_scores.reserve( total + 1 );
-        CUDA_OK( cudaMemcpyAsync( ctx.h_scores.p, d_all, total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        ctx.stats.d2h_bytes += total * sizeof( int32_t );
-        for( size_t g = 0; g < nglob; g++ ) scores[q][db.sorted_all[g]] = ctx.h_scores.p[( g % world ) * stride + g / world];
+        const int32_t * d_all = score_query( f.seq, f.len, nw );
+        ctx().h_scores.reserve( total + 1 );
+        CUDA_OK( cudaMemcpyAsync( ctx().h_scores.p, d_all, total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+        ctx().stats.d2h_bytes += total * sizeof( int32_t );
+        for( size_t g = 0; g < nglob; g++ ) scores[q][db.sorted_all[g]] = ctx().h_scores.p[( g % world ) * stride + g / world];
         if( !tiers ) continue;
 
-        bool have = false;
-        ctx.d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
-        int32_t * d_f = ctx.d_first.p;  // [stride] 8-bit tier | [stride] 16-bit tier: first overflowing column
+        bool have = false;   // d_first of every context: [stride] 8-bit tier | [stride] 16-bit tier, first overflowing column
         if( !nw ) {  // SW: score >= 255 / 65535 (src/algo/simd/search_simd_sw.c:372-379)
             const int32_t thr = req.bit_width == 8 ? 255 : 65535;
             for( size_t g = 0; g < nglob && !have; g++ ) have = scores[q][db.sorted_all[g]] >= thr;
             if( have ) {
-                std::vector<uint32_t> slots;
-                for( size_t sl = 0; sl < nloc; sl++ )
-                    if( ctx.h_scores.p[(size_t) ctx.rank * stride + sl] >= thr ) slots.push_back( (uint32_t) sl );
-                launch_fill( d_f, INT_MAX, 2 * stride );
-                Plan pl = make_plan( f.len );
-                run_wide( slots, f.seq, f.len, pl, false, true, d_f, d_f + stride, 1, ctx.stream );
+                const Plan pl = make_plan( f.len );
+                const int32_t * h_all = ctx().h_scores.p;   // the gathered scores, on the host
+                run_on_all( [&]() {
+                    std::vector<uint32_t> slots;
+                    const size_t nl = ctx().db.sorted_id.size();
+                    for( size_t sl = 0; sl < nl; sl++ )
+                        if( h_all[(size_t) ctx().rank * stride + sl] >= thr ) slots.push_back( (uint32_t) sl );
+                    ctx().d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+                    int32_t * d_fl = ctx().d_first.p;
+                    launch_fill( d_fl, INT_MAX, 2 * stride );
+                    run_wide( slots, f.seq, f.len, pl, false, true, d_fl, d_fl + stride, 1, ctx().stream );
+                    if( world > 1 ) gather_i32( d_fl, ctx().d_first.p + 2 * stride, 2 * stride );
+                } );
             }
         }
         else {  // NW: the saturating tiers, only for the entries static bounds cannot clear (nw_sat.cuh)
-            const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( f.len, 8 ) ) : 0;
-            const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( f.len, 16 ) );
             const int64_t longest = (int64_t) db.lens_all[db.sorted_all[0]];
             have = ( req.bit_width == 8 && longest > nw_tier_safe_len( f.len, 8 ) ) || longest > nw_tier_safe_len( f.len, 16 );
             if( have ) {
-                launch_fill( d_f, INT_MAX, 2 * stride );
-                if( n8 ) run_nw_sat( f.seq, f.len, 8, n8, d_f );
-                if( n16 ) run_nw_sat( f.seq, f.len, 16, n16, d_f + stride );
+                run_on_all( [&]() {
+                    const size_t n8 = req.bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( f.len, 8 ) ) : 0;
+                    const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( f.len, 16 ) );
+                    ctx().d_first.reserve( 2 * stride * ( world + 1 ) + 4 );
+                    int32_t * d_fl = ctx().d_first.p;
+                    launch_fill( d_fl, INT_MAX, 2 * stride );
+                    if( n8 ) run_nw_sat( f.seq, f.len, 8, n8, d_fl );
+                    if( n16 ) run_nw_sat( f.seq, f.len, 16, n16, d_fl + stride );
+                    if( world > 1 ) gather_i32( d_fl, ctx().d_first.p + 2 * stride, 2 * stride );
+                } );
             }
         }
         if( !have ) continue;
-        int32_t * d_f_all = d_f;
-        if( world > 1 ) {
-            d_f_all = ctx.d_first.p + 2 * stride;
-            gather_i32( d_f, d_f_all, 2 * stride );
-        }
-        ctx.h_first.reserve( 2 * total + 2 );
-        CUDA_OK( cudaMemcpyAsync( ctx.h_first.p, d_f_all, 2 * total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx.stream ) );
-        CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-        ctx.stats.d2h_bytes += 2 * total * sizeof( int32_t );
+        const int32_t * d_f_all = world > 1 ? ctx().d_first.p + 2 * stride : ctx().d_first.p;
+        ctx().h_first.reserve( 2 * total + 2 );
+        CUDA_OK( cudaMemcpyAsync( ctx().h_first.p, d_f_all, 2 * total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
+        CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+        ctx().stats.d2h_bytes += 2 * total * sizeof( int32_t );
         ovf8[q].assign( nslots, -1 );
         ovf16[q].assign( nslots, -1 );
         for( size_t g = 0; g < nglob; g++ ) {
             const size_t r = g % world, sl = g / world;
-            const int32_t c8 = ctx.h_first.p[r * 2 * stride + sl], c16 = ctx.h_first.p[r * 2 * stride + stride + sl];
+            const int32_t c8 = ctx().h_first.p[r * 2 * stride + sl], c16 = ctx().h_first.p[r * 2 * stride + stride + sl];
             if( req.bit_width == 8 && c8 != INT_MAX ) ovf8[q][db.sorted_all[g]] = c8 / 4;
             if( c16 != INT_MAX ) ovf16[q][db.sorted_all[g]] = c16 / 4;
         }
     }
-    CUDA_OK( cudaEventRecord( ctx.ev_end, ctx.stream ) );
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_end, ctx().stream ) );
+    CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     size_t n8 = 0, n16 = 0;
     general_search_order( db.lens_all, g_chunk_size * (size_t) db.buffer_max, req.bit_width, Q, db.buffer_max, scores, ovf8, ovf16,
             req.hitcount, fh, &n8, &n16 );
-    ctx.stats.overflow_8 = n8;
-    ctx.stats.overflow_16 = n16;
+    ctx().stats.overflow_8 = n8;
+    ctx().stats.overflow_16 = n16;
 }
 // ---- result records: reference src/algo/aligner.c:62-93 ----
 // The reference rebuilds the database side from the record with us_prepare_sequence( seq, len, frame, strand )
@@ -1834,7 +2171,7 @@ static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh
 // record of a one-strand search is translated from the complementary strand whichever strand was scored.  The
 // alignment is computed on that sequence; reproduced as is.
 static void finish_results( const SearchRequest & req, const std::vector<FrameHit> & fh, std::vector<HitAlignment> & out, cudaStream_t tb_stream ) {
-    const uint32_t bm = (uint32_t) ctx.db.buffer_max;
+    const uint32_t bm = (uint32_t) ctx().db.buffer_max;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
     const signed char * map = ( g_symtype == NUCLEOTIDE || translate_db ) ? map_ncbi_nt16 : map_ncbi_aa;
@@ -1869,7 +2206,7 @@ static void finish_results( const SearchRequest & req, const std::vector<FrameHi
     }
     if( req.align_type == COMPUTE_ALIGNMENT && !out.empty() ) {
         if( req.frames.size() == 1 ) {
-            traceback_hits( tb_stream, req.frames[0].seq, req.frames[0].len, nw, out, &ctx.stats, scored_sequence );
+            traceback_hits( tb_stream, req.frames[0].seq, req.frames[0].len, nw, out, &ctx().stats, scored_sequence );
         }
         else {
             for( size_t q = 0; q < req.frames.size(); q++ ) {
@@ -1881,29 +2218,21 @@ static void finish_results( const SearchRequest & req, const std::vector<FrameHi
                         group.push_back( std::move( out[i] ) );
                     }
                 if( group.empty() ) continue;
-                traceback_hits( tb_stream, req.frames[q].seq, req.frames[q].len, nw, group, &ctx.stats, scored_sequence );
+                traceback_hits( tb_stream, req.frames[q].seq, req.frames[q].len, nw, group, &ctx().stats, scored_sequence );
                 for( size_t j = 0; j < where.size(); j++ ) out[where[j]] = std::move( group[j] );
             }
         }
     }
 }
 
-static void reset_call_stats() {
-    ctx.stats.launches = 0;
-    ctx.stats.h2d_bytes = ctx.stats.d2h_bytes = 0;
-    ctx.stats.wide_tier_seqs = 0;
-    ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
-}
-
 void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     const double t_call = wall_ms();
     build_db();
-    PackedDb & db = ctx.db;
-    const size_t nloc = db.sorted_id.size();
+    PackedDb & db = ctx().db;
     const uint32_t bm = (uint32_t) db.buffer_max;
     out.clear();
     reset_call_stats();
-    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_begin, ctx().stream ) );
 
     std::vector<FrameHit> fh;
     bool done = false;
@@ -1921,20 +2250,17 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
     }
     if( !done ) search_frames( req, fh );
 
-    if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )  // reference src/algo/manager.c:157-160
+    if( ctx().stats.overflow_8 || ctx().stats.overflow_16 )  // reference src/algo/manager.c:157-160
         print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
-                (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
+                (long) ctx().stats.overflow_8, (long) ctx().stats.overflow_16 );
 
-    finish_results( req, fh, out, ctx.stream );
+    finish_results( req, fh, out, ctx().stream );
 
+    merge_call_stats();
     float ms = 0;
-    if( nloc ) {
-        cudaEventElapsedTime( &ms, ctx.ev_k0, ctx.ev_k1 );
-        ctx.stats.score_kernel_ms = ms;
-    }
-    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
-    ctx.stats.device_ms = ms;
-    ctx.stats.call_ms = wall_ms() - t_call;
+    cudaEventElapsedTime( &ms, ctx().ev_begin, ctx().ev_end );
+    ctx().stats.device_ms = ms;
+    ctx().stats.call_ms = wall_ms() - t_call;
 }
 
 // A batch of independent queries with the same search parameters: the results are those of one
@@ -1946,7 +2272,7 @@ void gpu_search( const SearchRequest & req, std::vector<HitAlignment> & out ) {
 void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std::vector<HitAlignment>> & outs ) {
     const double t_call = wall_ms();
     build_db();
-    PackedDb & db = ctx.db;
+    PackedDb & db = ctx().db;
     const size_t n = reqs.size();
     outs.assign( n, std::vector<HitAlignment>() );
     bool pipelined = db.buffer_max == 1 && n > 1;
@@ -1957,7 +2283,7 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
     }
     reset_call_stats();
     const size_t nglob = db.sorted_all.size();
-    const size_t world = (size_t) ctx.world;
+    const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;
     uint64_t cells = 0;
     bool armed[2] = { false, false };
@@ -1965,66 +2291,115 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
     auto enqueue = [&]( size_t i ) {
         const SearchRequest & r = reqs[i];
         const int slot = (int) ( i & 1 );
-        ctx.ss = slot;
+        g_stage_slot = slot;
         const bool nw = r.search_type == NEEDLEMAN_WUNSCH;
         const int32_t * d_all = score_query( r.frames[0].seq, r.frames[0].len, nw );
         // the replay path of this query, should it be needed, runs after the next query's scoring has overwritten d_all
-        ctx.d_all_slot[slot].reserve( stride * world + 2 );
-        if( nglob ) CUDA_OK( cudaMemcpyAsync( ctx.d_all_slot[slot].p, d_all, stride * world * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx.stream ) );
+        ctx().d_all_slot[slot].reserve( stride * world + 2 );
+        if( nglob ) CUDA_OK( cudaMemcpyAsync( ctx().d_all_slot[slot].p, d_all, stride * world * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx().stream ) );
         PackedDb::Arrival & base = arrival_for( r.bit_width, chunk, chunk <= (size_t) ARRIVAL_MAX_CHUNK );
         armed[slot] = topk_applicable( base, r.hitcount );
         if( armed[slot] ) enqueue_topk( d_all, base, r.hitcount, !nw && ( r.bit_width == 8 || r.bit_width == 16 ), slot );
     };
-    CUDA_OK( cudaEventRecord( ctx.ev_begin, ctx.stream ) );
+    CUDA_OK( cudaEventRecord( ctx().ev_begin, ctx().stream ) );
     enqueue( 0 );
     for( size_t i = 0; i < n; i++ ) {
         if( i + 1 < n ) enqueue( i + 1 );
         const SearchRequest & r = reqs[i];
         const int slot = (int) ( i & 1 );
         std::vector<Hit> hits;
-        ctx.stats.overflow_8 = ctx.stats.overflow_16 = 0;
+        ctx().stats.overflow_8 = ctx().stats.overflow_16 = 0;
         if( !( armed[slot] && collect_topk( r.hitcount, r.bit_width, slot, hits ) ) ) {
             // ties straddle the cut-off (or the hit count covers the database): the arrival-order replay, from this query's
             // own copy of the scores; it queues behind the next query's scoring
-            ctx.ss = slot;
-            select_replay( ctx.d_all_slot[slot].p, r.frames[0].seq, r.frames[0].len, r, hits );
+            g_stage_slot = slot;
+            select_replay( ctx().d_all_slot[slot].p, r.frames[0].seq, r.frames[0].len, r, hits );
         }
-        if( ctx.stats.overflow_8 || ctx.stats.overflow_16 )
+        if( ctx().stats.overflow_8 || ctx().stats.overflow_16 )
             print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
-                    (long) ctx.stats.overflow_8, (long) ctx.stats.overflow_16 );
-        cells += (uint64_t) r.frames[0].len * db.local_residues;
+                    (long) ctx().stats.overflow_8, (long) ctx().stats.overflow_16 );
+        cells += (uint64_t) r.frames[0].len * process_residues();
         std::vector<FrameHit> fh( hits.size() );
         for( size_t j = 0; j < hits.size(); j++ ) fh[j] = FrameHit{ (uint32_t) hits[j].db_id, 0, hits[j].score };
-        finish_results( r, fh, outs[i], ctx.stream_aux );
+        finish_results( r, fh, outs[i], ctx().stream_aux );
     }
-    CUDA_OK( cudaStreamSynchronize( ctx.stream ) );
-    ctx.ss = 0;
+    CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
+    g_stage_slot = 0;
+    merge_call_stats();
     float ms = 0;
-    cudaEventElapsedTime( &ms, ctx.ev_begin, ctx.ev_end );
-    ctx.stats.device_ms = ms;
-    ctx.stats.score_kernel_ms = 0;
-    ctx.stats.cells = cells;
-    ctx.stats.call_ms = wall_ms() - t_call;
+    cudaEventElapsedTime( &ms, ctx().ev_begin, ctx().ev_end );
+    ctx().stats.device_ms = ms;
+    ctx().stats.score_kernel_ms = 0;
+    ctx().stats.cells = cells;
+    ctx().stats.call_ms = wall_ms() - t_call;
 }
 
 // ---- additive API (include/libssa_b200.h) ----
 extern "C" {
 __attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_device( int device ) {
-    if( ctx.init && ctx.device != device ) gpu_release();
-    ctx.device = device;
+    if( !g_devs.empty() && ( g_devs.size() > 1 || g_devs[0]->device != device ) ) gpu_release();
+    g_cfg.device = device;
+}
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_device_count( int n ) {
+    if( n < 1 ) fatal( "libssa_b200: invalid device count %d", n );
+    if( !g_devs.empty() && (int) g_devs.size() != n ) gpu_release();
+    g_cfg.ndev = n;
+}
+__attribute__( ( visibility( "default" ) ) ) int ssa_b200_get_device_count( void ) {
+    ensure_ctx();
+    return (int) g_devs.size();
 }
 __attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_shard( int rank, int world_size ) {
     if( world_size < 1 || rank < 0 || rank >= world_size ) fatal( "libssa_b200: invalid shard %d of %d", rank, world_size );
-    ctx.rank = rank;
-    ctx.world = world_size;
+    if( g_devs.size() > 1 && world_size > 1 )
+        fatal( "libssa_b200: this process already drives %d GPUs; sharding over processes as well is not supported.", (int) g_devs.size() );
+    g_cfg.rank = rank;
+    g_cfg.world = world_size;
+    if( g_devs.size() == 1 ) {   // takes effect at the next search (the shard is rebuilt)
+        g_devs[0]->rank = rank;
+        g_devs[0]->world = world_size;
+    }
 }
 __attribute__( ( visibility( "default" ) ) ) void ssa_b200_set_allgather( ssa_b200_allgather_fn fn, void * c ) {
-    ctx.allgather = fn;
-    ctx.allgather_ctx = c;
+    g_cfg.allgather = fn;
+    g_cfg.allgather_ctx = c;
+}
+// ---- the collective inside the library, one process per GPU: rank 0 creates the NCCL id, the host program carries its
+// 128 bytes to the other ranks (any channel: MPI, a file, torch.distributed), every rank joins ----
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_nccl_unique_id( void * out_128_bytes ) {
+    load_nccl();
+    static_assert( sizeof( ncclUniqueId ) == 128, "ncclUniqueId is 128 bytes" );
+    ncclUniqueId id;
+    NCCL_OK( g_nccl.GetUniqueId( &id ) );
+    memcpy( out_128_bytes, &id, sizeof( id ) );
+}
+__attribute__( ( visibility( "default" ) ) ) void ssa_b200_nccl_init( const void * id_128_bytes, int rank, int world_size ) {
+    if( world_size < 1 || rank < 0 || rank >= world_size ) fatal( "libssa_b200: invalid rank %d of %d", rank, world_size );
+    g_cfg.rank = rank;
+    g_cfg.world = world_size;
+    ensure_ctx();
+    if( g_devs.size() > 1 ) fatal( "libssa_b200: ssa_b200_nccl_init is for one GPU per process." );
+    Ctx & c = *g_devs[0];
+    c.rank = rank;
+    c.world = world_size;
+    if( c.comm ) {
+        g_nccl.CommDestroy( c.comm );
+        c.comm = nullptr;
+    }
+    if( world_size == 1 ) return;
+    load_nccl();
+    ncclUniqueId id;
+    memcpy( &id, id_128_bytes, sizeof( id ) );
+    CUDA_OK( cudaSetDevice( c.device ) );
+    NCCL_OK( g_nccl.CommInitRank( &c.comm, world_size, id, rank ) );
 }
 __attribute__( ( visibility( "default" ) ) ) void ssa_b200_prepare_db( void ) { build_db(); }
 __attribute__( ( visibility( "default" ) ) ) void ssa_b200_get_stats( ssa_b200_stats_t * out ) {
-    if( out ) *out = ctx.stats;
+    if( !out ) return;
+    if( g_devs.empty() )
+        memset( out, 0, sizeof( *out ) );
+    else
+        *out = g_devs[0]->stats;
 }
 __attribute__( ( visibility( "default" ) ) ) int ssa_b200_version( void ) { return 100; }
 // host-only: the packed tier's passes for a query of qlen rows (see plan_passes)

@@ -1,9 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) as the collective.
-
-The C library shards the database itself (ssa_b200_set_shard) and needs exactly one collective per search:
-an all-gather of each rank's shard scores (4 bytes per local record).  It calls back into the function
-registered here with raw device pointers and its CUDA stream; we wrap the pointers as torch tensors
-(zero copy, __cuda_array_interface__) and issue dist.all_gather_into_tensor on that stream.
+"""Multi-GPU plumbing, one process per GPU (torchrun): the C library shards the database itself and merges the shard
+scores itself - ncclAllGather on its own CUDA stream, on a communicator it creates inside the library
+(ssa_b200_nccl_unique_id / ssa_b200_nccl_init, include/libssa_b200.h).  The only thing the host has to do is carry rank 0's
+128-byte NCCL id to the other ranks; here torch.distributed does that (and provides the barrier / reductions bench.py
+needs).  `collective="torch"` keeps the older route for hosts that bring their own collective: the library calls back
+into dist.all_gather_into_tensor with raw device pointers and its stream (ssa_b200_set_allgather).
 """
 import os
 
@@ -30,20 +30,31 @@ def make_torch_allgather(device):
     return allgather
 
 
-def init_from_env(lib, backend="nccl"):
-    """Reads RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* (torchrun), initialises torch.distributed and shards `lib`."""
+def init_from_env(lib, backend="nccl", collective=None):
+    """Reads RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* (torchrun), initialises torch.distributed and shards `lib`.
+    collective: "nccl" (default; $LIBSSA_B200_COLLECTIVE overrides) = the library's own NCCL communicator,
+    "torch" = callback into torch.distributed."""
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    collective = collective or os.environ.get("LIBSSA_B200_COLLECTIVE", "nccl")
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         torch.cuda.set_device(local)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
     lib.set_device(local)
-    lib.set_shard(rank, world)
-    if world > 1:
-        lib.set_allgather(make_torch_allgather(torch.device("cuda", local)))
+    if world > 1 and collective == "nccl":
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            ident = torch.tensor(list(lib.nccl_unique_id()), dtype=torch.uint8)
+        ident = ident.to(torch.device("cuda", local))
+        dist.broadcast(ident, 0)
+        lib.nccl_init(bytes(ident.cpu().tolist()), rank, world)
+    else:
+        lib.set_shard(rank, world)
+        if world > 1:
+            lib.set_allgather(make_torch_allgather(torch.device("cuda", local)))
     return rank, world, local
