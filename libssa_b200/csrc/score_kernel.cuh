@@ -40,7 +40,11 @@ namespace ssa {
 constexpr uint32_t COL_FIRST = 1u << 10;   // first column of a sequence pair
 constexpr uint32_t COL_LAST_B = 1u << 11;  // last real column of sequence B (low half)
 constexpr uint32_t COL_LAST_A = 1u << 12;  // last column of sequence A = last column of the pair
-constexpr uint32_t COL_VALID = 1u << 15;   // real column (padding columns of odd-length pairs are 0)
+constexpr uint32_t COL_VALID = 1u << 15;   // column to process (words beyond a batch read as 0)
+constexpr uint32_t PAD_RESIDUE = 31;       // residue code of the padding column that makes every pair an even number of columns:
+                                           // no alphabet uses it, its profile rows hold a non-positive score, so a packed
+                                           // Smith-Waterman step never needs a one-column path (the column can only repeat
+                                           // values that exist already; the next pair's first column resets the lane)
 
 constexpr int SCORE_THREADS = 256;
 
@@ -58,6 +62,7 @@ struct ScoreArgs {
     const Batch * batches;
     uint32_t nbatches;
     uint32_t * counter;        // work queue head
+    const uint32_t * nbatches_dev;   // if set: the number of batches is read from device memory (work lists built on the device)
     const uint32_t * profile;  // this pass' query profile, laid out for shared memory
     uint32_t group;            // lanes per systolic array: 4, 8, 16 or 32
     uint32_t k65536;           // the constant 65536 (see the profile merge in score_kernel)
@@ -161,8 +166,13 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     // F chains are independent, which doubles the instruction-level parallelism of the otherwise serial row loop,
     // and the per-step work (shuffles, flags, loads) is shared by 2R cells.  Sequence pairs are padded to an even
     // number of columns in the stream, so a sequence always starts in column A.
+    // PACKED Smith-Waterman has no one-column path: pairs are padded with a harmless column (PAD_RESIDUE)
+    constexpr bool HAS_SLOW = !PACKED || NW;
+    // passes of a long query on full-warp arrays: the group IS the warp, known at compile time
+    constexpr bool FULLWARP = MULTI == 1;
     const int lane = threadIdx.x & 31;
-    const int G = (int) a.group;
+    const int G = FULLWARP ? 32 : (int) a.group;
+    const uint32_t nbatches = a.nbatches_dev ? *a.nbatches_dev : a.nbatches;
     const int gmask = G - 1;
     const int gl = lane & gmask;                                   // lane within the group
     const unsigned group_mask = ( G == 32 ? FULL : ( ( 1u << G ) - 1u ) << ( lane & ~gmask ) );
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     const T QR = (T) a.qr_word;   // gapO + gapE, replicated per half for the packed tier
     const T RG = (T) a.rg_word;   // gapE
     const int row0 = a.rowbase + gl * R;
-    const bool gen_top = is_top && ( a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
+    const bool gen_top = is_top && ( MULTI == 0 || a.rowbase == 0 );  // this lane synthesises the matrix' top boundary
 
     T Hp[R], E[R];   // H of the last processed column / E entering the next column, per row of this lane
 #pragma unroll
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             uint32_t b = 0xffffffffu;
             if( is_top && !done ) b = atomicAdd( a.counter, 1u );
             b = __shfl_sync( group_mask, b, 0, G );
-            if( b >= a.nbatches ) {
+            if( b >= nbatches ) {
                 done = true;
                 nsteps_cols = 0;
                 nsteps = 0x7fffffff;
@@ -342,8 +352,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 }
             }
             t = 0;
+            if( FULLWARP && done ) break;   // warp-uniform: one group per warp, the exit test is off the per-step path
         }
-        if( __all_sync( FULL, done ) ) break;   // also the point where the groups of a warp reconverge every step
+        if( !FULLWARP && __all_sync( FULL, done ) ) break;   // also the point where the groups of a warp reconverge every step
 
         // Every lane reads the column words of ITS column pair (t - gl) straight from the stream, two steps ahead
         // of use: the G lanes of a group touch G consecutive 32-bit words, all groups run the same instructions.
@@ -453,7 +464,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             }
 
             const bool b_valid = ( cib & COL_VALID ) != 0;
-            const bool slow = !PACKED || !b_valid || ( NW && ( cia & ( COL_LAST_A | COL_LAST_B ) ) );
+            const bool slow = HAS_SLOW && ( !PACKED || !b_valid || ( NW && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) );
             if( slow ) {
                 // column by column: the wide tier, the padded last column of an odd-length pair, and NW results
                 // that must be read between the two columns

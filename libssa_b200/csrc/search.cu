@@ -585,7 +585,8 @@ size_t build_shard() {
                 if( c + 1 == la ) v |= COL_LAST_A;
                 out[c] = (uint16_t) v;
             }
-            if( la & 1 ) out[la] = 0;  // padding column of an odd-length pair: not VALID
+            // padding column of an odd-length pair: a processed column of PAD_RESIDUE in both halves (score_kernel.cuh)
+            if( la & 1 ) out[la] = (uint16_t) ( PAD_RESIDUE | ( PAD_RESIDUE << 5 ) | COL_VALID );
         }
         unknown_per_chunk[p0 / 1024] = unknown;
     } );
@@ -895,7 +896,9 @@ void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G,
     for( int d = 0; d < 32; d++ )
         for( int lane = 0; lane < 32; lane++ ) {
             const size_t row0 = rowbase + (size_t) ( lane % G ) * R;
-            auto score = [&]( int r ) { return row0 + r < qlen ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pad_score; };
+            auto score = [&]( int r ) {
+                return row0 + r < qlen && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pad_score;
+            };
             for( int r = 0; r < MR; r++ )
                 out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = (uint32_t) (uint16_t) (int16_t) score( r );
             for( int r = MR; r < R; r += 2 ) {
@@ -912,7 +915,7 @@ void fill_profile_wide( uint32_t * out, const uint8_t * q, size_t qlen, const Pl
         for( int d = 0; d < 32; d++ )
             for( int lane = 0; lane < 32; lane++ ) {
                 size_t row = ( (size_t) pass * G + (size_t) ( lane % G ) ) * R + r;
-                int v = row < qlen ? (int) g_matrix.m[( d << 5 ) + q[row]] : pl.pad_score;
+                int v = row < qlen && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q[row]] : pl.pad_score;
                 out[( r * 32 + d ) * 32 + lane] = (uint32_t) v;
             }
 }

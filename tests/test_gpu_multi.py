@@ -75,5 +75,6 @@ def test_unchanged_c_host_uses_all_gpus_through_the_environment(prod, tmp_path):
         r = subprocess.run([os.path.join(ROOT, "examples", "search_example"), db, qf, "sw", "8", "25", "align"],
                            capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr[-3000:]
-        outs.append([l for l in r.stdout.split("\n") if l and not l.startswith("libssa")])
+        # (with NCCL_DEBUG=VERSION in the environment NCCL prints its banner on stdout)
+        outs.append([l for l in r.stdout.split("\n") if l and not l.startswith("libssa") and not l.startswith("NCCL version")])
     assert outs[0] == outs[1] and len(outs[0]) == 25
