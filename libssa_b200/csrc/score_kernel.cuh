@@ -76,14 +76,14 @@ struct ScoreArgs {
     int32_t cap_lane;          // NW: lane / row-in-lane holding query row qlen-1, -1 if not in this pass
     int32_t cap_row;
     uint32_t first_pass;       // SW: 1 = store, 0 = max-combine with the previous passes
-    void * out;                // PACKED: uint32 (A:B) per pair; WIDE: int32 per slot
+    void * out;                // PACKED: uint32 (A:B), indexed by the stream column pair in which the pair of sequences ends
+                               // (bnd0 of a packed batch = its first stream column); WIDE: int32 per slot
     int32_t * first8;          // TRACK: first column reaching thr8 / thr16, per slot (atomicMin)
     int32_t * first16;
     int32_t thr8, thr16;
-    const uint32_t * bnd_h_in;  // boundary row from the previous pass (nullptr in pass 0)
-    const uint32_t * bnd_f_in;
-    uint32_t * bnd_h_out;       // boundary row for the next pass (nullptr in the last pass)
-    uint32_t * bnd_f_out;
+    const uint4 * bnd_in;       // boundary row from the previous pass (nullptr in pass 0): one entry per column pair,
+                                // { H column A, H column B, F column A, F column B } of the pass' last query row
+    uint4 * bnd_out;            // boundary row for the next pass (nullptr in the last pass)
     int32_t * guard;            // PACKED NW: largest diagonal candidate seen (both halves), for the host's range check
 };
 
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     // MULTI, full-warp groups: the previous pass' boundary row (H and F of two columns per step) is fetched by the
     // whole warp, 32 steps at a time and one block of 32 ahead - lane l holds the entry of step 32*blk + l - and reaches
     // the top lane through an indexed shuffle: no divergent code, no global latency on the step's path.
-    uint2 bh_cur = make_uint2( 0, 0 ), bf_cur = make_uint2( 0, 0 ), bh_nxt = make_uint2( 0, 0 ), bf_nxt = make_uint2( 0, 0 );
+    uint4 b_cur = make_uint4( 0, 0, 0, 0 ), b_nxt = make_uint4( 0, 0, 0, 0 );
 
     // one database column through this lane's R rows (used where the two-column loop does not apply)
     auto single_column = [&]( const uint32_t ci, const T h_in, const T f_in, T & h_last, T & f_last ) {
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             }
             if( PACKED ) {
                 if( ci & COL_LAST_B ) cap_b = sel;
-                if( ci & COL_LAST_A ) ( (uint32_t *) a.out )[out_idx++] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
+                if( ci & COL_LAST_A ) ( (uint32_t *) a.out )[bnd_base + (uint32_t) ( t - gl )] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
             }
             else {
                 if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
@@ -324,30 +324,18 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 nsteps = nsteps_cols + gmask;
                 out_idx = (int) bt.out0;
                 half = bt.half;
-                if( MULTI ) bnd_base = (uint32_t) ( bt.bnd0 >> 1 );
+                bnd_base = (uint32_t) ( bt.bnd0 >> 1 );
                 // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
                 w_n1 = ( gl == 0 ) ? st[0] : 0;
                 w_n2 = ( 1 - gl >= 0 && 1 - gl < nsteps_cols ) ? st[1 - gl] : 0;
-                if( MULTI == 1 && a.bnd_h_in ) {
-                    if( lane < nsteps_cols ) {
-                        bh_cur = ( (const uint2 *) a.bnd_h_in )[bnd_base + lane];
-                        bf_cur = ( (const uint2 *) a.bnd_f_in )[bnd_base + lane];
-                    }
-                    if( 32 + lane < nsteps_cols ) {
-                        bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + 32 + lane];
-                        bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + 32 + lane];
-                    }
+                if( MULTI == 1 && a.bnd_in ) {
+                    if( lane < nsteps_cols ) b_cur = a.bnd_in[bnd_base + lane];
+                    if( 32 + lane < nsteps_cols ) b_nxt = a.bnd_in[bnd_base + 32 + lane];
                 }
-                if( MULTI == 2 && a.bnd_h_in ) {
+                if( MULTI == 2 && a.bnd_in ) {
                     if( is_top ) {  // narrow groups (remainder pass): the top lane fetches its own entries, two steps ahead
-                        if( 0 < nsteps_cols ) {
-                            bh_cur = ( (const uint2 *) a.bnd_h_in )[bnd_base];
-                            bf_cur = ( (const uint2 *) a.bnd_f_in )[bnd_base];
-                        }
-                        if( 1 < nsteps_cols ) {
-                            bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + 1];
-                            bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + 1];
-                        }
+                        if( 0 < nsteps_cols ) b_cur = a.bnd_in[bnd_base];
+                        if( 1 < nsteps_cols ) b_nxt = a.bnd_in[bnd_base + 1];
                     }
                 }
             }
@@ -400,34 +388,26 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 }
             }
         }
-        if( MULTI == 2 && a.bnd_h_in ) {
+        if( MULTI == 2 && a.bnd_in ) {
             // Narrow groups: every group has its own batch and step counter, so the top lane of each group reads the
             // boundary entries of ITS column pair t itself (prefetched two steps ahead).  Only the remainder pass of a
             // long query runs this way (a few per cent of the work), the full passes use the warp-wide fetch below.
             if( is_top ) {
-                ha_in = (T) bh_cur.x;
-                hb_in = (T) bh_cur.y;
-                fa_in = (T) bf_cur.x;
-                fb_in = (T) bf_cur.y;
-                bh_cur = bh_nxt;
-                bf_cur = bf_nxt;
-                if( t + 2 < nsteps_cols ) {
-                    bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 2];
-                    bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 2];
-                }
+                ha_in = (T) b_cur.x;
+                hb_in = (T) b_cur.y;
+                fa_in = (T) b_cur.z;
+                fb_in = (T) b_cur.w;
+                b_cur = b_nxt;
+                if( t + 2 < nsteps_cols ) b_nxt = a.bnd_in[bnd_base + t + 2];
             }
         }
-        if( MULTI == 1 && a.bnd_h_in ) {  // warp-uniform (G = 32): t is the column pair of the top lane
+        if( MULTI == 1 && a.bnd_in ) {  // warp-uniform (G = 32): t is the column pair of the top lane
             if( ( t & 31 ) == 0 && t > 0 ) {
-                bh_cur = bh_nxt;
-                bf_cur = bf_nxt;
-                if( t + 32 + lane < nsteps_cols ) {
-                    bh_nxt = ( (const uint2 *) a.bnd_h_in )[bnd_base + t + 32 + lane];
-                    bf_nxt = ( (const uint2 *) a.bnd_f_in )[bnd_base + t + 32 + lane];
-                }
+                b_cur = b_nxt;
+                if( t + 32 + lane < nsteps_cols ) b_nxt = a.bnd_in[bnd_base + t + 32 + lane];
             }
-            const uint32_t bha = __shfl_sync( FULL, bh_cur.x, t & 31 ), bhb = __shfl_sync( FULL, bh_cur.y, t & 31 );
-            const uint32_t bfa = __shfl_sync( FULL, bf_cur.x, t & 31 ), bfb = __shfl_sync( FULL, bf_cur.y, t & 31 );
+            const uint32_t bha = __shfl_sync( FULL, b_cur.x, t & 31 ), bhb = __shfl_sync( FULL, b_cur.y, t & 31 );
+            const uint32_t bfa = __shfl_sync( FULL, b_cur.z, t & 31 ), bfb = __shfl_sync( FULL, b_cur.w, t & 31 );
             if( is_top ) {
                 ha_in = (T) bha;
                 hb_in = (T) bhb;
@@ -562,7 +542,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     }
                     if( is_bottom ) {
                         if( PACKED ) {
-                            uint32_t * o = (uint32_t *) a.out + out_idx++;
+                            uint32_t * o = (uint32_t *) a.out + ( bnd_base + (uint32_t) ( t - gmask ) );
                             *o = a.first_pass ? (uint32_t) s_out : __vmaxs2( *o, (uint32_t) s_out );
                         }
                         else {
@@ -576,10 +556,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     }
                 }
             }
-            if( MULTI && is_bottom && a.bnd_h_out ) {  // this lane's last row becomes the next pass' top boundary
-                ( (uint2 *) a.bnd_h_out )[bnd_base + t - gmask] = make_uint2( (uint32_t) ha_last, (uint32_t) hb_last );
-                ( (uint2 *) a.bnd_f_out )[bnd_base + t - gmask] = make_uint2( (uint32_t) fa_last, (uint32_t) fb_last );
-            }
+            if( MULTI && is_bottom && a.bnd_out )   // this lane's last row becomes the next pass' top boundary
+                a.bnd_out[bnd_base + t - gmask] = make_uint4( (uint32_t) ha_last, (uint32_t) hb_last, (uint32_t) fa_last, (uint32_t) fb_last );
         }
         ha_out = ha_last;
         fa_out = fa_last;

@@ -166,6 +166,9 @@ struct Ctx {
     DevBuf<uint32_t> d_cand_pos, d_cand_id;
     DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
+    DevBuf<uint32_t> d_spec_list;         // speculative packed tier: sequences listed for the 32-bit tier
+    PinBuf<uint32_t> h_spec_count[2];
+    bool spec_pending[2] = { false, false };
     ssa_b200_stats_t stats;
     bool scored = false;                  // score_shard launched kernels in the current call (ev_k0 / ev_k1 are valid)
 };
@@ -750,14 +753,55 @@ PackedDb::BatchTable & batch_table( uint32_t cols, uint32_t first_pair = 0, uint
 // small device kernels around the scoring kernels
 // ------------------------------------------------------------------------------------------------
 
-// (A:B) int16 pairs -> one int32 score per sorted position
-__global__ void unpack_scores_kernel( const uint32_t * packed, int32_t * scores, uint32_t pair0, uint32_t npairs, uint32_t nseq,
-        int32_t offset ) {
+// (A:B) int16 pairs, stored by stream position -> one int32 score per sorted position.  Speculative packed tier (Smith-Waterman): the pairs below
+// `spec_pairs` are not provably inside int16; a sequence whose running maximum came within one substitution score of the
+// int16 limit (>= spec_thr) may have wrapped and is listed for the exact 32-bit tier - the reference's own scheme of
+// "run narrow, detect, recompute" (reference src/algo/simd/search_simd_sw.c:372-379,422-423).
+__global__ void unpack_scores_kernel( const uint32_t * packed, const uint64_t * pair_col, int32_t * scores, uint32_t pair0, uint32_t npairs,
+        uint32_t nseq, int32_t offset, uint32_t spec_pairs, int32_t spec_thr, uint32_t * spec_list, uint32_t * spec_count ) {
     uint32_t p = pair0 + blockIdx.x * blockDim.x + threadIdx.x;
     if( p >= npairs ) return;
-    uint32_t w = packed[p];
-    scores[2 * p] = (int32_t) (int16_t) ( w >> 16 ) + offset;
-    if( 2 * p + 1 < nseq ) scores[2 * p + 1] = (int32_t) (int16_t) ( w & 0xffffu ) + offset;
+    uint32_t w = packed[pair_col[p + 1] / 2 - 1];   // the kernels store a pair's result at the column pair in which it ends
+    const int32_t sa = (int32_t) (int16_t) ( w >> 16 ), sb = (int32_t) (int16_t) ( w & 0xffffu );
+    scores[2 * p] = sa + offset;
+    if( 2 * p + 1 < nseq ) scores[2 * p + 1] = sb + offset;
+    if( p < spec_pairs ) {
+        if( sa >= spec_thr ) spec_list[atomicAdd( spec_count, 1u )] = 2 * p;
+        if( 2 * p + 1 < nseq && sb >= spec_thr ) spec_list[atomicAdd( spec_count, 1u )] = 2 * p + 1;
+    }
+}
+
+// work batches of the 32-bit tier for the sequences the speculative packed tier listed (at most `cap`, a host-side bound)
+__global__ void build_spec_batches_kernel( const uint32_t * list, const uint32_t * count, uint32_t cap, const uint64_t * pair_col,
+        const uint32_t * sorted_len, Batch * batches, uint32_t * nbatches ) {
+    if( blockIdx.x != 0 || threadIdx.x != 0 ) return;
+    const uint32_t n = min( *count, cap );
+    uint64_t bnd = 0;
+    for( uint32_t i = 0; i < n; i++ ) {
+        const uint32_t s = list[i];
+        Batch b;
+        b.col0 = pair_col[s / 2];
+        b.bnd0 = bnd;
+        b.ncols = ( sorted_len[s] + 1u ) & ~1u;
+        b.out0 = s;
+        b.half = s & 1u;
+        b.pad = 0;
+        bnd += b.ncols;
+        batches[i] = b;
+    }
+    *nbatches = n;
+}
+
+// wide-tier query profile (layout of fill_profile_wide) built on the device: [pass][row][residue][lane]
+__global__ void fill_profile_wide_kernel( const uint8_t * query, uint32_t qlen, const int32_t * matrix, int G, int R, int npass,
+        int32_t pad_score, uint32_t * out ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t words = (uint32_t) R * 1024u;
+    if( i >= words * (uint32_t) npass ) return;
+    const uint32_t pass = i / words, w = i % words;
+    const uint32_t lane = w & 31u, d = ( w >> 5 ) & 31u, r = w >> 10;
+    const uint32_t row = ( pass * (uint32_t) G + ( lane % (uint32_t) G ) ) * (uint32_t) R + r;
+    out[i] = (uint32_t) ( row < qlen && d != PAD_RESIDUE ? matrix[( d << 5 ) + query[row]] : pad_score );
 }
 
 // scores by (rank, local sorted position) -> scores by heap-arrival position.  `gathered` holds `world` blocks of
@@ -1008,7 +1052,7 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     ctx().d_profile_wide[slot].reserve( words * npass );
     CUDA_OK( cudaMemcpyAsync( ctx().d_profile_wide[slot].p, ctx().h_profile_wide[g_stage_slot][slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
     ctx().stats.h2d_bytes += words * npass * 4;
-    if( npass > 1 ) ctx().d_bnd_wide.reserve( 4 * bnd + 256 );
+    if( npass > 1 ) ctx().d_bnd_wide.reserve( 4 * bnd + 256 );   // 2 buffers x ( bnd / 2 + 1 ) entries x 4 words
     ctx().d_counter.reserve( 64 );
     for( int p = 0; p < npass; p++ ) {
         CUDA_OK( cudaMemsetAsync( ( ctx().d_counter.p + 16 + 8 * slot ), 0, 4, stream ) );
@@ -1040,18 +1084,83 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
         a.first16 = d_first16;
         a.thr8 = 255;
         a.thr16 = 65535;
-        if( npass > 1 ) {
-            uint32_t * base = ctx().d_bnd_wide.p;
-            uint32_t * h0 = base, * f0 = base + bnd, * h1 = base + 2 * bnd, * f1 = base + 3 * bnd;
-            a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
-            a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
-            a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
-            a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
+        if( npass > 1 ) {   // two buffers of one 16-byte entry per column pair, written and read alternately
+            uint4 * b0 = (uint4 *) ctx().d_bnd_wide.p, * b1 = b0 + ( bnd / 2 + 1 );
+            a.bnd_in = p > 0 ? ( ( p & 1 ) ? b0 : b1 ) : nullptr;
+            a.bnd_out = p + 1 < npass ? ( ( p & 1 ) ? b1 : b0 ) : nullptr;
         }
         launch_score_wide( R, nw, npass > 1, track, a, stream );
         ctx().stats.launches++;
     }
     ctx().stats.wide_tier_seqs += n;
+}
+
+void upload_matrix32() {
+    if( ctx().matrix32_version == g_matrix.version ) return;
+    int32_t m32[1024];
+    for( int i = 0; i < 1024; i++ ) m32[i] = (int32_t) g_matrix.m[i];
+    ctx().d_matrix32.reserve( 1024 );
+    CUDA_OK( cudaMemcpy( ctx().d_matrix32.p, m32, sizeof( m32 ), cudaMemcpyHostToDevice ) );
+    ctx().matrix32_version = g_matrix.version;
+}
+
+// The 32-bit tier over the sequences the speculative packed tier listed on the DEVICE (unpack_scores_kernel): batches,
+// profile and batch count never visit the host, so the common case - nothing listed - costs a few empty launches and no
+// synchronisation.  `cap` = sequences that can be listed at all (those the static bound does not clear), cap_cols their
+// stream columns.
+void run_wide_spec( const uint8_t * q, size_t qlen, const Plan & pl, uint32_t cap, uint64_t cap_cols, cudaStream_t stream ) {
+    PackedDb & db = ctx().db;
+    const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
+    const size_t words = (size_t) R * 1024;
+    upload_matrix32();
+    ctx().d_query.reserve( qlen + 1 );
+    CUDA_OK( cudaMemcpyAsync( ctx().d_query.p, q, qlen, cudaMemcpyHostToDevice, stream ) );
+    ctx().stats.h2d_bytes += qlen;
+    ctx().d_profile_wide[0].reserve( words * npass );
+    fill_profile_wide_kernel<<<(unsigned) ( ( words * npass + 255 ) / 256 ), 256, 0, stream>>>( ctx().d_query.p, (uint32_t) qlen,
+            ctx().d_matrix32.p, G, R, npass, pl.pad_score, ctx().d_profile_wide[0].p );
+    ctx().d_wide_batches[0].reserve( cap );
+    uint32_t * d_nb = ctx().d_counter.p + 48;
+    build_spec_batches_kernel<<<1, 32, 0, stream>>>( ctx().d_spec_list.p, ctx().d_counter.p + 44, cap, db.d_pair_col.p, db.d_sorted_len.p,
+            ctx().d_wide_batches[0].p, d_nb );
+    ctx().stats.launches += 2;
+    if( npass > 1 ) ctx().d_bnd_wide.reserve( 4 * cap_cols + 256 );
+    for( int p = 0; p < npass; p++ ) {
+        CUDA_OK( cudaMemsetAsync( ctx().d_counter.p + 16, 0, 4, stream ) );
+        ScoreArgs a;
+        memset( &a, 0, sizeof( a ) );
+        a.stream = db.d_stream.p;
+        a.batches = ctx().d_wide_batches[0].p;
+        a.nbatches = cap;               // sizes the grid; the kernel reads the real count
+        a.nbatches_dev = d_nb;
+        a.counter = ctx().d_counter.p + 16;
+        a.profile = ctx().d_profile_wide[0].p + p * words;
+        a.group = (uint32_t) G;
+        a.k65536 = 65536u;
+        a.qr_word = (uint32_t) ( (int) g_gapO + (int) g_gapE );
+        a.rg_word = (uint32_t) (int) g_gapE;
+        a.gap_open_extend = (int) g_gapO + (int) g_gapE;
+        a.gap_extend = g_gapE;
+        a.gap_open = g_gapO;
+        a.rowbase = p * G * R;
+        a.cap_lane = -1;
+        a.first_pass = ( p == 0 );
+        a.out = ctx().d_scores.p;
+        a.thr8 = 255;
+        a.thr16 = 65535;
+        if( npass > 1 ) {
+            uint4 * b0 = (uint4 *) ctx().d_bnd_wide.p, * b1 = b0 + ( cap_cols / 2 + 1 );
+            a.bnd_in = p > 0 ? ( ( p & 1 ) ? b0 : b1 ) : nullptr;
+            a.bnd_out = p + 1 < npass ? ( ( p & 1 ) ? b1 : b0 ) : nullptr;
+        }
+        launch_score_wide( R, false, npass > 1, false, a, stream );
+        ctx().stats.launches++;
+    }
+    // how many were recomputed: read back with the call's results (valid after the stream is synchronised)
+    ctx().h_spec_count[g_stage_slot].reserve( 1 );
+    CUDA_OK( cudaMemcpyAsync( ctx().h_spec_count[g_stage_slot].p, ctx().d_counter.p + 44, 4, cudaMemcpyDeviceToHost, stream ) );
+    ctx().spec_pending[g_stage_slot] = true;
+    ctx().stats.d2h_bytes += 4;
 }
 
 // One pass of the packed tier: G lanes x R rows from query row `rowbase` on, over its own list of work batches (the boundary
@@ -1062,6 +1171,12 @@ struct PassLaunch {
     const Batch * d_batches = nullptr;
     uint32_t nbatches = 0;
 };
+
+// LIBSSA_B200_NO_SW32=1: Smith-Waterman on full-warp arrays through the generic kernel as well (A/B measurements)
+bool sw32_enabled() {
+    static const bool on = getenv( "LIBSSA_B200_NO_SW32" ) == nullptr;
+    return on;
+}
 
 // The packed tier over one class of pairs: all passes of the query, one launch each.
 void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, const std::vector<PassLaunch> & passes,
@@ -1110,16 +1225,31 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         a.first_pass = ( p == 0 );
         a.out = ctx().d_out_packed.p;
         a.guard = nullptr;
-        if( npass > 1 ) {
-            uint32_t * base = ctx().d_bnd.p;
-            const uint64_t n = db.total_cols;
-            uint32_t * h0 = base, * f0 = base + n, * h1 = base + 2 * n, * f1 = base + 3 * n;
-            a.bnd_h_in = p > 0 ? ( ( p & 1 ) ? h0 : h1 ) : nullptr;
-            a.bnd_f_in = p > 0 ? ( ( p & 1 ) ? f0 : f1 ) : nullptr;
-            a.bnd_h_out = p + 1 < npass ? ( ( p & 1 ) ? h1 : h0 ) : nullptr;
-            a.bnd_f_out = p + 1 < npass ? ( ( p & 1 ) ? f1 : f0 ) : nullptr;
+        if( npass > 1 ) {   // two buffers of one 16-byte entry per stream column pair, written and read alternately
+            uint4 * b0 = (uint4 *) ctx().d_bnd.p, * b1 = b0 + ( db.total_cols / 2 + 1 );
+            a.bnd_in = p > 0 ? ( ( p & 1 ) ? b0 : b1 ) : nullptr;
+            a.bnd_out = p + 1 < npass ? ( ( p & 1 ) ? b1 : b0 ) : nullptr;
         }
-        launch_score_packed( ps.R, nw, multi, a, stream );
+        if( !nw && ps.G == 32 && sw32_enabled() ) {   // Smith-Waterman on full-warp arrays: the specialised kernel (sw32_kernel.cuh)
+            Sw32Args s32;
+            memset( &s32, 0, sizeof( s32 ) );
+            s32.stream32 = (const uint32_t *) db.d_stream.p;
+            s32.batches = a.batches;
+            s32.nbatches = a.nbatches;
+            s32.counter = a.counter;
+            s32.profile = a.profile;
+            s32.k65536 = a.k65536;
+            s32.qr_word = a.qr_word;
+            s32.rg_word = a.rg_word;
+            s32.first_pass = a.first_pass;
+            s32.out_by_col = ctx().d_out_packed.p;
+            s32.bnd_in = a.bnd_in;
+            s32.bnd_out = a.bnd_out;
+            launch_sw32( ps.R, multi, s32, stream );
+        }
+        else {
+            launch_score_packed( ps.R, nw, multi, a, stream );
+        }
         ctx().stats.launches++;
     }
 }
@@ -1212,8 +1342,18 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     int32_t offset = 0;
     const int qrows_max = std::max( pl.qpad, 32 * 32 * ( ( (int) qlen + 1023 ) / 1024 ) );
     int64_t safe = packed_safe_len( pl, nw, qrows_max, &offset );
-    if( (int) g_gapO + (int) g_gapE > 0 || g_gapE > 0 ) safe = 0;  // positive "penalties": only the wide tier is valid
-    const size_t p_safe = first_pair_not_longer( safe );
+    const bool positive_gaps = (int) g_gapO + (int) g_gapE > 0 || g_gapE > 0;
+    if( positive_gaps ) safe = 0;  // positive "penalties": only the wide tier is valid
+    const size_t p_static = first_pair_not_longer( safe );   // pairs [0, p_static) are not provably inside int16
+    // Speculative packed tier (Smith-Waterman): run those pairs in int16 all the same and recompute, in the 32-bit tier, only
+    // the sequences whose running maximum came within one substitution score of the limit.  A wrap needs a diagonal
+    // predecessor H > 32767 - hi+, every H is bounded by a diagonal candidate the running maximum has seen, and the maximum
+    // never decreases - so a final maximum below the threshold proves that nothing wrapped.  E and F stay above
+    // 2 (gapO + gapE).  (LIBSSA_B200_STATIC_TIERS=1: the static split, for A/B measurements.)
+    const int64_t hip = std::max<int64_t>( pl.hi, 0 );
+    const bool speculative = !nw && !positive_gaps && p_static > 0 && hip <= 1024 && pl.lo >= -1024 && !getenv( "LIBSSA_B200_STATIC_TIERS" );
+    const int32_t spec_thr = (int32_t) ( 32767 - hip );
+    const size_t p_safe = speculative ? 0 : p_static;
 
     // ---- shape of the packed tier ----
     // The bulk of the database runs on groups of G lanes x R rows (few padded rows, per-step work amortised over many
@@ -1252,12 +1392,16 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     }
 
     // batch size of the bulk class: at least ~3 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
-    const uint64_t groups = (uint64_t) sms * packed_blocks_per_sm( R, nw, npass > 1 ) * ( SCORE_THREADS / 32 ) * ( 32 / G );
-    uint32_t batch_cols = 4096;
+    // Smith-Waterman on full-warp arrays runs on sw32_kernel: its warps chain their batches (no wavefront fill per batch), so
+    // the batches can be small - at least ~8 per warp, down to 128 columns at the end of the queue
+    const bool chained = !nw && G == 32 && sw32_enabled();
+    const int resident = chained ? sw32_blocks_per_sm( R, npass > 1 ) : packed_blocks_per_sm( R, nw, npass > 1 );
+    const uint64_t groups = (uint64_t) sms * resident * ( SCORE_THREADS / 32 ) * ( 32 / G );
+    uint32_t batch_cols = chained ? 2048 : 4096;
     // (with the shrinking tail of batch_table the choice is flat between 2 and 12 batches per group [B200]; fewer, longer batches
     // mean fewer wavefront fills on small databases)
-    while( batch_cols > 256 && db.total_cols / batch_cols < 3 * groups ) batch_cols /= 2;
-    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, (uint32_t) std::max( 128, 16 * G ) );
+    while( batch_cols > 256 && db.total_cols / batch_cols < ( chained ? 8 : 3 ) * groups ) batch_cols /= 2;
+    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, chained ? 128u : (uint32_t) std::max( 128, 16 * G ) );
     const size_t b0 = std::lower_bound( bt.pair0.begin(), bt.pair0.end(), (uint32_t) p_long_end ) - bt.pair0.begin();
     const size_t bulk_pair0 = b0 < bt.batches.size() ? bt.pair0[b0] : db.npairs;   // bulk class = pairs [bulk_pair0, npairs)
     size_t long_pair0 = p_safe;                                                  // long class = pairs [long_pair0, bulk_pair0)
@@ -1267,7 +1411,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
 
     CUDA_OK( cudaEventRecord( ctx().ev_k0, ctx().stream ) );
     ctx().scored = true;
-    ctx().d_out_packed.reserve( db.npairs + 1 );
+    ctx().d_out_packed.reserve( db.total_cols / 2 + 64 );   // results by stream column pair (sparse: one word per pair of sequences)
     ctx().d_counter.reserve( 64 );
     // ---- auxiliary stream: the few sequences of the wide tier and the long class overlap the bulk launch ----
     const size_t n_long = bulk_pair0 - long_pair0;
@@ -1309,7 +1453,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
         std::vector<PassLaunch> passes;
         if( npass > 1 ) {
             passes = plan_passes( qlen, R, npass, db.total_cols - db.pair_col[bulk_pair0], db.sorted_len[2 * bulk_pair0], sms );
-            ctx().d_bnd.reserve( 4 * db.total_cols + 256 );
+            ctx().d_bnd.reserve( 4 * db.total_cols + 256 );   // 2 buffers x ( total_cols / 2 + 1 ) entries x 4 words
         }
         else {
             PassLaunch ps;
@@ -1324,10 +1468,13 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
                 continue;
             }
             // another shape has another number of resident groups: its own batches over the same pairs
-            const uint64_t ps_groups = (uint64_t) sms * packed_blocks_per_sm( ps.R, nw, true ) * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
-            uint32_t ps_cols = 4096;
-            while( ps_cols > 256 && db.total_cols / ps_cols < 6 * ps_groups ) ps_cols /= 2;
-            PackedDb::BatchTable & pt = batch_table( ps_cols, (uint32_t) bulk_pair0, (uint32_t) ps_groups, (uint32_t) std::max( 128, 16 * ps.G ) );
+            const bool ps_chained = !nw && ps.G == 32 && sw32_enabled();
+            const int ps_resident = ps_chained ? sw32_blocks_per_sm( ps.R, true ) : packed_blocks_per_sm( ps.R, nw, true );
+            const uint64_t ps_groups = (uint64_t) sms * ps_resident * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
+            uint32_t ps_cols = ps_chained ? 2048 : 4096;
+            while( ps_cols > 256 && db.total_cols / ps_cols < ( ps_chained ? 8 : 6 ) * ps_groups ) ps_cols /= 2;
+            PackedDb::BatchTable & pt = batch_table( ps_cols, (uint32_t) bulk_pair0, (uint32_t) ps_groups,
+                    ps_chained ? 128u : (uint32_t) std::max( 128, 16 * ps.G ) );
             ps.d_batches = pt.d_batches.p;
             ps.nbatches = (uint32_t) pt.batches.size();
         }
@@ -1336,9 +1483,20 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     if( use_aux ) CUDA_OK( cudaStreamWaitEvent( ctx().stream, ctx().ev_join, 0 ) );
     if( wide_pairs < db.npairs ) {
         const uint32_t np = (uint32_t) ( db.npairs - wide_pairs );
-        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx().stream>>>( ctx().d_out_packed.p, ctx().d_scores.p, (uint32_t) wide_pairs,
-                (uint32_t) db.npairs, (uint32_t) nloc, offset );
+        const uint32_t spec_cap = speculative ? (uint32_t) std::min( nloc, 2 * p_static ) : 0;
+        if( speculative ) {
+            ctx().d_spec_list.reserve( spec_cap + 2 );
+            CUDA_OK( cudaMemsetAsync( ctx().d_counter.p + 44, 0, 4, ctx().stream ) );
+        }
+        unpack_scores_kernel<<<( np + 255 ) / 256, 256, 0, ctx().stream>>>( ctx().d_out_packed.p, db.d_pair_col.p, ctx().d_scores.p, (uint32_t) wide_pairs,
+                (uint32_t) db.npairs, (uint32_t) nloc, offset, speculative ? (uint32_t) p_static : 0u, spec_thr, ctx().d_spec_list.p,
+                ctx().d_counter.p + 44 );
         ctx().stats.launches++;
+        if( speculative ) {
+            uint64_t cap_cols = 0;   // an upper bound for any spec_cap sequences: the longest ones
+            for( uint32_t i = 0; i < spec_cap; i++ ) cap_cols += ( (uint64_t) db.sorted_len[i] + 1 ) & ~1ull;
+            run_wide_spec( q, qlen, pl, spec_cap, cap_cols, ctx().stream );
+        }
     }
     CUDA_OK( cudaEventRecord( ctx().ev_k1, ctx().stream ) );
 }
@@ -1392,13 +1550,7 @@ size_t sorted_prefix_longer_than( int64_t len ) {
 void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t * d_first_col ) {
     PackedDb & db = ctx().db;
     if( count == 0 ) return;
-    if( ctx().matrix32_version != g_matrix.version ) {
-        int32_t m32[1024];
-        for( int i = 0; i < 1024; i++ ) m32[i] = (int32_t) g_matrix.m[i];
-        ctx().d_matrix32.reserve( 1024 );
-        CUDA_OK( cudaMemcpy( ctx().d_matrix32.p, m32, sizeof( m32 ), cudaMemcpyHostToDevice ) );
-        ctx().matrix32_version = g_matrix.version;
-    }
+    upload_matrix32();
     ctx().d_query.reserve( qlen + 1 );
     CUDA_OK( cudaMemcpyAsync( ctx().d_query.p, q, qlen, cudaMemcpyHostToDevice, ctx().stream ) );
     ctx().stats.h2d_bytes += qlen;
@@ -1593,6 +1745,10 @@ static void release_ctx( Ctx & c ) {
     c.d_cand_pos.release();
     c.d_cand_id.release();
     c.d_cand_score.release();
+    c.d_spec_list.release();
+    c.h_spec_count[0].release();
+    c.h_spec_count[1].release();
+    c.spec_pending[0] = c.spec_pending[1] = false;
     c.h_order.release();
     c.h_list.release();
     c.h_scores.release();
@@ -1677,6 +1833,11 @@ static void merge_call_stats() {
     ssa_b200_stats_t & st = g_devs[0]->stats;
     float kernel_ms = 0;
     for( Ctx * c : g_devs ) {
+        for( int slot = 0; slot < 2; slot++ )   // sequences the speculative packed tier sent to the 32-bit tier (copied back with the results)
+            if( c->spec_pending[slot] ) {
+                c->stats.wide_tier_seqs += *c->h_spec_count[slot].p;
+                c->spec_pending[slot] = false;
+            }
         if( c != g_devs[0] ) {
             st.launches += c->stats.launches;
             st.h2d_bytes += c->stats.h2d_bytes;
