@@ -462,7 +462,7 @@ def config4_record(lib, L, ref, sm_mhz, cores):
     return rec
 
 
-def run_ours(steps, warmup, n_gpus, per_config):
+def run_ours(steps, warmup, n_gpus, per_config, parity_checks=True):
     import torch
     import libssa_b200 as L
     from libssa_b200 import dist as ldist
@@ -512,10 +512,12 @@ def run_ours(steps, warmup, n_gpus, per_config):
 
     # ---- untimed parity checks: sharded == unsharded, and the compiled reference (one thread) on the full database ----
     parity = {}
+    if not parity_checks:
+        parity["skipped"] = "--no-parity"
     q0 = lib.init_sequence_fasta(L.READ_FROM_FILE, os.path.join(DATA, HEAD["queries"][0]))
     sharded = {(bw, k): keyed(lib.sw_align(q0, k, bw, L.COMPUTE_SCORE)) for bw in (8, 16) for k in (10, 100)}
     barrier()
-    if rank == 0:
+    if rank == 0 and parity_checks:
         if world > 1:
             lib.set_shard(0, 1)          # rank 0 alone re-searches the whole database on its GPU
             unsharded = {key: keyed(lib.sw_align(q0, key[1], key[0], L.COMPUTE_SCORE)) for key in sharded}
@@ -535,7 +537,7 @@ def run_ours(steps, warmup, n_gpus, per_config):
             ref = reference_api()
         except Exception as e:
             parity["reference_error"] = repr(e)
-        if ref is not None:
+        if ref is not None and parity_checks:
             ref.set_thread_count(1)
             setup_protein(ref, path)
             rq = ref.init_sequence_fasta(0, os.path.join(DATA, HEAD["queries"][0]))
@@ -652,11 +654,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-per-config", action="store_true", help="N = 1: skip the configs[1]/[2]/[4] sub-records")
+    ap.add_argument("--no-parity", action="store_true", help="development runs: skip the untimed parity checks")
     args = ap.parse_args()
     if args.impl == "reference":
         line = run_reference(args.steps, args.warmup, args.gpus)
     else:
-        line = run_ours(args.steps, max(args.warmup, 0), args.gpus, not args.no_per_config)
+        line = run_ours(args.steps, max(args.warmup, 0), args.gpus, not args.no_per_config, not args.no_parity)
     if line is not None:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -166,6 +166,7 @@ struct Ctx {
     DevBuf<uint32_t> d_cand_pos, d_cand_id;
     DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
+    DevBuf<uint32_t> d_pass_state;        // sw32_kernel, several passes per launch: [SW32_MAX_PASSES] queue heads | [nbatches] passes done
     DevBuf<uint32_t> d_spec_list;         // speculative packed tier: sequences listed for the 32-bit tier
     PinBuf<uint32_t> h_spec_count[2];
     bool spec_pending[2] = { false, false };
@@ -1199,6 +1200,50 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
     w0 = 0;
     for( int p = 0; p < npass; p++ ) {
         const PassLaunch & ps = passes[p];
+        if( !nw && ps.G == 32 && sw32_enabled() ) {
+            // Smith-Waterman on full-warp arrays: the specialised kernel (sw32_kernel.cuh).  Consecutive passes of one shape
+            // over the same batches - the full passes of a long query - are ONE launch: the kernel chains them itself, a batch
+            // of pass p+1 waits only for the same batch of pass p.  (LIBSSA_B200_PASS_PER_LAUNCH=1: one launch per pass.)
+            int run = 1;
+            static const bool per_launch = getenv( "LIBSSA_B200_PASS_PER_LAUNCH" ) != nullptr;
+            while( !per_launch && multi && p + run < npass && run < SW32_MAX_PASSES && passes[p + run].G == 32 && passes[p + run].R == ps.R &&
+                    passes[p + run].d_batches == ps.d_batches && passes[p + run].nbatches == ps.nbatches )
+                run++;
+            // work queue heads: one per pass of the launch (the class' own counter when there is only one)
+            uint32_t * counters = d_counter;
+            if( run > 1 ) {
+                ctx().d_pass_state.reserve( SW32_MAX_PASSES + ps.nbatches + 2 );
+                counters = ctx().d_pass_state.p;
+                CUDA_OK( cudaMemsetAsync( counters, 0, ( SW32_MAX_PASSES + (size_t) ps.nbatches ) * 4, stream ) );
+            }
+            else {
+                CUDA_OK( cudaMemsetAsync( d_counter, 0, 4, stream ) );
+            }
+            Sw32Args s32;
+            memset( &s32, 0, sizeof( s32 ) );
+            s32.stream32 = (const uint32_t *) db.d_stream.p;
+            s32.batches = ps.d_batches;
+            s32.nbatches = ps.nbatches;
+            s32.counters = counters;
+            s32.profile = d_profile + w0;
+            s32.k65536 = 65536u;
+            s32.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
+            s32.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
+            s32.npass = (uint32_t) run;
+            s32.pass0 = (uint32_t) p;
+            s32.more_passes = p + run < npass ? 1u : 0u;
+            s32.out_by_col = ctx().d_out_packed.p;
+            if( npass > 1 ) {
+                s32.bnd0 = (uint4 *) ctx().d_bnd.p;
+                s32.bnd1 = s32.bnd0 + ( db.total_cols / 2 + 1 );
+            }
+            s32.done = run > 1 ? counters + SW32_MAX_PASSES : nullptr;
+            launch_sw32( ps.R, multi, s32, stream );
+            ctx().stats.launches++;
+            w0 += (size_t) run * packed_profile_words( ps.R );
+            p += run - 1;
+            continue;
+        }
         CUDA_OK( cudaMemsetAsync( d_counter, 0, 4, stream ) );
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
@@ -1225,31 +1270,12 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         a.first_pass = ( p == 0 );
         a.out = ctx().d_out_packed.p;
         a.guard = nullptr;
-        if( npass > 1 ) {   // two buffers of one 16-byte entry per stream column pair, written and read alternately
+        if( npass > 1 ) {   // two buffers of one 16-byte entry per stream column pair: pass p reads [(p - 1) & 1], writes [p & 1]
             uint4 * b0 = (uint4 *) ctx().d_bnd.p, * b1 = b0 + ( db.total_cols / 2 + 1 );
             a.bnd_in = p > 0 ? ( ( p & 1 ) ? b0 : b1 ) : nullptr;
             a.bnd_out = p + 1 < npass ? ( ( p & 1 ) ? b1 : b0 ) : nullptr;
         }
-        if( !nw && ps.G == 32 && sw32_enabled() ) {   // Smith-Waterman on full-warp arrays: the specialised kernel (sw32_kernel.cuh)
-            Sw32Args s32;
-            memset( &s32, 0, sizeof( s32 ) );
-            s32.stream32 = (const uint32_t *) db.d_stream.p;
-            s32.batches = a.batches;
-            s32.nbatches = a.nbatches;
-            s32.counter = a.counter;
-            s32.profile = a.profile;
-            s32.k65536 = a.k65536;
-            s32.qr_word = a.qr_word;
-            s32.rg_word = a.rg_word;
-            s32.first_pass = a.first_pass;
-            s32.out_by_col = ctx().d_out_packed.p;
-            s32.bnd_in = a.bnd_in;
-            s32.bnd_out = a.bnd_out;
-            launch_sw32( ps.R, multi, s32, stream );
-        }
-        else {
-            launch_score_packed( ps.R, nw, multi, a, stream );
-        }
+        launch_score_packed( ps.R, nw, multi, a, stream );
         ctx().stats.launches++;
     }
 }
@@ -1746,6 +1772,7 @@ static void release_ctx( Ctx & c ) {
     c.d_cand_id.release();
     c.d_cand_score.release();
     c.d_spec_list.release();
+    c.d_pass_state.release();
     c.h_spec_count[0].release();
     c.h_spec_count[1].release();
     c.spec_pending[0] = c.spec_pending[1] = false;

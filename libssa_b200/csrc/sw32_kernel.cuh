@@ -14,7 +14,13 @@
 //     load with 64-bit address arithmetic, and four indexed shuffles + four selects out of eight live registers);
 //   * results are stored by stream position (the column pair in which a pair of sequences ends), boundary rows as one
 //     16-byte entry {H col A, H col B, F col A, F col B} per column pair, so no lane has to know which batch it is in;
-//   * there is no one-column path (pairs are padded with a PAD_RESIDUE column) and no per-step exit vote.
+//   * there is no one-column path (pairs are padded with a PAD_RESIDUE column) and no per-step exit vote;
+//   * ALL full passes of a long query run in ONE launch: a CTA works through the passes in order (its warps meet at a CTA
+//     barrier to swap the query profile in shared memory), every pass has its own work queue over the same batches, and a
+//     batch of pass p+1 starts as soon as the SAME batch of pass p is finished (a per-batch counter in global memory,
+//     release / acquire) - there is no grid-wide barrier between passes, so the idle tail of a pass (the longest pairs, the
+//     last small batches; 10-15 % of a pass on a 70 000-record shard) is filled with the next pass' work.  Waits only ever
+//     point to a lower pass of a batch some running warp has already claimed, so they cannot deadlock.
 #pragma once
 
 #include "score_kernel.cuh"
@@ -24,23 +30,26 @@ namespace ssa {
 constexpr int SW32_RING = 128;        // steps a warp's ring holds (power of two): 64 ahead of the top lane, 31 behind it, one block of slack
 constexpr int SW32_MIN_STEPS = 64;    // virtual length of a batch: a block of 32 steps crosses at most one batch boundary
 constexpr uint32_t SW32_IDLE = 0xffffffffu;
+constexpr int SW32_MAX_PASSES = 32;   // passes one launch can chain (counters live in one small array)
 
 struct Sw32Args {
     const uint32_t * stream32;   // the column stream, two 16-bit column words per element (one column pair = one step)
     const Batch * batches;       // whole pairs; col0 even
     uint32_t nbatches;
-    uint32_t * counter;          // work queue head
-    const uint32_t * profile;    // this pass' query profile (fill_profile_packed for G = 32)
+    uint32_t * counters;         // work queue heads, one per pass of this launch (zero at launch)
+    const uint32_t * profile;    // the query profiles of this launch's passes (fill_profile_packed for G = 32), one after the other
     uint32_t k65536;             // see score_kernel.cuh
     uint32_t qr_word, rg_word;   // gapO + gapE and gapE, replicated in both halves
-    uint32_t first_pass;         // 1 = store the result, 0 = max-combine with the previous passes
+    uint32_t npass;              // passes this launch runs (1 unless MULTIPASS)
+    uint32_t pass0;              // position of the first of them among the query's passes (pass 0 stores results, later ones max-combine)
+    uint32_t more_passes;        // 1 = the query has passes after this launch (the last pass here writes a boundary row too)
     uint32_t * out_by_col;       // (A:B) running maxima, indexed by the column pair in which the pair of sequences ends
-    const uint4 * bnd_in;        // boundary row of the previous pass per column pair (nullptr: first pass)
-    uint4 * bnd_out;             // boundary row for the next pass (nullptr: last pass)
+    uint4 * bnd0, * bnd1;        // MULTIPASS: boundary rows per column pair; an even pass reads bnd1 and writes bnd0, an odd pass the reverse
+    uint32_t * done;             // MULTIPASS, npass > 1: passes of this launch completed per batch (zero at launch)
 };
 
 // words of shared memory per warp for the ring: column words, stream positions, boundary entries
-template<bool MULTIPASS> __host__ __device__ constexpr int sw32_ring_words() { return 2 * SW32_RING + ( MULTIPASS ? 4 * SW32_RING : 0 ); }
+template<bool MULTIPASS> __host__ __device__ constexpr int sw32_ring_words() { return 2 * SW32_RING + ( MULTIPASS ? 5 * SW32_RING : 0 ); }
 template<int R, bool MULTIPASS> __host__ __device__ constexpr int sw32_smem_bytes() {
     return ( profile_words<true, R>() + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>() ) * 4;
 }
@@ -54,6 +63,14 @@ __device__ __forceinline__ void cp_async16( uint32_t smem_addr, const void * gme
 __device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;" ::: "memory" ); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile( "cp.async.wait_group %0;" ::"n"( N ) : "memory" ); }
 __device__ __forceinline__ void sts32( uint32_t addr, uint32_t v ) { asm volatile( "st.shared.u32 [%0], %1;" ::"r"( addr ), "r"( v ) : "memory" ); }
+__device__ __forceinline__ uint32_t ld_acquire( const uint32_t * p ) {
+    uint32_t v;
+    asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
+    return v;
+}
+__device__ __forceinline__ void st_release( uint32_t * p, uint32_t v ) {
+    asm volatile( "st.release.gpu.global.u32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
+}
 __device__ __forceinline__ void sts128( uint32_t addr, uint4 v ) {
     asm volatile( "st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"( addr ), "r"( v.x ), "r"( v.y ), "r"( v.z ), "r"( v.w ) : "memory" );
 }
@@ -68,18 +85,17 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     constexpr int NQ16 = ( R - MR ) / 4;
     extern __shared__ uint32_t smem[];
 
-    for( int i = threadIdx.x; i < PW; i += blockDim.x ) smem[i] = a.profile[i];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {   // every ring slot idle: lanes below the top one start on steps "before the launch"
         uint32_t * ring = smem + PW + warp * sw32_ring_words<MULTIPASS>();
         for( int i = lane; i < sw32_ring_words<MULTIPASS>(); i += 32 ) ring[i] = 0;
     }
-    __syncthreads();
 
     const uint32_t smem_base = (uint32_t) __cvta_generic_to_shared( smem );
     const uint32_t ring_w = smem_base + ( PW + warp * sw32_ring_words<MULTIPASS>() ) * 4;   // [RING] column words of the step
     const uint32_t ring_g = ring_w + SW32_RING * 4;                                          // [RING] column pair index in the stream
     const uint32_t ring_b = ring_g + SW32_RING * 4;                                          // [RING] boundary entry (MULTIPASS)
+    const uint32_t ring_e = ring_b + SW32_RING * 16;                                         // [RING] batch + 1 on its last step (MULTIPASS)
     const uint32_t prof_base = smem_base + lane * 16;            // 128-bit entries of the first MR rows
     const uint32_t prof_base16 = smem_base + MR * 4096 + lane * 8;   // 64-bit entries of the other rows
     const uint32_t K65536 = a.k65536;
@@ -98,29 +114,41 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     // ---- the warp's batches on its virtual step axis (warp-uniform) ----
     // cur / nxt: the two batches the staging front can touch.  A batch of n column pairs occupies max( n, SW32_MIN_STEPS )
     // virtual steps; steps past its columns, and everything after the queue ran dry, are idle.
-    uint32_t cur_s = 0, cur_e = 0, cur_n = 0, cur_g = 0;      // virtual begin / end, column pairs, first column pair in the stream
-    uint32_t nxt_e = 0, nxt_n = 0, nxt_g = 0;                 // (begins at cur_e)
+    uint32_t cur_s = 0, cur_e = 0, cur_n = 0, cur_g = 0, cur_b = 0;   // virtual begin / end, column pairs, first column pair in the stream, batch
+    uint32_t nxt_e = 0, nxt_n = 0, nxt_g = 0, nxt_b = 0;              // (begins at cur_e)
     uint32_t last_real_e = 0;                                 // virtual end of the last real batch
-    bool dry = false;                                         // the work queue is exhausted
+    bool dry = false;                                         // the work queue of the current pass is exhausted
+    uint32_t pp = 0;                                          // pass of this launch the CTA works on
+    uint32_t * counter = a.counters;
+    const uint4 * bnd_in = nullptr;
+    uint4 * bnd_out = nullptr;
+    bool first_pass = true, publish = false;
 
-    auto fetch = [&]( uint32_t begin, uint32_t & e, uint32_t & n, uint32_t & g ) {
+    auto fetch = [&]( uint32_t begin, uint32_t & e, uint32_t & n, uint32_t & g, uint32_t & bidx ) {
         uint32_t b = 0xffffffffu;
         if( !dry ) {
-            if( is_top ) b = atomicAdd( a.counter, 1u );
+            if( is_top ) b = atomicAdd( counter, 1u );
             b = __shfl_sync( FULL, b, 0 );
         }
         if( b >= a.nbatches ) {
             dry = true;
             n = 0;
             g = 0;
+            bidx = 0;
             e = begin + SW32_MIN_STEPS;
         }
         else {
             const Batch bt = a.batches[b];
             n = bt.ncols >> 1;
             g = (uint32_t) ( bt.col0 >> 1 );
+            bidx = b;
             e = begin + max( n, (uint32_t) SW32_MIN_STEPS );
             last_real_e = e;
+            if( MULTIPASS && pp > 0 ) {   // the previous pass of this launch must have finished this batch (its boundary row, its result)
+                if( is_top )
+                    while( ld_acquire( a.done + b ) < pp ) __nanosleep( 200 );
+                __syncwarp();
+            }
         }
     };
 
@@ -128,26 +156,29 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     auto stage = [&]( const uint32_t v0 ) {
         const uint32_t v = v0 + lane;
         const uint32_t slot = v & ( SW32_RING - 1 );
-        uint32_t c, n, g;
+        uint32_t c, n, g, bidx;
         if( v < cur_e ) {
             c = v - cur_s;
             n = cur_n;
             g = cur_g;
+            bidx = cur_b;
         }
         else {
             c = v - cur_e;
             n = nxt_n;
             g = nxt_g;
+            bidx = nxt_b;
         }
         if( c < n ) {
             const uint32_t pos = g + c;
             cp_async4( ring_w + slot * 4, a.stream32 + pos );
             sts32( ring_g + slot * 4, pos );
             if( MULTIPASS ) {
-                if( a.bnd_in )
-                    cp_async16( ring_b + slot * 16, a.bnd_in + pos );
+                if( bnd_in )
+                    cp_async16( ring_b + slot * 16, bnd_in + pos );
                 else
                     sts128( ring_b + slot * 16, make_uint4( 0, 0, 0, 0 ) );
+                sts32( ring_e + slot * 4, c + 1 == n ? bidx + 1 : 0 );
             }
         }
         else {
@@ -160,16 +191,37 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             cur_e = nxt_e;
             cur_n = nxt_n;
             cur_g = nxt_g;
-            fetch( cur_e, nxt_e, nxt_n, nxt_g );
+            cur_b = nxt_b;
+            fetch( cur_e, nxt_e, nxt_n, nxt_g, nxt_b );
         }
     };
 
-    fetch( 0, cur_e, cur_n, cur_g );
-    fetch( cur_e, nxt_e, nxt_n, nxt_g );
-    stage( 0 );
-    stage( 32 );
+    uint32_t t0 = 0;
+  for( pp = 0; pp < a.npass; pp++ ) {
+    // ---- the CTA moves to the next pass: every warp has drained its chain, the profile in shared memory is swapped ----
+    if( pp > 0 ) __syncthreads();
+    {
+        const uint32_t * src = a.profile + (size_t) pp * PW;
+        for( int i = threadIdx.x; i < PW; i += blockDim.x ) smem[i] = src[i];
+    }
+    __syncthreads();
+    {
+        const uint32_t abs_pass = a.pass0 + pp;
+        first_pass = abs_pass == 0;
+        bnd_in = MULTIPASS && abs_pass > 0 ? ( ( abs_pass & 1 ) ? a.bnd0 : a.bnd1 ) : nullptr;
+        bnd_out = MULTIPASS && ( pp + 1 < a.npass || a.more_passes ) ? ( ( abs_pass & 1 ) ? a.bnd1 : a.bnd0 ) : nullptr;
+        publish = MULTIPASS && pp + 1 < a.npass;
+        counter = a.counters + pp;
+    }
+    // the virtual axis simply continues: the steps already staged beyond t0 are idle ones and are staged again
+    dry = false;
+    cur_s = t0;
+    fetch( t0, cur_e, cur_n, cur_g, cur_b );
+    fetch( cur_e, nxt_e, nxt_n, nxt_g, nxt_b );
+    stage( t0 );
+    stage( t0 + 32 );
 
-    for( uint32_t t0 = 0;; t0 += 32 ) {
+    for( ;; t0 += 32 ) {
         stage( t0 + 64 );
         cp_async_wait<2>();     // everything but the two youngest blocks has landed: block t0 is complete
         __syncwarp();
@@ -272,13 +324,21 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 // ---- the pair ends in this step: the running maximum travels down the lanes with the wavefront ----
                 if( ( cia | cib ) & COL_LAST_A ) {
                     s_out = A::max2( s_in, S );
-                    if( is_bottom ) {
+                    if( is_bottom ) {   // (the earlier pass may have run on another SM: read around L1)
                         uint32_t * o = a.out_by_col + lds32( ring_g + slot4 );
-                        *o = a.first_pass ? s_out : __vmaxs2( *o, s_out );
+                        *o = first_pass ? s_out : __vmaxs2( __ldcg( o ), s_out );
                     }
                 }
-                if( MULTIPASS && is_bottom && a.bnd_out )   // this lane's last row is the next pass' top boundary
-                    a.bnd_out[lds32( ring_g + slot4 )] = make_uint4( ha_last, hb_last, fa_last, fb_last );
+                if( MULTIPASS && is_bottom && bnd_out ) {   // this lane's last row is the next pass' top boundary
+                    bnd_out[lds32( ring_g + slot4 )] = make_uint4( ha_last, hb_last, fa_last, fb_last );
+                    if( publish ) {   // last step of a batch: the same batch of the next pass may start
+                        const uint32_t e = lds32( ring_e + slot4 );
+                        if( e ) {
+                            __threadfence();
+                            st_release( a.done + ( e - 1 ), pp + 1 );
+                        }
+                    }
+                }
             }
             ha_out = ha_last;
             fa_out = fa_last;
@@ -286,6 +346,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             fb_out = fb_last;
         }
     }
+  }
     cp_async_wait<0>();
 }
 
