@@ -84,7 +84,6 @@ struct ScoreArgs {
     const uint4 * bnd_in;       // boundary row from the previous pass (nullptr in pass 0): one entry per column pair,
                                 // { H column A, H column B, F column A, F column B } of the pass' last query row
     uint4 * bnd_out;            // boundary row for the next pass (nullptr in the last pass)
-    int32_t * guard;            // PACKED NW: largest diagonal candidate seen (both halves), for the host's range check
 };
 
 template<bool PACKED> struct Arith;
@@ -197,14 +196,13 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         Hp[r] = A::bcast( 0 );
         E[r] = A::bcast( 0 );
     }
-    T S = A::bcast( NW ? -32768 : 0 );  // SW: running maximum of this lane's rows; NW: range guard
+    T S = A::bcast( 0 );                // SW: running maximum of this lane's rows
     T diag = A::bcast( 0 );             // H of (row0-1, last processed column)
     T top_h = A::bcast( 0 ), top_f = A::bcast( 0 );
     T ha_out = A::bcast( 0 ), fa_out = A::bcast( 0 ), hb_out = A::bcast( 0 ), fb_out = A::bcast( 0 ), s_out = A::bcast( 0 );
     T cap_b = A::bcast( 0 );            // NW PACKED: score of sequence B, kept until the pair ends
     int jcol = 0;                       // TRACK: column index within the sequence
     int f8 = 0x7fffffff, f16 = 0x7fffffff, f8_out = 0x7fffffff, f16_out = 0x7fffffff;
-    int guard_max = -0x7fffffff;
 
     // current work batch of this group
     const uint32_t * st = (const uint32_t *) a.stream;   // two 16-bit column words per element
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 hq = A::add( Hp[2 * k + 1], QR );
                 E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
                 f = A::addmax( f, RG, hq );
-                S = A::max3( S, t0, t1 );
+                if( !NW ) S = A::max3( S, t0, t1 );
             };
 #pragma unroll
             for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
@@ -444,10 +442,11 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             }
 
             const bool b_valid = ( cib & COL_VALID ) != 0;
-            const bool slow = HAS_SLOW && ( !PACKED || !b_valid || ( NW && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) );
+            const bool slow = HAS_SLOW && ( !PACKED || !b_valid || ( NW && gl == a.cap_lane && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) );
             if( slow ) {
-                // column by column: the wide tier, the padded last column of an odd-length pair, and NW results
-                // that must be read between the two columns
+                // column by column: the wide tier, and NW results that must be read between the two columns - only in the
+                // lane that owns the query's last row (a sequence end in column A makes ONE lane of the group leave the
+                // two-column path for one step; the other lanes compute the same cells two columns at a time)
                 single_column( cia, ha_in, fa_in, ha_last, fa_last );
                 if( NW ) nw_capture( cia );
                 if( b_valid ) {
@@ -499,10 +498,12 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     // The running maximum is taken over the diagonal candidates t = Hdiag + V instead of over H:
                     // with non-positive gap costs E and F never exceed an earlier H, so max(H) = max(0, t).  Giving
                     // t a second consumer also keeps ptxas from fusing the add into a VIADDMNMX, i.e. it stays a
-                    // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW uses the same accumulator
-                    // as an upper range guard.
-                    S = A::max3( S, ta0, ta1 );
-                    S = A::max3( S, tb0, tb1 );
+                    // VIADD.16x2 on the FMA-side pipe and off the (binding) ALU pipe.  NW needs no maximum: the packed tier
+                    // only runs pairs whose value range is statically inside int16 (packed_safe_len).
+                    if( !NW ) {
+                        S = A::max3( S, ta0, ta1 );
+                        S = A::max3( S, tb0, tb1 );
+                    }
                 };
                 // one shared load per sequence and column fetches the scores of four query rows
 #pragma unroll
@@ -564,13 +565,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         hb_out = hb_last;
         fb_out = fb_last;
 
-        if( NW && PACKED && t == nsteps - 1 ) {
-            const int hi = (int) (int16_t) ( (uint32_t) S >> 16 ), lo = (int) (int16_t) ( (uint32_t) S & 0xffffu );
-            guard_max = max( guard_max, max( hi, lo ) );
-        }
         t++;
     }
-    if( NW && PACKED && a.guard ) atomicMax( a.guard, guard_max );
 }
 
 }  // namespace ssa

@@ -1269,7 +1269,6 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         }
         a.first_pass = ( p == 0 );
         a.out = ctx().d_out_packed.p;
-        a.guard = nullptr;
         if( npass > 1 ) {   // two buffers of one 16-byte entry per stream column pair: pass p reads [(p - 1) & 1], writes [p & 1]
             uint4 * b0 = (uint4 *) ctx().d_bnd.p, * b1 = b0 + ( db.total_cols / 2 + 1 );
             a.bnd_in = p > 0 ? ( ( p & 1 ) ? b0 : b1 ) : nullptr;
