@@ -145,6 +145,11 @@ template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
     return PACKED ? merge_rows( R ) * 1024 + ( ( R - merge_rows( R ) ) / 2 ) * 1024 : R * 1024;
 }
 
+// dynamic shared memory of a kernel instance: the profile and, for packed Needleman-Wunsch, the start-value table
+template<bool PACKED, int R> __host__ __device__ constexpr int score_smem_bytes( bool nw ) {
+    return ( profile_words<PACKED, R>() + ( PACKED && nw ? 2 * R * 32 : 0 ) ) * 4;
+}
+
 // resident CTAs per SM the register allocator has to make room for (64K registers / 256 threads / blocks)
 template<bool PACKED, int R> __host__ __device__ constexpr int min_blocks() { return PACKED ? ( R <= 12 ? 4 : ( R <= 20 ? 3 : 2 ) ) : 2; }
 
@@ -157,6 +162,19 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     extern __shared__ uint32_t prof[];
 
     for( int i = threadIdx.x; i < profile_words<PACKED, R>(); i += blockDim.x ) prof[i] = a.profile[i];
+    // Packed Needleman-Wunsch: start values of every lane's rows - H(i, -1) = gapO + (i + 1) gapE and the E entering column 0,
+    // H + gapO + gapE, both minus the offset - as 128-bit entries [H | E][row quad][lane] behind the profile: a sequence start
+    // costs a lane R/2 shared loads instead of 3R additions (and the WARP runs that code once per lane and sequence pair)
+    constexpr int NW_TAB = profile_words<PACKED, R>();
+    if( NW && PACKED ) {
+        for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
+            const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;
+            const int row = a.rowbase + ( l & ( (int) a.group - 1 ) ) * R + r;
+            const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
+            prof[NW_TAB + i] = (uint32_t) A::bcast( h );
+            prof[NW_TAB + R * 32 + i] = (uint32_t) A::bcast( h + a.gap_open + a.gap_extend );
+        }
+    }
     __syncthreads();
 
     // A warp is split into 32/G independent systolic arrays of G lanes (G = 4, 8, 16 or 32, chosen per query so
@@ -417,21 +435,38 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         T ha_last = A::bcast( 0 ), fa_last = A::bcast( 0 ), hb_last = A::bcast( 0 ), fb_last = A::bcast( 0 );
         if( cia & COL_VALID ) {
             if( cia & COL_FIRST ) {  // a new sequence (pair) starts in this lane (always in column A)
-                T hv = A::bcast( 0 ), ev = A::bcast( 0 );
-                if( NW ) {
-                    hv = A::bcast( a.gap_open + ( row0 + 1 ) * a.gap_extend - a.offset );
-                    ev = A::bcast( 2 * a.gap_open + ( row0 + 2 ) * a.gap_extend - a.offset );
-                    // opaque to the optimiser: otherwise the 2R start values are hoisted out of the step loop as loop
-                    // invariants and occupy 2R registers for the whole kernel
-                    asm volatile( "" : "+r"( hv ), "+r"( ev ) );
-                }
+                if( NW && PACKED ) {
+                    const uint32_t tab = (uint32_t) __cvta_generic_to_shared( prof ) + NW_TAB * 4 + lane * 16;
 #pragma unroll
-                for( int r = 0; r < R; r++ ) {
-                    Hp[r] = hv;
-                    E[r] = ev;
+                    for( int q = 0; q < R / 4; q++ ) {
+                        const uint4 h = lds128( tab + q * 512 ), e = lds128( tab + R * 128 + q * 512 );
+                        Hp[4 * q] = (T) h.x;
+                        Hp[4 * q + 1] = (T) h.y;
+                        Hp[4 * q + 2] = (T) h.z;
+                        Hp[4 * q + 3] = (T) h.w;
+                        E[4 * q] = (T) e.x;
+                        E[4 * q + 1] = (T) e.y;
+                        E[4 * q + 2] = (T) e.z;
+                        E[4 * q + 3] = (T) e.w;
+                    }
+                }
+                else {
+                    T hv = A::bcast( 0 ), ev = A::bcast( 0 );
                     if( NW ) {
-                        hv = A::add( hv, RG );
-                        ev = A::add( ev, RG );
+                        hv = A::bcast( a.gap_open + ( row0 + 1 ) * a.gap_extend - a.offset );
+                        ev = A::bcast( 2 * a.gap_open + ( row0 + 2 ) * a.gap_extend - a.offset );
+                        // opaque to the optimiser: otherwise the 2R start values are hoisted out of the step loop as loop
+                        // invariants and occupy 2R registers for the whole kernel
+                        asm volatile( "" : "+r"( hv ), "+r"( ev ) );
+                    }
+#pragma unroll
+                    for( int r = 0; r < R; r++ ) {
+                        Hp[r] = hv;
+                        E[r] = ev;
+                        if( NW ) {
+                            hv = A::add( hv, RG );
+                            ev = A::add( ev, RG );
+                        }
                     }
                 }
                 diag = NW ? A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset ) : A::bcast( 0 );
@@ -504,6 +539,12 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                         S = A::max3( S, ta0, ta1 );
                         S = A::max3( S, tb0, tb1 );
                     }
+                    else if( PACKED ) {
+                        // (NW: a candidate with a single consumer would be fused into VIADDMNMX + VIMNMX, 5 instead of 4 ALU-pipe
+                        // instructions per word; one multiply-add per two words on the FMA-side pipe keeps it a value - sw32_kernel.cuh)
+                        S = (T) ( (uint32_t) ta0 * (uint32_t) S + (uint32_t) ta1 );
+                        S = (T) ( (uint32_t) tb0 * (uint32_t) S + (uint32_t) tb1 );
+                    }
                 };
                 // one shared load per sequence and column fetches the scores of four query rows
 #pragma unroll
@@ -567,6 +608,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
 
         t++;
     }
+    if( NW && PACKED && (uint32_t) S == 0x9e3779b9u && a.nbatches == 0xffffffffu ) ( (uint32_t *) a.out )[0] = (uint32_t) S;   // never true
 }
 
 }  // namespace ssa

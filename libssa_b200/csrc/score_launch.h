@@ -12,9 +12,9 @@ int launch_score_packed( int R, bool nw, bool multi, const ScoreArgs & args, cud
 // resident CTAs per SM of the packed kernel variant (for sizing the work batches)
 int packed_blocks_per_sm( int R, bool nw, bool multi );
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & args, cudaStream_t stream );
-// launches sw32_kernel<R, multipass> (Smith-Waterman, packed tier, full-warp arrays); returns the grid size used
-int launch_sw32( int R, bool multipass, const Sw32Args & args, cudaStream_t stream );
-int sw32_blocks_per_sm( int R, bool multipass );
+// launches sw32_kernel<R, multipass, nw> (packed tier, full-warp arrays, chained batches); returns the grid size used
+int launch_sw32( int R, bool nw, bool multipass, const Sw32Args & args, cudaStream_t stream );
+int sw32_blocks_per_sm( int R, bool nw, bool multipass );
 }  // namespace ssa
 
 #include <cstdio>

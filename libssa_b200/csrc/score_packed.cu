@@ -19,7 +19,7 @@ template<typename K> static int launch( K kernel, int smem_bytes, const ScoreArg
 }
 
 template<int R> static int pick( bool nw, bool multi, const ScoreArgs & a, cudaStream_t s ) {
-    const int smem = profile_words<true, R>() * 4;
+    const int smem = score_smem_bytes<true, R>( nw );
     if( multi && a.group != 32 )  // remainder pass of a long query on narrow groups
         return nw ? launch( score_kernel<true, R, true, 2, false>, smem, a, s ) : launch( score_kernel<true, R, false, 2, false>, smem, a, s );
     if( nw ) return multi ? launch( score_kernel<true, R, true, 1, false>, smem, a, s )
@@ -31,7 +31,7 @@ template<int R> static int pick( bool nw, bool multi, const ScoreArgs & a, cudaS
 template<typename K> static int occupancy( K kernel, int smem_bytes ) { return kernel_limits( kernel, smem_bytes ).second; }
 
 template<int R> static int occ_pick( bool nw, bool multi ) {
-    const int smem = profile_words<true, R>() * 4;
+    const int smem = score_smem_bytes<true, R>( nw );
     if( nw ) return multi ? occupancy( score_kernel<true, R, true, 1, false>, smem ) : occupancy( score_kernel<true, R, true, 0, false>, smem );
     return multi ? occupancy( score_kernel<true, R, false, 1, false>, smem ) : occupancy( score_kernel<true, R, false, 0, false>, smem );
 }

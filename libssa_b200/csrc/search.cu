@@ -1173,10 +1173,11 @@ struct PassLaunch {
     uint32_t nbatches = 0;
 };
 
-// LIBSSA_B200_NO_SW32=1: Smith-Waterman on full-warp arrays through the generic kernel as well (A/B measurements)
-bool sw32_enabled() {
-    static const bool on = getenv( "LIBSSA_B200_NO_SW32" ) == nullptr;
-    return on;
+// LIBSSA_B200_NO_SW32=1: full-warp arrays through the generic kernel as well; LIBSSA_B200_NO_NW32=1: only Needleman-Wunsch
+// (A/B measurements)
+bool sw32_enabled( bool nw ) {
+    static const bool on = getenv( "LIBSSA_B200_NO_SW32" ) == nullptr, on_nw = getenv( "LIBSSA_B200_NO_NW32" ) == nullptr;
+    return on && ( !nw || on_nw );
 }
 
 // The packed tier over one class of pairs: all passes of the query, one launch each.
@@ -1200,8 +1201,8 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
     w0 = 0;
     for( int p = 0; p < npass; p++ ) {
         const PassLaunch & ps = passes[p];
-        if( !nw && ps.G == 32 && sw32_enabled() ) {
-            // Smith-Waterman on full-warp arrays: the specialised kernel (sw32_kernel.cuh).  Consecutive passes of one shape
+        if( ps.G == 32 && sw32_enabled( nw ) ) {
+            // Full-warp arrays: the specialised kernel (sw32_kernel.cuh).  Consecutive passes of one shape
             // over the same batches - the full passes of a long query - are ONE launch: the kernel chains them itself, a batch
             // of pass p+1 waits only for the same batch of pass p.  (LIBSSA_B200_PASS_PER_LAUNCH=1: one launch per pass.)
             int run = 1;
@@ -1238,7 +1239,19 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
                 s32.bnd1 = s32.bnd0 + ( db.total_cols / 2 + 1 );
             }
             s32.done = run > 1 ? counters + SW32_MAX_PASSES : nullptr;
-            launch_sw32( ps.R, multi, s32, stream );
+            s32.cap_pass = -1;
+            if( nw ) {
+                s32.gap_open = g_gapO;
+                s32.gap_extend = g_gapE;
+                s32.offset = offset;
+                for( int c = p; c < p + run; c++ )   // the pass (of this launch) that holds the query's last row
+                    if( passes[c].rowbase <= qlen - 1 && qlen - 1 < passes[c].rowbase + (size_t) 32 * ps.R ) {
+                        s32.cap_pass = c;
+                        s32.cap_lane = (int) ( ( qlen - 1 - passes[c].rowbase ) / ps.R );
+                        s32.cap_row = (int) ( ( qlen - 1 - passes[c].rowbase ) % ps.R );
+                    }
+            }
+            launch_sw32( ps.R, nw, multi, s32, stream );
             ctx().stats.launches++;
             w0 += (size_t) run * packed_profile_words( ps.R );
             p += run - 1;
@@ -1375,6 +1388,10 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     // predecessor H > 32767 - hi+, every H is bounded by a diagonal candidate the running maximum has seen, and the maximum
     // never decreases - so a final maximum below the threshold proves that nothing wrapped.  E and F stay above
     // 2 (gapO + gapE).  (LIBSSA_B200_STATIC_TIERS=1: the static split, for A/B measurements.)
+    // (The static split is not the cheaper choice even for a handful of long records: with all full passes of the bulk in ONE
+    // persistent launch the 32-bit tier's launches on the auxiliary stream find no free multiprocessor slot after the first
+    // and run behind the bulk - measured +10 ms on the 570 k-record database for 34 records [B200].
+    // LIBSSA_B200_STATIC_TIERS=1 forces it for A/B measurements and tests.)
     const int64_t hip = std::max<int64_t>( pl.hi, 0 );
     const bool speculative = !nw && !positive_gaps && p_static > 0 && hip <= 1024 && pl.lo >= -1024 && !getenv( "LIBSSA_B200_STATIC_TIERS" );
     const int32_t spec_thr = (int32_t) ( 32767 - hip );
@@ -1419,8 +1436,8 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     // batch size of the bulk class: at least ~3 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
     // Smith-Waterman on full-warp arrays runs on sw32_kernel: its warps chain their batches (no wavefront fill per batch), so
     // the batches can be small - at least ~8 per warp, down to 128 columns at the end of the queue
-    const bool chained = !nw && G == 32 && sw32_enabled();
-    const int resident = chained ? sw32_blocks_per_sm( R, npass > 1 ) : packed_blocks_per_sm( R, nw, npass > 1 );
+    const bool chained = G == 32 && sw32_enabled( nw );
+    const int resident = chained ? sw32_blocks_per_sm( R, nw, npass > 1 ) : packed_blocks_per_sm( R, nw, npass > 1 );
     const uint64_t groups = (uint64_t) sms * resident * ( SCORE_THREADS / 32 ) * ( 32 / G );
     uint32_t batch_cols = chained ? 2048 : 4096;
     // (with the shrinking tail of batch_table the choice is flat between 2 and 12 batches per group [B200]; fewer, longer batches
@@ -1493,8 +1510,8 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
                 continue;
             }
             // another shape has another number of resident groups: its own batches over the same pairs
-            const bool ps_chained = !nw && ps.G == 32 && sw32_enabled();
-            const int ps_resident = ps_chained ? sw32_blocks_per_sm( ps.R, true ) : packed_blocks_per_sm( ps.R, nw, true );
+            const bool ps_chained = ps.G == 32 && sw32_enabled( nw );
+            const int ps_resident = ps_chained ? sw32_blocks_per_sm( ps.R, nw, true ) : packed_blocks_per_sm( ps.R, nw, true );
             const uint64_t ps_groups = (uint64_t) sms * ps_resident * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
             uint32_t ps_cols = ps_chained ? 2048 : 4096;
             while( ps_cols > 256 && db.total_cols / ps_cols < ( ps_chained ? 8 : 6 ) * ps_groups ) ps_cols /= 2;

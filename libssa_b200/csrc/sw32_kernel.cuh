@@ -1,7 +1,7 @@
-// Smith-Waterman scoring on full-warp systolic arrays, packed tier (two database sequences per int16 x 2 word): the hot
-// kernel of protein searches (reference src/algo/simd/search_simd_sw.c:172-441 and its chunk loop).  Same recurrence and
-// same data as score_kernel.cuh (which keeps the narrow groups, Needleman-Wunsch, the 32-bit tier and the tracker); what is
-// different is everything AROUND the recurrence - that was 143 of 591 instructions per step of 64 packed words:
+// Smith-Waterman / Needleman-Wunsch scoring on full-warp systolic arrays, packed tier (two database sequences per int16 x 2
+// word): the hot kernel of protein searches (reference src/algo/simd/search_simd_sw.c:172-441, search_simd_nw.c and their
+// chunk loop).  Same recurrence and same data as score_kernel.cuh (which keeps the narrow groups, the 32-bit tier and the
+// tracker); what is different is everything AROUND the recurrence - that was 143 of 591 instructions per step of 64 packed words:
 //
 //   * one warp = one array of 32 lanes x R rows, known at compile time;
 //   * the work batches of a warp are CHAINED: the warp runs on a virtual step axis on which its batches follow each other
@@ -14,7 +14,9 @@
 //     load with 64-bit address arithmetic, and four indexed shuffles + four selects out of eight live registers);
 //   * results are stored by stream position (the column pair in which a pair of sequences ends), boundary rows as one
 //     16-byte entry {H col A, H col B, F col A, F col B} per column pair, so no lane has to know which batch it is in;
-//   * there is no one-column path (pairs are padded with a PAD_RESIDUE column) and no per-step exit vote;
+//   * there is no one-column path (pairs are padded with a PAD_RESIDUE column) and no per-step exit vote.  Needleman-Wunsch
+//     reads its result between the two columns of a step when a sequence ends in the first of them: only the ONE lane that
+//     holds the query's last row leaves the two-column path for that step;
 //   * ALL full passes of a long query run in ONE launch: a CTA works through the passes in order (its warps meet at a CTA
 //     barrier to swap the query profile in shared memory), every pass has its own work queue over the same batches, and a
 //     batch of pass p+1 starts as soon as the SAME batch of pass p is finished (a per-batch counter in global memory,
@@ -46,12 +48,19 @@ struct Sw32Args {
     uint32_t * out_by_col;       // (A:B) running maxima, indexed by the column pair in which the pair of sequences ends
     uint4 * bnd0, * bnd1;        // MULTIPASS: boundary rows per column pair; an even pass reads bnd1 and writes bnd0, an odd pass the reverse
     uint32_t * done;             // MULTIPASS, npass > 1: passes of this launch completed per batch (zero at launch)
+    // Needleman-Wunsch
+    int32_t gap_open, gap_extend;   // gapO, gapE (non-positive)
+    int32_t offset;                 // values are stored minus this offset (centres the value range on 0)
+    int32_t cap_pass;               // pass of the QUERY (not of the launch) that holds the query's last row ...
+    int32_t cap_lane, cap_row;      // ... and the lane / row in the lane
 };
 
 // words of shared memory per warp for the ring: column words, stream positions, boundary entries
-template<bool MULTIPASS> __host__ __device__ constexpr int sw32_ring_words() { return 2 * SW32_RING + ( MULTIPASS ? 5 * SW32_RING : 0 ); }
-template<int R, bool MULTIPASS> __host__ __device__ constexpr int sw32_smem_bytes() {
-    return ( profile_words<true, R>() + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>() ) * 4;
+template<bool MULTIPASS> __host__ __device__ constexpr int sw32_ring_words() { return 2 * SW32_RING + ( MULTIPASS ? 5 * SW32_RING : 0 ) + 16; }
+// Needleman-Wunsch: start values of a lane's rows (H(i, -1) and the E entering column 0), [H | E][row quad][lane] as 128-bit entries
+template<int R> __host__ __device__ constexpr int sw32_nw_table_words() { return 2 * R * 32; }
+template<int R, bool MULTIPASS, bool NW = false> __host__ __device__ constexpr int sw32_smem_bytes() {
+    return ( profile_words<true, R>() + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>() + ( NW ? sw32_nw_table_words<R>() : 0 ) ) * 4;
 }
 
 __device__ __forceinline__ void cp_async4( uint32_t smem_addr, const void * gmem ) {
@@ -75,7 +84,7 @@ __device__ __forceinline__ void sts128( uint32_t addr, uint4 v ) {
     asm volatile( "st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"( addr ), "r"( v.x ), "r"( v.y ), "r"( v.z ), "r"( v.w ) : "memory" );
 }
 
-template<int R, bool MULTIPASS>
+template<int R, bool MULTIPASS, bool NW>
 __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_kernel( const Sw32Args a ) {
     typedef Arith<true> A;
     typedef uint32_t T;
@@ -96,6 +105,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     const uint32_t ring_g = ring_w + SW32_RING * 4;                                          // [RING] column pair index in the stream
     const uint32_t ring_b = ring_g + SW32_RING * 4;                                          // [RING] boundary entry (MULTIPASS)
     const uint32_t ring_e = ring_b + SW32_RING * 16;                                         // [RING] batch + 1 on its last step (MULTIPASS)
+    const uint32_t ring_ws = ring_w + ( sw32_ring_words<MULTIPASS>() - 16 ) * 4;             // [12] the warp's batch bookkeeping (WS_*)
+    const uint32_t ring_cap = ring_w + ( sw32_ring_words<MULTIPASS>() - 4 ) * 4;             // NW: score of sequence B until the pair ends
+    constexpr int NW_TAB = PW + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>();        // first word of the NW start-value table
+    const uint32_t nw_tab = smem_base + NW_TAB * 4 + lane * 16;
     const uint32_t prof_base = smem_base + lane * 16;            // 128-bit entries of the first MR rows
     const uint32_t prof_base16 = smem_base + MR * 4096 + lane * 8;   // 64-bit entries of the other rows
     const uint32_t K65536 = a.k65536;
@@ -110,31 +123,36 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     }
     T S = 0, diag = 0;
     T ha_out = 0, fa_out = 0, hb_out = 0, fb_out = 0, s_out = 0;
+    // Needleman-Wunsch: the matrix' top boundary H(-1, j) = gapO + (j + 1) gapE is generated by the top lane of the query's first
+    // pass (F(-1, j) = H(-1, j) + gapO + gapE); a lane's rows start a sequence at H(i, -1) = gapO + (i + 1) gapE
+    T top_h = 0;
+    bool is_cap = false;           // this lane holds the query's last row in the current pass
 
     // ---- the warp's batches on its virtual step axis (warp-uniform) ----
     // cur / nxt: the two batches the staging front can touch.  A batch of n column pairs occupies max( n, SW32_MIN_STEPS )
-    // virtual steps; steps past its columns, and everything after the queue ran dry, are idle.
-    uint32_t cur_s = 0, cur_e = 0, cur_n = 0, cur_g = 0, cur_b = 0;   // virtual begin / end, column pairs, first column pair in the stream, batch
-    uint32_t nxt_e = 0, nxt_n = 0, nxt_g = 0, nxt_b = 0;              // (begins at cur_e)
-    uint32_t last_real_e = 0;                                 // virtual end of the last real batch
-    bool dry = false;                                         // the work queue of the current pass is exhausted
+    // virtual steps; steps past its columns, and everything after the queue ran dry, are idle.  This bookkeeping is touched
+    // once per 32 steps, so it lives in shared memory (every lane writes and reads the same words) and not in registers the
+    // recurrence needs: WS_CUR_S virtual begin of the current batch, _E its end (= begin of the next), _N column pairs, _G first
+    // column pair in the stream, _B batch index; WS_LAST virtual end of the last real batch; WS_DRY the pass' queue is exhausted.
+    enum { WS_CUR_S = 0, WS_CUR_E, WS_CUR_N, WS_CUR_G, WS_CUR_B, WS_NXT_E, WS_NXT_N, WS_NXT_G, WS_NXT_B, WS_LAST, WS_DRY };
+    auto ws_get = [&]( int i ) { return lds32( ring_ws + i * 4 ); };
+    auto ws_set = [&]( int i, uint32_t v ) { sts32( ring_ws + i * 4, v ); };
     uint32_t pp = 0;                                          // pass of this launch the CTA works on
     uint32_t * counter = a.counters;
     const uint4 * bnd_in = nullptr;
     uint4 * bnd_out = nullptr;
     bool first_pass = true, publish = false;
 
-    auto fetch = [&]( uint32_t begin, uint32_t & e, uint32_t & n, uint32_t & g, uint32_t & bidx ) {
+    // pulls the next batch from the pass' queue; it begins at virtual step `begin`; fills slot WS_CUR_* (which = 0) or WS_NXT_* (1)
+    auto fetch = [&]( const uint32_t begin, const int which ) {
         uint32_t b = 0xffffffffu;
-        if( !dry ) {
+        if( !ws_get( WS_DRY ) ) {
             if( is_top ) b = atomicAdd( counter, 1u );
             b = __shfl_sync( FULL, b, 0 );
         }
+        uint32_t e, n = 0, g = 0, bidx = 0;
         if( b >= a.nbatches ) {
-            dry = true;
-            n = 0;
-            g = 0;
-            bidx = 0;
+            ws_set( WS_DRY, 1 );
             e = begin + SW32_MIN_STEPS;
         }
         else {
@@ -143,31 +161,37 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             g = (uint32_t) ( bt.col0 >> 1 );
             bidx = b;
             e = begin + max( n, (uint32_t) SW32_MIN_STEPS );
-            last_real_e = e;
+            ws_set( WS_LAST, e );
             if( MULTIPASS && pp > 0 ) {   // the previous pass of this launch must have finished this batch (its boundary row, its result)
                 if( is_top )
                     while( ld_acquire( a.done + b ) < pp ) __nanosleep( 200 );
                 __syncwarp();
             }
         }
+        ws_set( which ? WS_NXT_E : WS_CUR_E, e );
+        ws_set( which ? WS_NXT_N : WS_CUR_N, n );
+        ws_set( which ? WS_NXT_G : WS_CUR_G, g );
+        ws_set( which ? WS_NXT_B : WS_CUR_B, bidx );
+        return e;
     };
 
     // stages the 32 virtual steps [v0, v0 + 32): lane l prepares step v0 + l
     auto stage = [&]( const uint32_t v0 ) {
         const uint32_t v = v0 + lane;
         const uint32_t slot = v & ( SW32_RING - 1 );
+        const uint32_t cur_e = ws_get( WS_CUR_E );
         uint32_t c, n, g, bidx;
         if( v < cur_e ) {
-            c = v - cur_s;
-            n = cur_n;
-            g = cur_g;
-            bidx = cur_b;
+            c = v - ws_get( WS_CUR_S );
+            n = ws_get( WS_CUR_N );
+            g = ws_get( WS_CUR_G );
+            bidx = ws_get( WS_CUR_B );
         }
         else {
             c = v - cur_e;
-            n = nxt_n;
-            g = nxt_g;
-            bidx = nxt_b;
+            n = ws_get( WS_NXT_N );
+            g = ws_get( WS_NXT_G );
+            bidx = ws_get( WS_NXT_B );
         }
         if( c < n ) {
             const uint32_t pos = g + c;
@@ -187,12 +211,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         }
         cp_async_commit();
         if( v0 + 32 >= cur_e ) {   // the front leaves the current batch: the next one becomes current, another is pulled
-            cur_s = cur_e;
-            cur_e = nxt_e;
-            cur_n = nxt_n;
-            cur_g = nxt_g;
-            cur_b = nxt_b;
-            fetch( cur_e, nxt_e, nxt_n, nxt_g, nxt_b );
+            __syncwarp();          // (every lane has read the old values)
+            const uint32_t nxt_e = ws_get( WS_NXT_E ), nxt_n = ws_get( WS_NXT_N ), nxt_g = ws_get( WS_NXT_G ), nxt_b = ws_get( WS_NXT_B );
+            __syncwarp();
+            ws_set( WS_CUR_S, cur_e );
+            ws_set( WS_CUR_E, nxt_e );
+            ws_set( WS_CUR_N, nxt_n );
+            ws_set( WS_CUR_G, nxt_g );
+            ws_set( WS_CUR_B, nxt_b );
+            fetch( nxt_e, 1 );
+            __syncwarp();
         }
     };
 
@@ -204,6 +232,15 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         const uint32_t * src = a.profile + (size_t) pp * PW;
         for( int i = threadIdx.x; i < PW; i += blockDim.x ) smem[i] = src[i];
     }
+    if( NW ) {   // start values of this pass' rows: H(i, -1) = gapO + (i + 1) gapE, E = H + gapO + gapE (both minus the offset)
+        for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
+            const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;   // word i of the H half: [row quad][lane][row in quad]
+            const int row = (int) ( a.pass0 + pp ) * 32 * R + l * R + r;
+            const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
+            smem[NW_TAB + i] = A::bcast( h );
+            smem[NW_TAB + R * 32 + i] = A::bcast( h + a.gap_open + a.gap_extend );
+        }
+    }
     __syncthreads();
     {
         const uint32_t abs_pass = a.pass0 + pp;
@@ -212,20 +249,42 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         bnd_out = MULTIPASS && ( pp + 1 < a.npass || a.more_passes ) ? ( ( abs_pass & 1 ) ? a.bnd1 : a.bnd0 ) : nullptr;
         publish = MULTIPASS && pp + 1 < a.npass;
         counter = a.counters + pp;
+        if( NW ) is_cap = (int) abs_pass == a.cap_pass && lane == a.cap_lane;
     }
     // the virtual axis simply continues: the steps already staged beyond t0 are idle ones and are staged again
-    dry = false;
-    cur_s = t0;
-    fetch( t0, cur_e, cur_n, cur_g, cur_b );
-    fetch( cur_e, nxt_e, nxt_n, nxt_g, nxt_b );
+    __syncwarp();
+    ws_set( WS_DRY, 0 );
+    ws_set( WS_LAST, 0 );
+    ws_set( WS_CUR_S, t0 );
+    __syncwarp();
+    fetch( fetch( t0, 0 ), 1 );
+    __syncwarp();
     stage( t0 );
     stage( t0 + 32 );
+
+    // Needleman-Wunsch: the lane that owns the query's last row records H of that row at the last column of sequence B / A
+    // (the score of B waits in shared memory until the pair ends)
+    auto nw_capture = [&]( const uint32_t ci, const uint32_t slot4 ) {
+        if( ci & ( COL_LAST_A | COL_LAST_B ) ) {
+            // H of the query's last row without turning Hp[] into an indexable (local-memory) array: a chain of predicated moves
+            T sel = Hp[0];
+#pragma unroll
+            for( int r = 1; r < R; r++ ) {
+                T cand = Hp[r];
+                asm volatile( "" : "+r"( cand ) );
+                if( r == a.cap_row ) sel = cand;
+                asm volatile( "" : "+r"( sel ) );
+            }
+            if( ci & COL_LAST_B ) sts32( ring_cap, sel );
+            if( ci & COL_LAST_A ) a.out_by_col[lds32( ring_g + slot4 )] = __byte_perm( lds32( ring_cap ), sel, 0x7610 );
+        }
+    };
 
     for( ;; t0 += 32 ) {
         stage( t0 + 64 );
         cp_async_wait<2>();     // everything but the two youngest blocks has landed: block t0 is complete
         __syncwarp();
-        if( dry && t0 >= last_real_e + 32 ) break;   // the bottom lane has passed the last real step
+        if( ws_get( WS_DRY ) && t0 >= ws_get( WS_LAST ) + 32 ) break;   // the bottom lane has passed the last real step
 
 #pragma unroll 1
         for( uint32_t t = t0; t < t0 + 32; t++ ) {
@@ -237,14 +296,23 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             T fa_in = __shfl_up_sync( FULL, fa_out, 1 );
             T hb_in = __shfl_up_sync( FULL, hb_out, 1 );
             T fb_in = __shfl_up_sync( FULL, fb_out, 1 );
-            T s_in = __shfl_up_sync( FULL, s_out, 1 );
+            T s_in = 0;
+            if( !NW ) s_in = __shfl_up_sync( FULL, s_out, 1 );
             if( is_top ) {
-                if( MULTIPASS ) {
+                if( MULTIPASS && !( NW && first_pass ) ) {
                     const uint4 b = lds128( ring_b + slot4 * 4 );
                     ha_in = b.x;
                     hb_in = b.y;
                     fa_in = b.z;
                     fb_in = b.w;
+                }
+                else if( NW ) {
+                    if( cia & COL_FIRST ) top_h = A::bcast( a.gap_open + a.gap_extend - a.offset );
+                    ha_in = top_h;
+                    fa_in = A::add( top_h, QR );
+                    hb_in = A::add( top_h, RG );
+                    fb_in = A::add( hb_in, QR );
+                    top_h = A::add( hb_in, RG );
                 }
                 else {
                     ha_in = 0;
@@ -259,16 +327,76 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             s_out = 0;
             if( cia & COL_VALID ) {
                 if( cia & COL_FIRST ) {   // a new pair of sequences starts in this lane (always in column A)
+                    if( NW ) {   // H(i, -1) and E of this lane's rows from the pass' table, H(row0 - 1, -1) as the first diagonal
 #pragma unroll
-                    for( int r = 0; r < R; r++ ) {
-                        Hp[r] = 0;
-                        E[r] = 0;
+                        for( int q = 0; q < R / 4; q++ ) {
+                            const uint4 h = lds128( nw_tab + q * 512 ), e = lds128( nw_tab + R * 128 + q * 512 );
+                            Hp[4 * q] = h.x;
+                            Hp[4 * q + 1] = h.y;
+                            Hp[4 * q + 2] = h.z;
+                            Hp[4 * q + 3] = h.w;
+                            E[4 * q] = e.x;
+                            E[4 * q + 1] = e.y;
+                            E[4 * q + 2] = e.z;
+                            E[4 * q + 3] = e.w;
+                        }
+                        const int row0 = (int) ( a.pass0 + pp ) * 32 * R + lane * R;
+                        diag = A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset );
                     }
-                    diag = 0;
-                    S = 0;
+                    else {
+#pragma unroll
+                        for( int r = 0; r < R; r++ ) {
+                            Hp[r] = 0;
+                            E[r] = 0;
+                        }
+                        diag = 0;
+                        S = 0;
+                    }
                 }
-                // ---- two columns per step (see score_kernel.cuh for the recurrence and its instruction selection) ----
                 const uint32_t ra = cia & 31u, rb = ( cia >> 5 ) & 31u, sa = cib & 31u, sb = ( cib >> 5 ) & 31u;
+                if( NW && is_cap && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) {
+                    // ---- Needleman-Wunsch, the lane with the query's last row, a sequence ends in the FIRST column of the step:
+                    // the result has to be read between the two columns, so this lane (alone) goes column by column ----
+                    auto single_column = [&]( const uint32_t r0, const uint32_t r1, const T h_in, const T f_in, T & h_last, T & f_last ) {
+                        T f = f_in;
+                        T hd = diag;
+                        diag = h_in;
+                        auto dp_pair1 = [&]( const int k, const uint32_t v0, const uint32_t v1 ) {
+                            const T t0 = A::add( hd, v0 );
+                            const T t1 = A::add( Hp[2 * k], v1 );
+                            hd = Hp[2 * k + 1];
+                            T hq;
+                            Hp[2 * k] = A::max3( t0, E[2 * k], f );
+                            hq = A::add( Hp[2 * k], QR );
+                            E[2 * k] = A::addmax( E[2 * k], RG, hq );
+                            f = A::addmax( f, RG, hq );
+                            Hp[2 * k + 1] = A::max3( t1, E[2 * k + 1], f );
+                            hq = A::add( Hp[2 * k + 1], QR );
+                            E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
+                            f = A::addmax( f, RG, hq );
+                        };
+#pragma unroll
+                        for( int q = 0; q < MR / 4; q++ ) {
+                            const uint4 la = lds128( prof_base + ( r0 << 9 ) + q * 16384 ), lb = lds128( prof_base + ( r1 << 9 ) + q * 16384 );
+                            dp_pair1( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
+                            dp_pair1( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+                        }
+#pragma unroll
+                        for( int q = 0; q < NQ16; q++ ) {
+                            const uint2 la = lds64( prof_base16 + ( r0 << 8 ) + q * 8192 ), lb = lds64( prof_base16 + ( r1 << 8 ) + q * 8192 );
+                            dp_pair1( MR / 2 + 2 * q, __byte_perm( lb.x, la.x, 0x5410 ), __byte_perm( lb.x, la.x, 0x7632 ) );
+                            dp_pair1( MR / 2 + 2 * q + 1, __byte_perm( lb.y, la.y, 0x5410 ), __byte_perm( lb.y, la.y, 0x7632 ) );
+                        }
+                        h_last = Hp[R - 1];
+                        f_last = f;
+                    };
+                    single_column( ra, rb, ha_in, fa_in, ha_last, fa_last );
+                    nw_capture( cia, slot4 );
+                    single_column( sa, sb, hb_in, fb_in, hb_last, fb_last );
+                    nw_capture( cib, slot4 );
+                }
+                else {
+                // ---- two columns per step (see score_kernel.cuh for the recurrence and its instruction selection) ----
                 T fa = fa_in, fb = fb_in;
                 T ha_prev = ha_in;
                 T hda = diag;
@@ -278,27 +406,37 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                     const T ta1 = A::add( Hp[2 * k], va1 );
                     hda = Hp[2 * k + 1];
                     T hq;
-                    const T ha0 = A::max3_relu( ta0, E[2 * k], fa );
+                    const T ha0 = NW ? A::max3( ta0, E[2 * k], fa ) : A::max3_relu( ta0, E[2 * k], fa );
                     hq = A::add( ha0, QR );
                     const T ea0 = A::addmax( E[2 * k], RG, hq );
                     fa = A::addmax( fa, RG, hq );
                     const T tb0 = A::add( ha_prev, vb0 );
-                    Hp[2 * k] = A::max3_relu( tb0, ea0, fb );
+                    Hp[2 * k] = NW ? A::max3( tb0, ea0, fb ) : A::max3_relu( tb0, ea0, fb );
                     hq = A::add( Hp[2 * k], QR );
                     E[2 * k] = A::addmax( ea0, RG, hq );
                     fb = A::addmax( fb, RG, hq );
-                    const T ha1 = A::max3_relu( ta1, E[2 * k + 1], fa );
+                    const T ha1 = NW ? A::max3( ta1, E[2 * k + 1], fa ) : A::max3_relu( ta1, E[2 * k + 1], fa );
                     hq = A::add( ha1, QR );
                     const T ea1 = A::addmax( E[2 * k + 1], RG, hq );
                     fa = A::addmax( fa, RG, hq );
                     const T tb1 = A::add( ha0, vb1 );
-                    Hp[2 * k + 1] = A::max3_relu( tb1, ea1, fb );
+                    Hp[2 * k + 1] = NW ? A::max3( tb1, ea1, fb ) : A::max3_relu( tb1, ea1, fb );
                     hq = A::add( Hp[2 * k + 1], QR );
                     E[2 * k + 1] = A::addmax( ea1, RG, hq );
                     fb = A::addmax( fb, RG, hq );
                     ha_prev = ha1;
-                    S = A::max3( S, ta0, ta1 );
-                    S = A::max3( S, tb0, tb1 );
+                    if( !NW ) {
+                        S = A::max3( S, ta0, ta1 );
+                        S = A::max3( S, tb0, tb1 );
+                    }
+                    else {
+                        // Needleman-Wunsch has no running maximum, and a diagonal candidate with a single consumer is fused by
+                        // ptxas into VIADDMNMX + VIMNMX - two instructions of the binding ALU pipe instead of VIADD.16x2 (FMA-side
+                        // pipe) + VIMNMX3 (5 instead of 4 ALU-pipe instructions per word).  One multiply-add per two words on the
+                        // FMA-side pipe keeps the candidates alive as values (its result is never used for anything real).
+                        S = ta0 * S + ta1;
+                        S = tb0 * S + tb1;
+                    }
                 };
 #pragma unroll
                 for( int q = 0; q < MR / 4; q++ ) {
@@ -320,9 +458,11 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 fa_last = fa;
                 hb_last = Hp[R - 1];
                 fb_last = fb;
+                if( NW && is_cap ) nw_capture( cib, slot4 );
+                }
 
                 // ---- the pair ends in this step: the running maximum travels down the lanes with the wavefront ----
-                if( ( cia | cib ) & COL_LAST_A ) {
+                if( !NW && ( ( cia | cib ) & COL_LAST_A ) ) {
                     s_out = A::max2( s_in, S );
                     if( is_bottom ) {   // (the earlier pass may have run on another SM: read around L1)
                         uint32_t * o = a.out_by_col + lds32( ring_g + slot4 );
@@ -348,6 +488,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     }
   }
     cp_async_wait<0>();
+    if( NW && S == 0x9e3779b9u && a.nbatches == 0xffffffffu ) a.out_by_col[0] = S;   // never true: keeps the candidate chain alive
 }
 
 }  // namespace ssa

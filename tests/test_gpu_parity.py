@@ -113,6 +113,63 @@ def test_exact_scores_vs_oracle_port(prod, port, tmp_path, qlen):
         prod.free_sequence(qh)
 
 
+@pytest.mark.parametrize("R", [4, 8, 12, 16, 20, 24, 28, 32])
+def test_full_warp_kernel_every_shape(prod, port, tmp_path, monkeypatch, R):
+    """sw32_kernel<R, MULTIPASS, NW>: every rows-per-lane instantiation forced with LIBSSA_B200_SHAPE=32,R, one pass (query fills
+    the array, ends in its last / first / a middle row) and several passes, SW and NW, pairs of equal / odd / even lengths"""
+    from libssa_b200 import synth
+    rng = np.random.default_rng(100 + R)
+    monkeypatch.setenv("LIBSSA_B200_SHAPE", "32,%d" % R)
+    base = synth.random_protein(rng, 3 * 32 * R)
+    seqs = synth.protein_db(200, 7 * R, query=base[:32 * R], homolog_frac=0.15, n_dup=8, mu=4.6, sigma=0.9, min_len=1, max_len=2500)
+    seqs += [base[:40], base[:40], base[:41], base[5:46], base[:1], base[:2], base[:32 * R], base[:32 * R + 1]]   # equal, odd/even neighbours
+    path = tmp_path / "db.fas"
+    synth.write_fasta(str(path), seqs)
+    codes = [port.map_db(s, False) for s in seqs]
+    M = matrix_of("blosum62")
+    prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    prod.init_score_matrix(cases.MATRIX_BUILDIN, "blosum62")
+    prod.init_gap_penalties(-11, -1)
+    prod.init_db(str(path))
+    for qlen in (32 * R, 32 * R - R, 32 * R - R + 1, 17 * R + 3, 32 * R + 1, 2 * 32 * R + R // 2 + 1, 3 * 32 * R):
+        q = base[:qlen]
+        qc = port.map_query(q, False)
+        qh = prod.init_sequence_fasta(cases.READ_FROM_STRING, q)
+        for nw in (False, True):
+            _, sc = prod.score_all(qh, nw)
+            exp = port.score_db(codes, qc, M, -11, -1, nw)
+            bad = np.nonzero(sc != exp)[0]
+            assert len(bad) == 0, (R, qlen, nw, bad[:5], sc[bad[:5]], exp[bad[:5]])
+        prod.free_sequence(qh)
+
+
+@pytest.mark.parametrize("tiers", ["LIBSSA_B200_STATIC_TIERS", "LIBSSA_B200_DEFAULT_TIERS"])
+def test_static_and_speculative_tier_split(prod, port, tmp_path, monkeypatch, tiers):
+    """match 127: every pair longer than 257 residues is beyond the static int16 bound; both ways of handling them (32-bit tier
+    up front / packed tier + recomputation of the sequences that came near the limit) give the oracle's scores"""
+    from libssa_b200 import synth
+    monkeypatch.setenv(tiers, "1")
+    rng = np.random.default_rng(77)
+    q = synth.random_protein(rng, 700)
+    seqs = synth.protein_db(400, 78, query=q, homolog_frac=0.2, n_dup=10, mu=5.5, sigma=0.8, min_len=1, max_len=3000)
+    seqs[7] = q
+    seqs[8] = q[:300] + q[350:]
+    path = tmp_path / "db.fas"
+    synth.write_fasta(str(path), seqs)
+    codes = [port.map_db(s, False) for s in seqs]
+    qc = port.map_query(q, False)
+    prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    prod.init_constant_scores(127, -1)
+    prod.init_gap_penalties(-1, -1)
+    prod.init_db(str(path))
+    qh = prod.init_sequence_fasta(cases.READ_FROM_STRING, q)
+    _, sc = prod.score_all(qh, False)
+    exp = port.score_db(codes, qc, port.constant_matrix(127, -1), -1, -1, False)
+    assert (sc == exp).all() and sc.max() == 127 * 700
+    assert prod.stats().wide_tier_seqs > 0
+    prod.free_sequence(qh)
+
+
 def test_nucleotide_long_query_wide_tier(prod, port, tmp_path):
     """BASELINE config 5 in small: 3 kbp query, match 5: NW leaves the 16-bit range for the long homologs"""
     from libssa_b200 import synth
