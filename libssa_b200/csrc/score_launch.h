@@ -12,6 +12,23 @@ int launch_score_packed( int R, bool nw, bool multi, const ScoreArgs & args, cud
 // resident CTAs per SM of the packed kernel variant (for sizing the work batches)
 int packed_blocks_per_sm( int R, bool nw, bool multi );
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & args, cudaStream_t stream );
+// The 32-bit tier for queries of more than one pass (wide_pipe.cu): all passes of a sequence run as a pipeline in ONE launch.
+constexpr int WIDE_PIPE_R = 16;   // rows per lane: 64 KB of profile per CTA, two CTAs per multiprocessor
+struct WidePipeArgs {
+    const uint16_t * stream;
+    const Batch * batches;             // one sequence each (col0, ncols, half, out0 = output slot, bnd0 = first boundary column)
+    uint32_t nbatches;                 // sizes the grid ...
+    const uint32_t * nbatches_dev;     // ... if set, the real number is read from device memory
+    uint32_t * counter;                // task queue head (zero at launch)
+    const uint32_t * profile;          // npass profiles of WIDE_PIPE_R x 1024 words, [row][residue][lane]
+    uint32_t npass;
+    int32_t gap_open, gap_extend;
+    int32_t cap_pass, cap_lane, cap_row;   // NW: where the query's last row lives
+    int32_t * out;                     // score per output slot (SW: zero at launch, passes combine by atomicMax)
+    uint4 * bnd0, * bnd1;              // boundary rows { H col A, H col B, F col A, F col B } per column pair, two buffers
+    uint32_t * progress;               // [batch][pass] column pairs whose boundary row is written (zero at launch)
+};
+int launch_wide_pipe( bool nw, const WidePipeArgs & args, cudaStream_t stream );
 // launches sw32_kernel<R, multipass, nw> (packed tier, full-warp arrays, chained batches); returns the grid size used
 int launch_sw32( int R, bool nw, bool multipass, const Sw32Args & args, cudaStream_t stream );
 int sw32_blocks_per_sm( int R, bool nw, bool multipass );

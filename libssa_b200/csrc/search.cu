@@ -167,6 +167,7 @@ struct Ctx {
     DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
     DevBuf<uint32_t> d_pass_state;        // sw32_kernel, several passes per launch: [SW32_MAX_PASSES] queue heads | [nbatches] passes done
+    DevBuf<uint32_t> d_wide_progress[2];  // pipelined 32-bit tier: [batch][pass] progress counters
     DevBuf<uint32_t> d_spec_list;         // speculative packed tier: sequences listed for the 32-bit tier
     PinBuf<uint32_t> h_spec_count[2];
     bool spec_pending[2] = { false, false };
@@ -772,9 +773,16 @@ __global__ void unpack_scores_kernel( const uint32_t * packed, const uint64_t * 
     }
 }
 
-// work batches of the 32-bit tier for the sequences the speculative packed tier listed (at most `cap`, a host-side bound)
+// the output slots of a list of 32-bit-tier batches set to zero (the passes of the pipelined tier combine by atomicMax)
+__global__ void zero_slots_kernel( const Batch * batches, uint32_t n, int32_t * out ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n ) out[batches[i].out0] = 0;
+}
+
+// work batches of the 32-bit tier for the sequences the speculative packed tier listed (at most `cap`, a host-side bound);
+// zero_out: the listed sequences' scores are reset (pipelined tier)
 __global__ void build_spec_batches_kernel( const uint32_t * list, const uint32_t * count, uint32_t cap, const uint64_t * pair_col,
-        const uint32_t * sorted_len, Batch * batches, uint32_t * nbatches ) {
+        const uint32_t * sorted_len, Batch * batches, uint32_t * nbatches, int32_t * zero_out ) {
     if( blockIdx.x != 0 || threadIdx.x != 0 ) return;
     const uint32_t n = min( *count, cap );
     uint64_t bnd = 0;
@@ -789,6 +797,7 @@ __global__ void build_spec_batches_kernel( const uint32_t * list, const uint32_t
         b.pad = 0;
         bnd += b.ncols;
         batches[i] = b;
+        if( zero_out ) zero_out[s] = 0;
     }
     *nbatches = n;
 }
@@ -1021,6 +1030,48 @@ void launch_fill( int32_t * p, int32_t v, size_t n ) {
     ctx().stats.launches++;
 }
 
+// The pipelined 32-bit tier (wide_pipe.cu) serves every query of more than one of ITS passes (32 lanes x WIDE_PIPE_R rows),
+// except the first-crossing tracker.  LIBSSA_B200_NO_WIDE_PIPE=1: one launch per pass as before (A/B measurements, tests).
+bool wide_pipe_applies( size_t qlen ) { return qlen > (size_t) 32 * WIDE_PIPE_R && !getenv( "LIBSSA_B200_NO_WIDE_PIPE" ); }
+
+Plan wide_pipe_plan( const Plan & pl, size_t qlen ) {
+    Plan p = pl;
+    p.wide_G = 32;
+    p.wide_R = WIDE_PIPE_R;
+    p.wide_npass = (int) ( ( qlen + (size_t) 32 * WIDE_PIPE_R - 1 ) / ( (size_t) 32 * WIDE_PIPE_R ) );
+    p.wide_qpad = p.wide_npass * 32 * WIDE_PIPE_R;
+    return p;
+}
+
+// batches in d_wide_batches[slot] (n of them, or *d_nb on the device), profiles in d_profile_wide[slot]; bnd_cols = boundary columns of all batches
+void launch_wide_pipe_tier( int slot, uint32_t n, const uint32_t * d_nb, uint64_t bnd_cols, size_t qlen, int npass, bool nw, cudaStream_t stream ) {
+    ctx().d_bnd_wide.reserve( 4 * bnd_cols + 256 );   // 2 buffers x ( bnd_cols / 2 + 1 ) entries x 4 words
+    ctx().d_wide_progress[slot].reserve( (size_t) n * npass + 1 );
+    ctx().d_counter.reserve( 64 );
+    CUDA_OK( cudaMemsetAsync( ctx().d_wide_progress[slot].p, 0, ( (size_t) n * npass + 1 ) * 4, stream ) );
+    CUDA_OK( cudaMemsetAsync( ctx().d_counter.p + 16 + 8 * slot, 0, 4, stream ) );
+    WidePipeArgs a;
+    memset( &a, 0, sizeof( a ) );
+    a.stream = ctx().db.d_stream.p;
+    a.batches = ctx().d_wide_batches[slot].p;
+    a.nbatches = n;
+    a.nbatches_dev = d_nb;
+    a.counter = ctx().d_counter.p + 16 + 8 * slot;
+    a.profile = ctx().d_profile_wide[slot].p;
+    a.npass = (uint32_t) npass;
+    a.gap_open = g_gapO;
+    a.gap_extend = g_gapE;
+    a.cap_pass = (int) ( ( qlen - 1 ) / ( (size_t) 32 * WIDE_PIPE_R ) );
+    a.cap_lane = (int) ( ( ( qlen - 1 ) % ( (size_t) 32 * WIDE_PIPE_R ) ) / WIDE_PIPE_R );
+    a.cap_row = (int) ( ( qlen - 1 ) % WIDE_PIPE_R );
+    a.out = ctx().d_scores.p;
+    a.bnd0 = (uint4 *) ctx().d_bnd_wide.p;
+    a.bnd1 = a.bnd0 + ( bnd_cols / 2 + 1 );
+    a.progress = ctx().d_wide_progress[slot].p;
+    launch_wide_pipe( nw, a, stream );
+    ctx().stats.launches++;
+}
+
 // runs the wide tier over `items` (slots = sorted positions); optional first-crossing tracking
 // `slot` selects the staging buffers (0 = wide tier of a search, 1 = overflow tracking) so that a second use inside
 // one search never overwrites pinned memory an earlier asynchronous copy has not consumed yet
@@ -1046,6 +1097,23 @@ void run_wide( const std::vector<uint32_t> & slots, const uint8_t * q, size_t ql
     ctx().d_wide_batches[slot].reserve( n );
     CUDA_OK( cudaMemcpyAsync( ctx().d_wide_batches[slot].p, ctx().h_wide_batches[g_stage_slot][slot].p, n * sizeof( Batch ), cudaMemcpyHostToDevice, stream ) );
     ctx().stats.h2d_bytes += n * sizeof( Batch );
+    if( !track && wide_pipe_applies( qlen ) ) {   // several passes: all of them in one launch, as a pipeline per sequence
+        const Plan plp = wide_pipe_plan( pl, qlen );
+        const int npass = plp.wide_npass;
+        const size_t words = (size_t) WIDE_PIPE_R * 1024;
+        ctx().h_profile_wide[g_stage_slot][slot].reserve( words * npass );
+        for( int p = 0; p < npass; p++ ) fill_profile_wide( ctx().h_profile_wide[g_stage_slot][slot].p + p * words, q, qlen, plp, p );
+        ctx().d_profile_wide[slot].reserve( words * npass );
+        CUDA_OK( cudaMemcpyAsync( ctx().d_profile_wide[slot].p, ctx().h_profile_wide[g_stage_slot][slot].p, words * npass * 4, cudaMemcpyHostToDevice, stream ) );
+        ctx().stats.h2d_bytes += words * npass * 4;
+        if( !nw ) {
+            zero_slots_kernel<<<(unsigned) ( ( n + 255 ) / 256 ), 256, 0, stream>>>( ctx().d_wide_batches[slot].p, (uint32_t) n, ctx().d_scores.p );
+            ctx().stats.launches++;
+        }
+        launch_wide_pipe_tier( slot, (uint32_t) n, nullptr, bnd, qlen, npass, nw, stream );
+        ctx().stats.wide_tier_seqs += n;
+        return;
+    }
     const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
     const size_t words = (size_t) R * 1024;
     ctx().h_profile_wide[g_stage_slot][slot].reserve( words * npass );
@@ -1111,7 +1179,9 @@ void upload_matrix32() {
 // stream columns.
 void run_wide_spec( const uint8_t * q, size_t qlen, const Plan & pl, uint32_t cap, uint64_t cap_cols, cudaStream_t stream ) {
     PackedDb & db = ctx().db;
-    const int npass = pl.wide_npass, R = pl.wide_R, G = pl.wide_G;
+    const bool pipe = wide_pipe_applies( qlen );
+    const Plan plw = pipe ? wide_pipe_plan( pl, qlen ) : pl;
+    const int npass = plw.wide_npass, R = plw.wide_R, G = plw.wide_G;
     const size_t words = (size_t) R * 1024;
     upload_matrix32();
     ctx().d_query.reserve( qlen + 1 );
@@ -1123,10 +1193,11 @@ void run_wide_spec( const uint8_t * q, size_t qlen, const Plan & pl, uint32_t ca
     ctx().d_wide_batches[0].reserve( cap );
     uint32_t * d_nb = ctx().d_counter.p + 48;
     build_spec_batches_kernel<<<1, 32, 0, stream>>>( ctx().d_spec_list.p, ctx().d_counter.p + 44, cap, db.d_pair_col.p, db.d_sorted_len.p,
-            ctx().d_wide_batches[0].p, d_nb );
+            ctx().d_wide_batches[0].p, d_nb, pipe ? ctx().d_scores.p : nullptr );
     ctx().stats.launches += 2;
+    if( pipe ) launch_wide_pipe_tier( 0, cap, d_nb, cap_cols, qlen, npass, false, stream );
     if( npass > 1 ) ctx().d_bnd_wide.reserve( 4 * cap_cols + 256 );
-    for( int p = 0; p < npass; p++ ) {
+    for( int p = 0; p < npass && !pipe; p++ ) {
         CUDA_OK( cudaMemsetAsync( ctx().d_counter.p + 16, 0, 4, stream ) );
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
@@ -1788,6 +1859,8 @@ static void release_ctx( Ctx & c ) {
     c.d_cand_id.release();
     c.d_cand_score.release();
     c.d_spec_list.release();
+    c.d_wide_progress[0].release();
+    c.d_wide_progress[1].release();
     c.d_pass_state.release();
     c.h_spec_count[0].release();
     c.h_spec_count[1].release();
