@@ -81,6 +81,10 @@ struct ScoreArgs {
     int32_t * first8;          // TRACK: first column reaching thr8 / thr16, per slot (atomicMin)
     int32_t * first16;
     int32_t thr8, thr16;
+    // DUAL (two QUERIES per packed word, one database sequence per launch half)
+    uint32_t dual_half;        // 0 = the launch scores sequence A of every pair (bits 0-4), 1 = sequence B (bits 5-9)
+    uint32_t out_stride;       // words between the result arrays of the two halves
+    int32_t cap_lane2, cap_row2;   // NW: lane / row of the SECOND query's last row (cap_lane / cap_row: the first query's)
     const uint4 * bnd_in;       // boundary row from the previous pass (nullptr in pass 0): one entry per column pair,
                                 // { H column A, H column B, F column A, F column B } of the pass' last query row
     uint4 * bnd_out;            // boundary row for the next pass (nullptr in the last pass)
@@ -154,18 +158,25 @@ template<bool PACKED, int R> __host__ __device__ constexpr int score_smem_bytes(
 template<bool PACKED, int R> __host__ __device__ constexpr int min_blocks() { return PACKED ? ( R <= 12 ? 4 : ( R <= 20 ? 3 : 2 ) ) : 2; }
 
 // MULTI: 0 = the whole query in one pass; 1 = one pass of several, full-warp groups; 2 = one pass of several, narrow groups
-template<bool PACKED, int R, bool NW, int MULTI, bool TRACK>
+// DUAL (packed tier, one pass): the two halves of every word belong to two QUERIES scored against the SAME database
+// sequence (sequence A of every pair in one launch, sequence B in another).  Both halves then see the same residue, so a
+// profile entry IS the (q1 : q2) word of a row: one LDS.128 delivers four rows ready for use - no merge instruction, half
+// the lookups: 5.75 (SW) / 5.25 (NW) instead of 7.5 / 7 instructions per word, 3.5 / 3 of them on the ALU pipe.  Used by
+// ssa_b200_align_batch for consecutive queries (the reference takes one query per call, src/libssa.h:240-250).
+template<bool PACKED, int R, bool NW, int MULTI, bool TRACK, bool DUAL = false>
 __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) score_kernel( const ScoreArgs a ) {
     typedef Arith<PACKED> A;
     typedef typename A::T T;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ uint32_t prof[];
+    static_assert( !DUAL || ( PACKED && MULTI == 0 && !TRACK ), "DUAL: packed tier, one pass" );
+    constexpr int PWORDS = DUAL ? R * 1024 : profile_words<PACKED, R>();
 
-    for( int i = threadIdx.x; i < profile_words<PACKED, R>(); i += blockDim.x ) prof[i] = a.profile[i];
+    for( int i = threadIdx.x; i < PWORDS; i += blockDim.x ) prof[i] = a.profile[i];
     // Packed Needleman-Wunsch: start values of every lane's rows - H(i, -1) = gapO + (i + 1) gapE and the E entering column 0,
     // H + gapO + gapE, both minus the offset - as 128-bit entries [H | E][row quad][lane] behind the profile: a sequence start
     // costs a lane R/2 shared loads instead of 3R additions (and the WARP runs that code once per lane and sequence pair)
-    constexpr int NW_TAB = profile_words<PACKED, R>();
+    constexpr int NW_TAB = PWORDS;
     if( NW && PACKED ) {
         for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
             const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     const bool is_top = gl == 0;
     const bool is_bottom = gl == gmask;
     // packed tier: 64-bit entries [row quad][residue][lane] = two (row pair) words; wide tier: 32-bit entries [row][residue][lane]
-    constexpr int MR = PACKED ? merge_rows( R ) : 0;
+    constexpr int MR = DUAL ? R : ( PACKED ? merge_rows( R ) : 0 );   // (DUAL: every row has a 128-bit entry of ready-made words)
     // packed tier: 128-bit entries for the first MR rows, then 64-bit entries; wide tier: 32-bit entries [row][residue][lane]
     const uint32_t prof_base = (uint32_t) __cvta_generic_to_shared( prof ) + lane * ( PACKED ? 16 : 4 );
     constexpr int NQ16 = PACKED ? ( R - MR ) / 4 : 0;   // 64-bit entries (4 rows, two scores per word) after the first MR rows
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         T hd = diag;
         diag = h_in;
         if( PACKED ) {
-            const uint32_t ra = ci & 31u, rb = ( ci >> 5 ) & 31u;
+            const uint32_t ra = DUAL ? ( ci >> ( half * 5u ) ) & 31u : ci & 31u, rb = ( ci >> 5 ) & 31u;
             T hd2 = hd;
             // rows 2k, 2k+1 with their (A:B) substitution scores v0, v1
             auto dp_pair = [&]( const int k, const uint32_t v0, const uint32_t v1 ) {
@@ -260,9 +271,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             };
 #pragma unroll
             for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
-                const uint4 la = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lb = lds128( prof_base + ( rb << 9 ) + q * 16384 );
-                dp_pair( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
-                dp_pair( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+                const uint4 la = lds128( prof_base + ( ra << 9 ) + q * 16384 );
+                if( DUAL ) {
+                    dp_pair( 2 * q, la.x, la.y );
+                    dp_pair( 2 * q + 1, la.z, la.w );
+                }
+                else {
+                    const uint4 lb = lds128( prof_base + ( rb << 9 ) + q * 16384 );
+                    dp_pair( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
+                    dp_pair( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+                }
             }
 #pragma unroll
             for( int q = 0; q < NQ16; q++ ) {      // two scores per word, four rows per load
@@ -300,6 +318,27 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
 
     // NW: the lane that owns the query's last row records H at the last column of sequence A / B
     auto nw_capture = [&]( const uint32_t ci ) {
+        if( DUAL ) {   // the sequence of this launch half ends here: each query's last row may live in another lane
+            if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) {
+                uint16_t * o = (uint16_t *) ( (uint32_t *) a.out + half * a.out_stride + bnd_base + (uint32_t) ( t - gl ) );
+#pragma unroll
+                for( int which = 0; which < 2; which++ ) {
+                    if( gl == ( which ? a.cap_lane2 : a.cap_lane ) ) {
+                        const int row = which ? a.cap_row2 : a.cap_row;
+                        T sel = Hp[0];
+#pragma unroll
+                        for( int r = 1; r < R; r++ ) {
+                            T cand = Hp[r];
+                            asm volatile( "" : "+r"( cand ) );
+                            if( r == row ) sel = cand;
+                            asm volatile( "" : "+r"( sel ) );
+                        }
+                        o[which ? 0 : 1] = (uint16_t) ( which ? (uint32_t) sel & 0xffffu : (uint32_t) sel >> 16 );   // first query = high half
+                    }
+                }
+            }
+            return;
+        }
         if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
             // pick H of the query's last row without turning Hp[] into an indexable (local-memory) array:
             // a chain of predicated moves, kept opaque to the optimiser
@@ -339,7 +378,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 nsteps_cols = (int) ( bt.ncols >> 1 );
                 nsteps = nsteps_cols + gmask;
                 out_idx = (int) bt.out0;
-                half = bt.half;
+                half = DUAL ? a.dual_half : bt.half;
                 bnd_base = (uint32_t) ( bt.bnd0 >> 1 );
                 // lane gl works on column pair t - gl at step t: preload the column words of steps 0 and 1
                 w_n1 = ( gl == 0 ) ? st[0] : 0;
@@ -477,7 +516,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             }
 
             const bool b_valid = ( cib & COL_VALID ) != 0;
-            const bool slow = HAS_SLOW && ( !PACKED || !b_valid || ( NW && gl == a.cap_lane && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) );
+            const bool slow = HAS_SLOW && ( !PACKED || !b_valid ||
+                    ( NW && !DUAL && gl == a.cap_lane && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) ||
+                    ( NW && DUAL && ( gl == a.cap_lane || gl == a.cap_lane2 ) && ( cia & ( half ? COL_LAST_B : COL_LAST_A ) ) ) );
             if( slow ) {
                 // column by column: the wide tier, and NW results that must be read between the two columns - only in the
                 // lane that owns the query's last row (a sequence end in column A makes ONE lane of the group leave the
@@ -495,7 +536,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // needs neither, so the two F chains overlap.  The diagonal candidate of the NEXT row of column A
                 // (old H + substitution score) is formed before that row's H register is overwritten, so every H
                 // stays in one physical register across steps.
-                const uint32_t ra = cia & 31u, rb = ( cia >> 5 ) & 31u, sa = cib & 31u, sb = ( cib >> 5 ) & 31u;
+                const uint32_t hs = DUAL ? half * 5u : 0u;   // DUAL: the residue of this launch half's sequence
+                const uint32_t ra = ( cia >> hs ) & 31u, rb = ( cia >> 5 ) & 31u, sa = ( cib >> hs ) & 31u, sb = ( cib >> 5 ) & 31u;
                 T fa = fa_in, fb = fb_in;
                 T ha_prev = ha_in;                       // H of column A, previous row (diagonal of column B)
                 T hda = diag;                            // H of column A-1, previous row (diagonal of column A)
@@ -549,10 +591,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 // one shared load per sequence and column fetches the scores of four query rows
 #pragma unroll
                 for( int q = 0; q < MR / 4; q++ ) {   // one zero-extended score per word: merge by multiply-add
-                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lba = lds128( prof_base + ( rb << 9 ) + q * 16384 );
-                    const uint4 lab = lds128( prof_base + ( sa << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
-                    dp_pair( 2 * q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y );
-                    dp_pair( 2 * q + 1, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
+                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lab = lds128( prof_base + ( sa << 9 ) + q * 16384 );
+                    if( DUAL ) {   // the entry holds the (q1 : q2) words of four rows
+                        dp_pair( 2 * q, laa.x, laa.y, lab.x, lab.y );
+                        dp_pair( 2 * q + 1, laa.z, laa.w, lab.z, lab.w );
+                    }
+                    else {
+                        const uint4 lba = lds128( prof_base + ( rb << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
+                        dp_pair( 2 * q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y );
+                        dp_pair( 2 * q + 1, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
+                    }
                 }
 #pragma unroll
                 for( int q = 0; q < NQ16; q++ ) {      // two scores per word, four rows per load
@@ -572,7 +620,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
 
             // ---- SW results at sequence ends (rare, divergent) ----
             if( !NW ) {
-                const uint32_t last_mask = PACKED ? COL_LAST_A : ( half ? COL_LAST_B : COL_LAST_A );
+                const uint32_t last_mask = PACKED && !DUAL ? COL_LAST_A : ( half ? COL_LAST_B : COL_LAST_A );
                 s_out = A::bcast( 0 );
                 f8_out = 0x7fffffff;
                 f16_out = 0x7fffffff;
@@ -584,7 +632,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                     }
                     if( is_bottom ) {
                         if( PACKED ) {
-                            uint32_t * o = (uint32_t *) a.out + ( bnd_base + (uint32_t) ( t - gmask ) );
+                            uint32_t * o = (uint32_t *) a.out + ( DUAL ? half * a.out_stride : 0u ) + ( bnd_base + (uint32_t) ( t - gmask ) );
                             *o = a.first_pass ? (uint32_t) s_out : __vmaxs2( *o, (uint32_t) s_out );
                         }
                         else {

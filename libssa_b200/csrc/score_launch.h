@@ -12,6 +12,9 @@ int launch_score_packed( int R, bool nw, bool multi, const ScoreArgs & args, cud
 // resident CTAs per SM of the packed kernel variant (for sizing the work batches)
 int packed_blocks_per_sm( int R, bool nw, bool multi );
 int launch_score_wide( int R, bool nw, bool multi, bool track, const ScoreArgs & args, cudaStream_t stream );
+// two queries per packed word (score_kernel<..., DUAL = true>, one pass): args.dual_half selects sequence A or B of every pair
+int launch_score_dual( int R, bool nw, const ScoreArgs & args, cudaStream_t stream );
+int dual_blocks_per_sm( int R, bool nw );
 // The 32-bit tier for queries of more than one pass (wide_pipe.cu): all passes of a sequence run as a pipeline in ONE launch.
 constexpr int WIDE_PIPE_R = 16;   // rows per lane: 64 KB of profile per CTA, two CTAs per multiprocessor
 struct WidePipeArgs {

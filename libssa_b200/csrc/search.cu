@@ -142,7 +142,10 @@ struct Ctx {
     PinBuf<Batch> h_long_batches[2];
     PinBuf<uint32_t> h_profile_long[2];
     DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
-    DevBuf<int32_t> d_all_slot[2];      // batch: the gathered scores of the two queries in flight
+    DevBuf<int32_t> d_all_slot[4];      // batch: the gathered scores of the (up to four) queries in flight
+    DevBuf<int32_t> d_scores2;          // two queries per word: scores of the second query
+    DevBuf<uint32_t> d_profile_dual;
+    PinBuf<uint32_t> h_profile_dual[2];
     std::vector<uint32_t> order_tmp;
     DevBuf<Batch> d_wide_batches[2];
     DevBuf<uint32_t> d_profile_wide[2];
@@ -150,10 +153,10 @@ struct Ctx {
     DevBuf<uint32_t> d_order, d_wave_list, d_topk_ids;
     DevBuf<int32_t> d_topk_scores;
     DevBuf<SelectState> d_select;
-    PinBuf<SelectState> h_select[2];      // top-k results, per pipeline slot
-    PinBuf<uint32_t> h_topk_ids[2], h_counts[2];
-    PinBuf<int32_t> h_topk_scores[2];
-    cudaEvent_t ev_topk[2] = { nullptr, nullptr };
+    PinBuf<SelectState> h_select[4];      // top-k results, per result slot (query index & 3)
+    PinBuf<uint32_t> h_topk_ids[4], h_counts[4];
+    PinBuf<int32_t> h_topk_scores[4];
+    cudaEvent_t ev_topk[4] = { nullptr, nullptr, nullptr, nullptr };
     DevBuf<int16_t> d_nw_scratch;
     DevBuf<uint8_t> d_query;
     DevBuf<int32_t> d_matrix32;
@@ -311,7 +314,7 @@ void init_ctx( Ctx * c, int device, int rank, int world ) {
     CUDA_OK( cudaEventCreate( &c->ev_k0 ) );
     CUDA_OK( cudaEventCreate( &c->ev_k1 ) );
     CUDA_OK( cudaEventCreate( &c->ev_end ) );
-    for( int i = 0; i < 2; i++ ) CUDA_OK( cudaEventCreateWithFlags( &c->ev_topk[i], cudaEventDisableTiming ) );
+    for( int i = 0; i < 4; i++ ) CUDA_OK( cudaEventCreateWithFlags( &c->ev_topk[i], cudaEventDisableTiming ) );
     memset( &c->stats, 0, sizeof( c->stats ) );
 }
 
@@ -773,6 +776,22 @@ __global__ void unpack_scores_kernel( const uint32_t * packed, const uint64_t * 
     }
 }
 
+// Two queries per word: (q1 : q2) int16 pairs per SEQUENCE, stored by the stream position in which the sequence ends (one
+// array per launch half: sequence A resp. B of every pair) -> one int32 score per sorted position and query.
+__global__ void unpack_dual_kernel( const uint32_t * packed, uint32_t out_stride, const uint64_t * pair_col, const uint32_t * sorted_len,
+        int32_t * scores1, int32_t * scores2, uint32_t npairs, uint32_t nseq, int32_t offset ) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if( p >= npairs ) return;
+    const uint32_t wa = packed[pair_col[p + 1] / 2 - 1];
+    scores1[2 * p] = (int32_t) (int16_t) ( wa >> 16 ) + offset;
+    scores2[2 * p] = (int32_t) (int16_t) ( wa & 0xffffu ) + offset;
+    if( 2 * p + 1 < nseq ) {
+        const uint32_t wb = packed[out_stride + ( pair_col[p] + sorted_len[2 * p + 1] - 1 ) / 2];
+        scores1[2 * p + 1] = (int32_t) (int16_t) ( wb >> 16 ) + offset;
+        scores2[2 * p + 1] = (int32_t) (int16_t) ( wb & 0xffffu ) + offset;
+    }
+}
+
 // the output slots of a list of 32-bit-tier batches set to zero (the passes of the pipelined tier combine by atomicMax)
 __global__ void zero_slots_kernel( const Batch * batches, uint32_t n, int32_t * out ) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -959,6 +978,21 @@ void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G,
                 const int k = ( r - MR ) / 2;   // row pair within the 64-bit part
                 out16[( ( ( k / 2 ) * 32 + d ) * 32 + lane ) * 2 + ( k & 1 )] =
                         ( (uint32_t) (uint16_t) (int16_t) score( r + 1 ) << 16 ) | (uint32_t) (uint16_t) (int16_t) score( r );
+            }
+        }
+}
+
+// Profile of the two-queries-per-word kernels: 128-bit entries [row quad][residue][lane] of four rows, each word = (score of
+// query 1 : score of query 2) for that row and residue; rows beyond a query's end hold pad_score in its half.
+void fill_profile_dual( uint32_t * out, const uint8_t * q1, size_t len1, const uint8_t * q2, size_t len2, int G, int R, int pad_score ) {
+    for( int d = 0; d < 32; d++ )
+        for( int lane = 0; lane < 32; lane++ ) {
+            const size_t row0 = (size_t) ( lane % G ) * R;
+            for( int r = 0; r < R; r++ ) {
+                const size_t row = row0 + r;
+                const int s1 = row < len1 && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q1[row]] : pad_score;
+                const int s2 = row < len2 && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q2[row]] : pad_score;
+                out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = ( (uint32_t) (uint16_t) (int16_t) s1 << 16 ) | (uint32_t) (uint16_t) (int16_t) s2;
             }
         }
 }
@@ -1614,6 +1648,129 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     CUDA_OK( cudaEventRecord( ctx().ev_k1, ctx().stream ) );
 }
 
+// Two queries per packed word (score_kernel<..., DUAL>): both queries of a batch call against the whole shard, one pass, packed
+// tier only - every sequence is scored by two launches (sequence A resp. B of every pair), each word holding one cell of
+// query 1 and of query 2.  Applies when both queries fit one pass, every pair is statically inside int16 for the longer of
+// them and no pair is long enough to need the full-warp class next to narrow groups (dual_plan; otherwise the caller
+// scores the queries one after the other).  Scores by sorted position: ctx().d_scores (query 1), ctx().d_scores2 (query 2).
+struct DualPlan {
+    int G = 0, R = 0;
+    int32_t offset = 0;
+    int pad_score = 0;
+    int qrows_max = 0;
+    Plan pl;
+};
+
+// whether two queries of these lengths can share a scoring pass, and its shape
+bool dual_plan( size_t len1, size_t len2, bool nw, DualPlan & dp ) {
+    PackedDb & db = ctx().db;
+    const size_t nloc = db.sorted_id.size();
+    const size_t lmax = std::max( len1, len2 );
+    if( getenv( "LIBSSA_B200_NO_DUAL" ) || nloc == 0 || len1 == 0 || len2 == 0 || lmax > 1024 || ctx().world != 1 ) return false;
+    if( (int) g_gapO + (int) g_gapE > 0 || g_gapE > 0 ) return false;
+    dp.pl = make_plan( lmax );
+    if( dp.pl.npass != 1 ) return false;
+    dp.qrows_max = std::max( dp.pl.qpad, 1024 );
+    const int64_t safe = packed_safe_len( dp.pl, nw, dp.qrows_max, &dp.offset );
+    if( first_pair_not_longer( safe ) != 0 ) return false;   // some pair is not provably inside int16: single-query path (speculation / 32-bit tier)
+    int sms = 148;
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx().device );
+    // shape: G lanes x R rows with few padded rows; narrow groups only if no pair would outlast the launch on them
+    const int nopt = sizeof( PACKED_R ) / sizeof( int );
+    double best = 1e300;
+    dp.G = 0;
+    for( int g = 4; g <= 32; g *= 2 ) {
+        int r = 0;
+        for( int i = nopt - 1; i >= 0; i-- )
+            if( (size_t) g * PACKED_R[i] >= lmax ) r = PACKED_R[i];
+        if( r == 0 ) continue;
+        const int64_t long_len = g == 32 ? INT64_MAX : std::max<int64_t>( 64, (int64_t) ( (double) db.total_cols * g / ( 1165.0 * sms ) ) );
+        if( first_pair_not_longer( long_len ) != 0 ) continue;
+        double cost = ( g / 32.0 ) * ( 5.75 * r + 60 );
+        if( r > 24 ) cost *= 1.6;   // 112-128 KB of profile: one resident CTA per multiprocessor
+        if( cost < best ) {
+            best = cost;
+            dp.G = g;
+            dp.R = r;
+        }
+    }
+    if( dp.G == 0 ) return false;
+    dp.pad_score = dp.pl.pad_score;
+    if( nw ) dp.offset = nw_offset_for( dp.pl, dp.qrows_max, db.sorted_len[0] );
+    return true;
+}
+
+void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size_t len2, bool nw, const DualPlan & dp ) {
+    PackedDb & db = ctx().db;
+    const size_t nloc = db.sorted_id.size();
+    const int G = dp.G, R = dp.R;
+    const int32_t offset = dp.offset;
+    const Plan & pl = dp.pl;
+    int sms = 148;
+    cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, ctx().device );
+    if( db.batch_tables.size() >= 24 ) {
+        CUDA_OK( cudaDeviceSynchronize() );
+        for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
+        db.batch_tables.clear();
+    }
+    const int resident = dual_blocks_per_sm( R, nw );
+    const uint64_t groups = (uint64_t) sms * resident * ( SCORE_THREADS / 32 ) * ( 32 / G );
+    uint32_t batch_cols = 4096;
+    while( batch_cols > 256 && db.total_cols / batch_cols < 3 * groups ) batch_cols /= 2;
+    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, (uint32_t) std::max( 128, 16 * G ) );
+
+    const size_t words = (size_t) R * 1024;
+    ctx().h_profile_dual[g_stage_slot].reserve( words );
+    ctx().d_profile_dual.reserve( words );
+    fill_profile_dual( ctx().h_profile_dual[g_stage_slot].p, q1, len1, q2, len2, G, R, pl.pad_score );
+    CUDA_OK( cudaMemcpyAsync( ctx().d_profile_dual.p, ctx().h_profile_dual[g_stage_slot].p, words * 4, cudaMemcpyHostToDevice, ctx().stream ) );
+    ctx().stats.h2d_bytes += words * 4;
+    const uint32_t out_stride = (uint32_t) ( db.total_cols / 2 + 64 );
+    ctx().d_out_packed.reserve( 2 * (size_t) out_stride );
+    ctx().d_counter.reserve( 64 );
+    ctx().d_scores.reserve( nloc + 2 );
+    ctx().d_scores2.reserve( nloc + 2 );
+    CUDA_OK( cudaEventRecord( ctx().ev_k0, ctx().stream ) );
+    ctx().scored = true;
+    for( uint32_t half = 0; half < 2; half++ ) {
+        if( half == 1 && nloc < 2 ) break;
+        CUDA_OK( cudaMemsetAsync( ctx().d_counter.p, 0, 4, ctx().stream ) );
+        ScoreArgs a;
+        memset( &a, 0, sizeof( a ) );
+        a.stream = db.d_stream.p;
+        a.batches = bt.d_batches.p;
+        a.nbatches = (uint32_t) bt.batches.size();
+        a.counter = ctx().d_counter.p;
+        a.profile = ctx().d_profile_dual.p;
+        a.group = (uint32_t) G;
+        a.k65536 = 65536u;
+        a.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
+        a.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
+        a.gap_open_extend = (int) g_gapO + (int) g_gapE;
+        a.gap_extend = g_gapE;
+        a.gap_open = g_gapO;
+        a.offset = offset;
+        a.rowbase = 0;
+        a.cap_lane = a.cap_lane2 = -1;
+        if( nw ) {
+            a.cap_lane = (int) ( ( len1 - 1 ) / R );
+            a.cap_row = (int) ( ( len1 - 1 ) % R );
+            a.cap_lane2 = (int) ( ( len2 - 1 ) / R );
+            a.cap_row2 = (int) ( ( len2 - 1 ) % R );
+        }
+        a.first_pass = 1;
+        a.out = ctx().d_out_packed.p;
+        a.dual_half = half;
+        a.out_stride = out_stride;
+        launch_score_dual( R, nw, a, ctx().stream );
+        ctx().stats.launches++;
+    }
+    unpack_dual_kernel<<<(unsigned) ( ( db.npairs + 255 ) / 256 ), 256, 0, ctx().stream>>>( ctx().d_out_packed.p, out_stride, db.d_pair_col.p,
+            db.d_sorted_len.p, ctx().d_scores.p, ctx().d_scores2.p, (uint32_t) db.npairs, (uint32_t) nloc, offset );
+    ctx().stats.launches++;
+    CUDA_OK( cudaEventRecord( ctx().ev_k1, ctx().stream ) );
+}
+
 // ---- order emulation of the reference's narrow NW tiers (nw_sat.cuh) ----
 
 // Longest database sequence for which the saturating `bits`-wide NW kernel of the reference provably never
@@ -1873,8 +2030,19 @@ static void release_ctx( Ctx & c ) {
     c.h_cand_pos.release();
     c.h_cand_id.release();
     c.h_cand_score.release();
-    for( int i = 0; i < 2; i++ ) {
+    c.d_scores2.release();
+    c.d_profile_dual.release();
+    for( int i = 0; i < 4; i++ ) {
         c.d_all_slot[i].release();
+        c.h_select[i].release();
+        c.h_topk_ids[i].release();
+        c.h_topk_scores[i].release();
+        c.h_counts[i].release();
+        if( c.ev_topk[i] ) cudaEventDestroy( c.ev_topk[i] );
+        c.ev_topk[i] = nullptr;
+    }
+    for( int i = 0; i < 2; i++ ) {
+        c.h_profile_dual[i].release();
         c.d_wide_batches[i].release();
         c.d_profile_wide[i].release();
         for( int j = 0; j < 2; j++ ) {
@@ -1884,12 +2052,6 @@ static void release_ctx( Ctx & c ) {
         c.h_long_batches[i].release();
         c.h_profile_long[i].release();
         c.h_profile[i].release();
-        c.h_select[i].release();
-        c.h_topk_ids[i].release();
-        c.h_topk_scores[i].release();
-        c.h_counts[i].release();
-        if( c.ev_topk[i] ) cudaEventDestroy( c.ev_topk[i] );
-        c.ev_topk[i] = nullptr;
     }
     cudaEventDestroy( c.ev_begin );
     cudaEventDestroy( c.ev_k0 );
@@ -2566,42 +2728,74 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
     const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;
     uint64_t cells = 0;
-    bool armed[2] = { false, false };
+    // Units of work: two consecutive queries of the same kind share one scoring pass (two queries per packed word,
+    // score_shard_dual) where that applies, otherwise a unit is one query.  The scoring and device top-k of unit u+1 are enqueued
+    // before the host waits for unit u; result buffers are per query (index & 3), pinned upload staging per unit (u & 1).
+    struct Unit {
+        size_t first;
+        int count;
+    };
+    std::vector<Unit> units;
+    std::vector<DualPlan> plans;
+    for( size_t i = 0; i < n; ) {
+        DualPlan dp;
+        const bool pair = i + 1 < n && reqs[i].search_type == reqs[i + 1].search_type && world == 1 && g_devs.size() == 1 &&
+                dual_plan( reqs[i].frames[0].len, reqs[i + 1].frames[0].len, reqs[i].search_type == NEEDLEMAN_WUNSCH, dp );
+        units.push_back( Unit{ i, pair ? 2 : 1 } );
+        plans.push_back( dp );
+        i += pair ? 2 : 1;
+    }
+    bool armed[4] = { false, false, false, false };
     const size_t chunk = g_chunk_size;
-    auto enqueue = [&]( size_t i ) {
+    auto enqueue_selection = [&]( size_t i, const int32_t * d_all ) {
         const SearchRequest & r = reqs[i];
-        const int slot = (int) ( i & 1 );
-        g_stage_slot = slot;
+        const int rslot = (int) ( i & 3 );
         const bool nw = r.search_type == NEEDLEMAN_WUNSCH;
-        const int32_t * d_all = score_query( r.frames[0].seq, r.frames[0].len, nw );
-        // the replay path of this query, should it be needed, runs after the next query's scoring has overwritten d_all
-        ctx().d_all_slot[slot].reserve( stride * world + 2 );
-        if( nglob ) CUDA_OK( cudaMemcpyAsync( ctx().d_all_slot[slot].p, d_all, stride * world * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx().stream ) );
+        // the replay path of this query, should it be needed, runs after later scoring passes have overwritten d_all
+        ctx().d_all_slot[rslot].reserve( stride * world + 2 );
+        if( nglob ) CUDA_OK( cudaMemcpyAsync( ctx().d_all_slot[rslot].p, d_all, stride * world * sizeof( int32_t ), cudaMemcpyDeviceToDevice, ctx().stream ) );
         PackedDb::Arrival & base = arrival_for( r.bit_width, chunk, chunk <= (size_t) ARRIVAL_MAX_CHUNK );
-        armed[slot] = topk_applicable( base, r.hitcount );
-        if( armed[slot] ) enqueue_topk( d_all, base, r.hitcount, !nw && ( r.bit_width == 8 || r.bit_width == 16 ), slot );
+        armed[rslot] = topk_applicable( base, r.hitcount );
+        if( armed[rslot] ) enqueue_topk( d_all, base, r.hitcount, !nw && ( r.bit_width == 8 || r.bit_width == 16 ), rslot );
+    };
+    auto enqueue = [&]( size_t u ) {
+        const Unit & un = units[u];
+        g_stage_slot = (int) ( u & 1 );
+        const SearchRequest & r0 = reqs[un.first];
+        const bool nw = r0.search_type == NEEDLEMAN_WUNSCH;
+        if( un.count == 2 ) {
+            const SearchRequest & r1 = reqs[un.first + 1];
+            score_shard_dual( r0.frames[0].seq, r0.frames[0].len, r1.frames[0].seq, r1.frames[0].len, nw, plans[u] );
+            enqueue_selection( un.first, ctx().d_scores.p );
+            enqueue_selection( un.first + 1, ctx().d_scores2.p );
+        }
+        else
+            enqueue_selection( un.first, score_query( r0.frames[0].seq, r0.frames[0].len, nw ) );
     };
     CUDA_OK( cudaEventRecord( ctx().ev_begin, ctx().stream ) );
     enqueue( 0 );
-    for( size_t i = 0; i < n; i++ ) {
-        if( i + 1 < n ) enqueue( i + 1 );
-        const SearchRequest & r = reqs[i];
-        const int slot = (int) ( i & 1 );
-        std::vector<Hit> hits;
-        ctx().stats.overflow_8 = ctx().stats.overflow_16 = 0;
-        if( !( armed[slot] && collect_topk( r.hitcount, r.bit_width, slot, hits ) ) ) {
-            // ties straddle the cut-off (or the hit count covers the database): the arrival-order replay, from this query's
-            // own copy of the scores; it queues behind the next query's scoring
-            g_stage_slot = slot;
-            select_replay( ctx().d_all_slot[slot].p, r.frames[0].seq, r.frames[0].len, r, hits );
+    for( size_t u = 0; u < units.size(); u++ ) {
+        if( u + 1 < units.size() ) enqueue( u + 1 );
+        for( int j = 0; j < units[u].count; j++ ) {
+            const size_t i = units[u].first + j;
+            const SearchRequest & r = reqs[i];
+            const int rslot = (int) ( i & 3 );
+            std::vector<Hit> hits;
+            ctx().stats.overflow_8 = ctx().stats.overflow_16 = 0;
+            if( !( armed[rslot] && collect_topk( r.hitcount, r.bit_width, rslot, hits ) ) ) {
+                // ties straddle the cut-off (or the hit count covers the database): the arrival-order replay, from this query's
+                // own copy of the scores; it queues behind the next unit's scoring
+                g_stage_slot = (int) ( u & 1 );
+                select_replay( ctx().d_all_slot[rslot].p, r.frames[0].seq, r.frames[0].len, r, hits );
+            }
+            if( ctx().stats.overflow_8 || ctx().stats.overflow_16 )
+                print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
+                        (long) ctx().stats.overflow_8, (long) ctx().stats.overflow_16 );
+            cells += (uint64_t) r.frames[0].len * process_residues();
+            std::vector<FrameHit> fh( hits.size() );
+            for( size_t k = 0; k < hits.size(); k++ ) fh[k] = FrameHit{ (uint32_t) hits[k].db_id, 0, hits[k].score };
+            finish_results( r, fh, outs[i], ctx().stream_aux );
         }
-        if( ctx().stats.overflow_8 || ctx().stats.overflow_16 )
-            print_info( "Overflow occurred: %ld sequences were re-aligned with 16 bit, and %ld sequences with 64 bit\n",
-                    (long) ctx().stats.overflow_8, (long) ctx().stats.overflow_16 );
-        cells += (uint64_t) r.frames[0].len * process_residues();
-        std::vector<FrameHit> fh( hits.size() );
-        for( size_t j = 0; j < hits.size(); j++ ) fh[j] = FrameHit{ (uint32_t) hits[j].db_id, 0, hits[j].score };
-        finish_results( r, fh, outs[i], ctx().stream_aux );
     }
     CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     g_stage_slot = 0;

@@ -409,6 +409,38 @@ def test_batched_queries_equal_single_calls(prod, ref):
             prod.free_sequence(q)
 
 
+def test_batch_two_queries_per_word(prod, tmp_path, monkeypatch):
+    """ssa_b200_align_batch scores consecutive queries of one kind two per packed word (score_kernel<..., DUAL>, every shape:
+    groups of 4 / 8 / 16 / 32 lanes on a length-matched database): lists and alignments equal single calls, for pairs of
+    equal, similar and very different lengths, an odd query count, SW and NW; and the same batch with the pairing disabled."""
+    from libssa_b200 import synth
+    rng = np.random.default_rng(99)
+    seqs = synth.protein_db(3001, 1234, mu=float(np.log(300)), sigma=0.04, min_len=250, max_len=360, n_dup=20)
+    lens = [300, 310, 64, 350, 17, 5, 128, 128, 1000, 900, 33, 700, 250]
+    texts = [synth.random_protein(rng, n) for n in lens]
+    seqs[5] = texts[1]
+    seqs[6] = texts[0][:150] + texts[3][100:300]
+    path = tmp_path / "lm.fas"
+    synth.write_fasta(str(path), seqs)
+    prod.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+    prod.init_score_matrix(cases.MATRIX_BUILDIN, "blosum62")
+    prod.init_gap_penalties(-11, -1)
+    prod.init_db(str(path))
+    queries = [prod.init_sequence_fasta(cases.READ_FROM_STRING, t) for t in texts]
+    try:
+        for nw, bits, k, align in ((True, 16, 10, 0), (False, 16, 10, 0), (True, 16, 8, 1), (False, 8, 12, 1), (True, 8, 40, 0)):
+            single = [[_key(h, align) for h in (prod.nw_align if nw else prod.sw_align)(q, k, bits, align)] for q in queries]
+            batch = [[_key(h, align) for h in hits] for hits in prod.align_batch(queries, k, bits, align, nw=nw)]
+            assert batch == single, (nw, bits, k, align, [i for i in range(len(lens)) if batch[i] != single[i]])
+            monkeypatch.setenv("LIBSSA_B200_NO_DUAL", "1")
+            plain = [[_key(h, align) for h in hits] for hits in prod.align_batch(queries, k, bits, align, nw=nw)]
+            monkeypatch.delenv("LIBSSA_B200_NO_DUAL")
+            assert plain == single
+    finally:
+        for q in queries:
+            prod.free_sequence(q)
+
+
 def test_batched_queries_multi_frame_fallback(prod, tmp_path):
     """batches of multi-frame searches run query by query (no pipelining) and must still equal single calls"""
     import frames as F
