@@ -33,8 +33,9 @@ struct WidePipeArgs {
 };
 int launch_wide_pipe( bool nw, const WidePipeArgs & args, cudaStream_t stream );
 // launches sw32_kernel<R, multipass, nw> (packed tier, full-warp arrays, chained batches); returns the grid size used
-int launch_sw32( int R, bool nw, bool multipass, const Sw32Args & args, cudaStream_t stream );
-int sw32_blocks_per_sm( int R, bool nw, bool multipass );
+// G: lanes per array (32, or 16 - one pass only); dual: two queries per packed word (one pass only)
+int launch_sw32( int R, bool nw, bool multipass, const Sw32Args & args, cudaStream_t stream, int G = 32, bool dual = false );
+int sw32_blocks_per_sm( int R, bool nw, bool multipass, int G = 32, bool dual = false );
 }  // namespace ssa
 
 #include <cstdio>

@@ -1284,6 +1284,15 @@ bool sw32_enabled( bool nw ) {
     static const bool on = getenv( "LIBSSA_B200_NO_SW32" ) == nullptr, on_nw = getenv( "LIBSSA_B200_NO_NW32" ) == nullptr;
     return on && ( !nw || on_nw );
 }
+// whether groups of G lanes run on the chained kernel (sw32_kernel.cuh): full warps, and half warps for one-pass queries
+// (LIBSSA_B200_NO_G16=1: half warps on the generic kernel, A/B measurements)
+// Measured [B200], 375-aa query: Smith-Waterman on half-warp chains +1.6 % (570 k records) / +4 % (71 k records) over the generic
+// kernel, Needleman-Wunsch -4 % (its instantiation sits at the register limit) - so NW keeps the generic kernel for G = 16
+// unless two queries share the word (dual: +4 %).
+bool chained_shape( int G, bool nw, bool one_pass, bool dual = false ) {
+    static const bool g16 = getenv( "LIBSSA_B200_NO_G16" ) == nullptr;
+    return sw32_enabled( nw ) && ( G == 32 || ( G == 16 && one_pass && g16 && ( !nw || dual ) ) );
+}
 
 // The packed tier over one class of pairs: all passes of the query, one launch each.
 void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, const std::vector<PassLaunch> & passes,
@@ -1306,7 +1315,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
     w0 = 0;
     for( int p = 0; p < npass; p++ ) {
         const PassLaunch & ps = passes[p];
-        if( ps.G == 32 && sw32_enabled( nw ) ) {
+        if( chained_shape( ps.G, nw, npass == 1 ) ) {
             // Full-warp arrays: the specialised kernel (sw32_kernel.cuh).  Consecutive passes of one shape
             // over the same batches - the full passes of a long query - are ONE launch: the kernel chains them itself, a batch
             // of pass p+1 waits only for the same batch of pass p.  (LIBSSA_B200_PASS_PER_LAUNCH=1: one launch per pass.)
@@ -1350,13 +1359,13 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
                 s32.gap_extend = g_gapE;
                 s32.offset = offset;
                 for( int c = p; c < p + run; c++ )   // the pass (of this launch) that holds the query's last row
-                    if( passes[c].rowbase <= qlen - 1 && qlen - 1 < passes[c].rowbase + (size_t) 32 * ps.R ) {
+                    if( passes[c].rowbase <= qlen - 1 && qlen - 1 < passes[c].rowbase + (size_t) ps.G * ps.R ) {
                         s32.cap_pass = c;
                         s32.cap_lane = (int) ( ( qlen - 1 - passes[c].rowbase ) / ps.R );
                         s32.cap_row = (int) ( ( qlen - 1 - passes[c].rowbase ) % ps.R );
                     }
             }
-            launch_sw32( ps.R, nw, multi, s32, stream );
+            launch_sw32( ps.R, nw, multi && ps.G == 32, s32, stream, ps.G );
             ctx().stats.launches++;
             w0 += (size_t) run * packed_profile_words( ps.R );
             p += run - 1;
@@ -1527,7 +1536,9 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
             const size_t pl_end = std::max( p_safe, first_pair_not_longer( long_len ) );
             const double cols_long = (double) ( db.pair_col[pl_end] - db.pair_col[p_safe] );
             const double cols_bulk = (double) ( db.total_cols - db.pair_col[pl_end] );
-            const double cost = cols_bulk * ( g / 32.0 ) * ( 7.5 * r + 60 ) + cols_long * ( 7.5 * r32 + 60 );
+            // per-step work around the recurrence: ~90 instructions on the chained kernel (sw32_kernel.cuh), ~140 on the generic one
+            const double frame = chained_shape( g, nw, true ) ? 90 : 140, frame32 = sw32_enabled( nw ) ? 90 : 140;
+            const double cost = cols_bulk * ( g / 32.0 ) * ( 7.5 * r + frame ) + cols_long * ( 7.5 * r32 + frame32 );
             if( cost < best ) {
                 best = cost;
                 G = g;
@@ -1541,8 +1552,8 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     // batch size of the bulk class: at least ~3 batches per resident group of lanes, 256..4096 columns (powers of two, cached)
     // Smith-Waterman on full-warp arrays runs on sw32_kernel: its warps chain their batches (no wavefront fill per batch), so
     // the batches can be small - at least ~8 per warp, down to 128 columns at the end of the queue
-    const bool chained = G == 32 && sw32_enabled( nw );
-    const int resident = chained ? sw32_blocks_per_sm( R, nw, npass > 1 ) : packed_blocks_per_sm( R, nw, npass > 1 );
+    const bool chained = chained_shape( G, nw, npass == 1 );
+    const int resident = chained ? sw32_blocks_per_sm( R, nw, npass > 1, G ) : packed_blocks_per_sm( R, nw, npass > 1 );
     const uint64_t groups = (uint64_t) sms * resident * ( SCORE_THREADS / 32 ) * ( 32 / G );
     uint32_t batch_cols = chained ? 2048 : 4096;
     // (with the shrinking tail of batch_table the choice is flat between 2 and 12 batches per group [B200]; fewer, longer batches
@@ -1615,7 +1626,7 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
                 continue;
             }
             // another shape has another number of resident groups: its own batches over the same pairs
-            const bool ps_chained = ps.G == 32 && sw32_enabled( nw );
+            const bool ps_chained = chained_shape( ps.G, nw, false );
             const int ps_resident = ps_chained ? sw32_blocks_per_sm( ps.R, nw, true ) : packed_blocks_per_sm( ps.R, nw, true );
             const uint64_t ps_groups = (uint64_t) sms * ps_resident * ( SCORE_THREADS / 32 ) * ( 32 / ps.G );
             uint32_t ps_cols = ps_chained ? 2048 : 4096;
@@ -1713,11 +1724,13 @@ void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size
         for( auto & kv : db.batch_tables ) kv.second.d_batches.release();
         db.batch_tables.clear();
     }
-    const int resident = dual_blocks_per_sm( R, nw );
+    // arrays of 16 / 32 lanes run on the chained kernel (small batches, at least ~8 per array), narrower ones on the generic kernel
+    const bool chained = chained_shape( G, nw, true, true ) && !getenv( "LIBSSA_B200_NO_DUAL_CHAINED" );
+    const int resident = chained ? sw32_blocks_per_sm( R, nw, false, G, true ) : dual_blocks_per_sm( R, nw );
     const uint64_t groups = (uint64_t) sms * resident * ( SCORE_THREADS / 32 ) * ( 32 / G );
-    uint32_t batch_cols = 4096;
-    while( batch_cols > 256 && db.total_cols / batch_cols < 3 * groups ) batch_cols /= 2;
-    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, (uint32_t) std::max( 128, 16 * G ) );
+    uint32_t batch_cols = chained ? 2048 : 4096;
+    while( batch_cols > 256 && db.total_cols / batch_cols < ( chained ? 8 : 3 ) * groups ) batch_cols /= 2;
+    PackedDb::BatchTable & bt = batch_table( batch_cols, 0, (uint32_t) groups, chained ? 128u : (uint32_t) std::max( 128, 16 * G ) );
 
     const size_t words = (size_t) R * 1024;
     ctx().h_profile_dual[g_stage_slot].reserve( words );
@@ -1735,6 +1748,36 @@ void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size
     for( uint32_t half = 0; half < 2; half++ ) {
         if( half == 1 && nloc < 2 ) break;
         CUDA_OK( cudaMemsetAsync( ctx().d_counter.p, 0, 4, ctx().stream ) );
+        if( chained ) {
+            Sw32Args s32;
+            memset( &s32, 0, sizeof( s32 ) );
+            s32.stream32 = (const uint32_t *) db.d_stream.p;
+            s32.batches = bt.d_batches.p;
+            s32.nbatches = (uint32_t) bt.batches.size();
+            s32.counters = ctx().d_counter.p;
+            s32.profile = ctx().d_profile_dual.p;
+            s32.k65536 = 65536u;
+            s32.qr_word = (uint32_t) (uint16_t) (int16_t) ( (int) g_gapO + (int) g_gapE ) * 0x10001u;
+            s32.rg_word = (uint32_t) (uint16_t) (int16_t) (int) g_gapE * 0x10001u;
+            s32.npass = 1;
+            s32.out_by_col = ctx().d_out_packed.p;
+            s32.gap_open = g_gapO;
+            s32.gap_extend = g_gapE;
+            s32.offset = offset;
+            s32.cap_pass = nw ? 0 : -1;
+            s32.cap_lane = s32.cap_lane2 = -1;
+            if( nw ) {
+                s32.cap_lane = (int) ( ( len1 - 1 ) / R );
+                s32.cap_row = (int) ( ( len1 - 1 ) % R );
+                s32.cap_lane2 = (int) ( ( len2 - 1 ) / R );
+                s32.cap_row2 = (int) ( ( len2 - 1 ) % R );
+            }
+            s32.dual_half = half;
+            s32.out_stride = out_stride;
+            launch_sw32( R, nw, false, s32, ctx().stream, G, true );
+            ctx().stats.launches++;
+            continue;
+        }
         ScoreArgs a;
         memset( &a, 0, sizeof( a ) );
         a.stream = db.d_stream.p;

@@ -3,7 +3,8 @@
 // chunk loop).  Same recurrence and same data as score_kernel.cuh (which keeps the narrow groups, the 32-bit tier and the
 // tracker); what is different is everything AROUND the recurrence - that was 143 of 591 instructions per step of 64 packed words:
 //
-//   * one warp = one array of 32 lanes x R rows, known at compile time;
+//   * one warp = one array of 32 lanes x R rows (or, for queries of up to 16 x 32 rows, two independent arrays of 16 lanes with
+//     their own chains and rings), known at compile time;
 //   * the work batches of a warp are CHAINED: the warp runs on a virtual step axis on which its batches follow each other
 //     without a gap, lane l works on virtual step T - l, so the 32-lane wavefront fills and drains once per launch instead
 //     of once per batch, and batches can be small (fine-grained balance of the work queue at no cost);
@@ -29,8 +30,11 @@
 
 namespace ssa {
 
-constexpr int SW32_RING = 128;        // steps a warp's ring holds (power of two): 64 ahead of the top lane, 31 behind it, one block of slack
-constexpr int SW32_MIN_STEPS = 64;    // virtual length of a batch: a block of 32 steps crosses at most one batch boundary
+// An array of G lanes (G = 32: the warp; G = 16: two independent arrays per warp, one pass only) stages its steps in blocks of
+// G, two blocks ahead; its ring holds 4 G steps (2 G ahead of the top lane, G - 1 behind it, one block being written); a batch
+// occupies at least 2 G virtual steps, so a block crosses at most one batch boundary.
+__host__ __device__ constexpr int sw32_ring( int G ) { return 4 * G; }
+__host__ __device__ constexpr int sw32_min_steps( int G ) { return 2 * G; }
 constexpr uint32_t SW32_IDLE = 0xffffffffu;
 constexpr int SW32_MAX_PASSES = 32;   // passes one launch can chain (counters live in one small array)
 
@@ -53,14 +57,21 @@ struct Sw32Args {
     int32_t offset;                 // values are stored minus this offset (centres the value range on 0)
     int32_t cap_pass;               // pass of the QUERY (not of the launch) that holds the query's last row ...
     int32_t cap_lane, cap_row;      // ... and the lane / row in the lane
+    // DUAL (two QUERIES per packed word, score_kernel.cuh): one launch per sequence of the pairs
+    uint32_t dual_half;             // 0 = sequence A of every pair (residue bits 0-4), 1 = sequence B (bits 5-9)
+    uint32_t out_stride;            // words between the result arrays of the two launch halves
+    int32_t cap_lane2, cap_row2;    // NW: lane / row of the second query's last row (cap_lane / cap_row: the first query's)
 };
 
 // words of shared memory per warp for the ring: column words, stream positions, boundary entries
-template<bool MULTIPASS> __host__ __device__ constexpr int sw32_ring_words() { return 2 * SW32_RING + ( MULTIPASS ? 5 * SW32_RING : 0 ) + 16; }
+template<bool MULTIPASS, int G = 32> __host__ __device__ constexpr int sw32_ring_words() {
+    return 2 * sw32_ring( G ) + ( MULTIPASS ? 5 * sw32_ring( G ) : 0 ) + 16;
+}
 // Needleman-Wunsch: start values of a lane's rows (H(i, -1) and the E entering column 0), [H | E][row quad][lane] as 128-bit entries
 template<int R> __host__ __device__ constexpr int sw32_nw_table_words() { return 2 * R * 32; }
-template<int R, bool MULTIPASS, bool NW = false> __host__ __device__ constexpr int sw32_smem_bytes() {
-    return ( profile_words<true, R>() + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>() + ( NW ? sw32_nw_table_words<R>() : 0 ) ) * 4;
+template<int R, bool DUAL> __host__ __device__ constexpr int sw32_profile_words() { return DUAL ? R * 1024 : profile_words<true, R>(); }
+template<int R, bool MULTIPASS, bool NW = false, int G = 32, bool DUAL = false> __host__ __device__ constexpr int sw32_smem_bytes() {
+    return ( sw32_profile_words<R, DUAL>() + ( SCORE_THREADS / G ) * sw32_ring_words<MULTIPASS, G>() + ( NW ? sw32_nw_table_words<R>() : 0 ) ) * 4;
 }
 
 __device__ __forceinline__ void cp_async4( uint32_t smem_addr, const void * gmem ) {
@@ -84,36 +95,46 @@ __device__ __forceinline__ void sts128( uint32_t addr, uint4 v ) {
     asm volatile( "st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"( addr ), "r"( v.x ), "r"( v.y ), "r"( v.z ), "r"( v.w ) : "memory" );
 }
 
-template<int R, bool MULTIPASS, bool NW>
+template<int R, bool MULTIPASS, bool NW, int G = 32, bool DUAL = false>
 __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_kernel( const Sw32Args a ) {
     typedef Arith<true> A;
     typedef uint32_t T;
+    static_assert( G == 32 || G == 16, "arrays of 32 or 16 lanes" );
+    static_assert( !MULTIPASS || ( G == 32 && !DUAL ), "several passes: full-warp arrays, one query per word" );
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int PW = profile_words<true, R>();
-    constexpr int MR = merge_rows( R );
+    constexpr int PW = sw32_profile_words<R, DUAL>();
+    constexpr int MR = DUAL ? R : merge_rows( R );   // (DUAL: every row has a 128-bit entry of ready-made (q1 : q2) words)
     constexpr int NQ16 = ( R - MR ) / 4;
+    constexpr int RING = sw32_ring( G ), BLK = G, MIN_STEPS = sw32_min_steps( G );
+    constexpr int RW = sw32_ring_words<MULTIPASS, G>();   // shared-memory words of one array's ring
     extern __shared__ uint32_t smem[];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & ( G - 1 );                       // lane within the array
+    const int grp = threadIdx.x / G;                       // array within the CTA
+    const unsigned gmask = G == 32 ? FULL : 0xffffu << ( lane & 16 );   // the lanes of this array
     {   // every ring slot idle: lanes below the top one start on steps "before the launch"
-        uint32_t * ring = smem + PW + warp * sw32_ring_words<MULTIPASS>();
-        for( int i = lane; i < sw32_ring_words<MULTIPASS>(); i += 32 ) ring[i] = 0;
+        uint32_t * ring = smem + PW + grp * RW;
+        for( int i = gl; i < RW; i += G ) ring[i] = 0;
     }
 
     const uint32_t smem_base = (uint32_t) __cvta_generic_to_shared( smem );
-    const uint32_t ring_w = smem_base + ( PW + warp * sw32_ring_words<MULTIPASS>() ) * 4;   // [RING] column words of the step
-    const uint32_t ring_g = ring_w + SW32_RING * 4;                                          // [RING] column pair index in the stream
-    const uint32_t ring_b = ring_g + SW32_RING * 4;                                          // [RING] boundary entry (MULTIPASS)
-    const uint32_t ring_e = ring_b + SW32_RING * 16;                                         // [RING] batch + 1 on its last step (MULTIPASS)
-    const uint32_t ring_ws = ring_w + ( sw32_ring_words<MULTIPASS>() - 16 ) * 4;             // [12] the warp's batch bookkeeping (WS_*)
-    const uint32_t ring_cap = ring_w + ( sw32_ring_words<MULTIPASS>() - 4 ) * 4;             // NW: score of sequence B until the pair ends
-    constexpr int NW_TAB = PW + ( SCORE_THREADS / 32 ) * sw32_ring_words<MULTIPASS>();        // first word of the NW start-value table
+    const uint32_t ring_w = smem_base + ( PW + grp * RW ) * 4;                               // [RING] column words of the step
+    const uint32_t ring_g = ring_w + RING * 4;                                               // [RING] column pair index in the stream
+    const uint32_t ring_b = ring_g + RING * 4;                                               // [RING] boundary entry (MULTIPASS)
+    const uint32_t ring_e = ring_b + RING * 16;                                              // [RING] batch + 1 on its last step (MULTIPASS)
+    const uint32_t ring_ws = ring_w + ( RW - 16 ) * 4;                                       // [12] the array's batch bookkeeping (WS_*)
+    const uint32_t ring_cap = ring_w + ( RW - 4 ) * 4;                                       // NW: score of sequence B until the pair ends
+    constexpr int NW_TAB = PW + ( SCORE_THREADS / G ) * RW;                                  // first word of the NW start-value table
     const uint32_t nw_tab = smem_base + NW_TAB * 4 + lane * 16;
     const uint32_t prof_base = smem_base + lane * 16;            // 128-bit entries of the first MR rows
     const uint32_t prof_base16 = smem_base + MR * 4096 + lane * 8;   // 64-bit entries of the other rows
     const uint32_t K65536 = a.k65536;
     const T QR = a.qr_word, RG = a.rg_word;
-    const bool is_top = lane == 0, is_bottom = lane == 31;
+    const bool is_top = gl == 0, is_bottom = gl == G - 1;
+    const uint32_t hs = DUAL ? a.dual_half * 5u : 0u;                                        // DUAL: which residue of a column word
+    const uint32_t end_mask = DUAL ? ( a.dual_half ? COL_LAST_B : COL_LAST_A ) : COL_LAST_A; // the column that ends what this launch scores
+    uint32_t * const out = a.out_by_col + ( DUAL ? a.dual_half * a.out_stride : 0u );
 
     T Hp[R], E[R];
 #pragma unroll
@@ -157,24 +178,24 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         uint32_t b = 0xffffffffu;
         if( !ws_get( WS_DRY ) ) {
             if( is_top ) b = atomicAdd( counter, 1u );
-            b = __shfl_sync( FULL, b, 0 );
+            b = __shfl_sync( gmask, b, lane & ~( G - 1 ) );
         }
         uint32_t e, n = 0, g = 0, bidx = 0;
         if( b >= a.nbatches ) {
             ws_set( WS_DRY, 1 );
-            e = begin + SW32_MIN_STEPS;
+            e = begin + MIN_STEPS;
         }
         else {
             const Batch bt = a.batches[b];
             n = bt.ncols >> 1;
             g = (uint32_t) ( bt.col0 >> 1 );
             bidx = b;
-            e = begin + max( n, (uint32_t) SW32_MIN_STEPS );
+            e = begin + max( n, (uint32_t) MIN_STEPS );
             ws_set( WS_LAST, e );
             if( MULTIPASS && pp > 0 ) {   // the previous pass of this launch must have finished this batch (its boundary row, its result)
                 if( is_top )
                     while( ld_acquire( a.done + b ) < pp ) __nanosleep( 200 );
-                __syncwarp();
+                __syncwarp( gmask );
             }
         }
         ws_set( which ? WS_NXT_E : WS_CUR_E, e );
@@ -184,10 +205,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         return e;
     };
 
-    // stages the 32 virtual steps [v0, v0 + 32): lane l prepares step v0 + l
+    // stages the G virtual steps [v0, v0 + G) of this array: its lane l prepares step v0 + l
     auto stage = [&]( const uint32_t v0 ) {
-        const uint32_t v = v0 + lane;
-        const uint32_t slot = v & ( SW32_RING - 1 );
+        const uint32_t v = v0 + gl;
+        const uint32_t slot = v & ( RING - 1 );
         const uint32_t cur_e = ws_get( WS_CUR_E );
         uint32_t c, n, g, bidx;
         if( v < cur_e ) {
@@ -219,17 +240,17 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
             sts32( ring_g + slot * 4, SW32_IDLE );
         }
         cp_async_commit();
-        if( v0 + 32 >= cur_e ) {   // the front leaves the current batch: the next one becomes current, another is pulled
-            __syncwarp();          // (every lane has read the old values)
+        if( v0 + BLK >= cur_e ) {   // the front leaves the current batch: the next one becomes current, another is pulled
+            __syncwarp( gmask );    // (every lane has read the old values)
             const uint32_t nxt_e = ws_get( WS_NXT_E ), nxt_n = ws_get( WS_NXT_N ), nxt_g = ws_get( WS_NXT_G ), nxt_b = ws_get( WS_NXT_B );
-            __syncwarp();
+            __syncwarp( gmask );
             ws_set( WS_CUR_S, cur_e );
             ws_set( WS_CUR_E, nxt_e );
             ws_set( WS_CUR_N, nxt_n );
             ws_set( WS_CUR_G, nxt_g );
             ws_set( WS_CUR_B, nxt_b );
             fetch( nxt_e, 1 );
-            __syncwarp();
+            __syncwarp( gmask );
         }
     };
 
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     if( NW ) {   // start values of this pass' rows: H(i, -1) = gapO + (i + 1) gapE, E = H + gapO + gapE (both minus the offset)
         for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
             const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;   // word i of the H half: [row quad][lane][row in quad]
-            const int row = (int) ( a.pass0 + pp ) * 32 * R + l * R + r;
+            const int row = (int) ( a.pass0 + pp ) * 32 * R + ( l & ( G - 1 ) ) * R + r;
             const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
             smem[NW_TAB + i] = A::bcast( h );
             smem[NW_TAB + R * 32 + i] = A::bcast( h + a.gap_open + a.gap_extend );
@@ -258,7 +279,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         bnd_out = MULTIPASS && ( pp + 1 < a.npass || a.more_passes ) ? ( ( abs_pass & 1 ) ? a.bnd1 : a.bnd0 ) : nullptr;
         publish = MULTIPASS && pp + 1 < a.npass;
         counter = a.counters + pp;
-        if( NW ) is_cap = (int) abs_pass == a.cap_pass && lane == a.cap_lane;
+        if( NW ) is_cap = (int) abs_pass == a.cap_pass && ( gl == a.cap_lane || ( DUAL && gl == a.cap_lane2 ) );
     }
     // the virtual axis simply continues: the steps already staged beyond t0 are idle ones and are staged again
     __syncwarp();
@@ -269,11 +290,32 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     fetch( fetch( t0, 0 ), 1 );
     __syncwarp();
     stage( t0 );
-    stage( t0 + 32 );
+    stage( t0 + BLK );
 
     // Needleman-Wunsch: the lane that owns the query's last row records H of that row at the last column of sequence B / A
     // (the score of B waits in shared memory until the pair ends)
     auto nw_capture = [&]( const uint32_t ci, const uint32_t slot4 ) {
+        if( DUAL ) {   // the sequence this launch scores ends here: each query's last row may live in another lane
+            if( ci & end_mask ) {
+                uint16_t * o = (uint16_t *) ( out + lds32( ring_g + slot4 ) );
+#pragma unroll
+                for( int which = 0; which < 2; which++ ) {
+                    if( gl == ( which ? a.cap_lane2 : a.cap_lane ) ) {
+                        const int row = which ? a.cap_row2 : a.cap_row;
+                        T sel = Hp[0];
+#pragma unroll
+                        for( int r = 1; r < R; r++ ) {
+                            T cand = Hp[r];
+                            asm volatile( "" : "+r"( cand ) );
+                            if( r == row ) sel = cand;
+                            asm volatile( "" : "+r"( sel ) );
+                        }
+                        o[which ? 0 : 1] = (uint16_t) ( which ? sel & 0xffffu : sel >> 16 );   // first query = high half
+                    }
+                }
+            }
+            return;
+        }
         if( ci & ( COL_LAST_A | COL_LAST_B ) ) {
             // H of the query's last row without turning Hp[] into an indexable (local-memory) array: a chain of predicated moves
             T sel = Hp[0];
@@ -285,28 +327,31 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 asm volatile( "" : "+r"( sel ) );
             }
             if( ci & COL_LAST_B ) sts32( ring_cap, sel );
-            if( ci & COL_LAST_A ) a.out_by_col[lds32( ring_g + slot4 )] = __byte_perm( lds32( ring_cap ), sel, 0x7610 );
+            if( ci & COL_LAST_A ) out[lds32( ring_g + slot4 )] = __byte_perm( lds32( ring_cap ), sel, 0x7610 );
         }
     };
 
-    for( ;; t0 += 32 ) {
-        stage( t0 + 64 );
+    for( ;; t0 += BLK ) {
+        stage( t0 + 2 * BLK );
         cp_async_wait<2>();     // everything but the two youngest blocks has landed: block t0 is complete
         __syncwarp();
-        if( ws_get( WS_DRY ) && t0 >= ws_get( WS_LAST ) + 32 ) break;   // the bottom lane has passed the last real step
+        {   // the bottom lane has passed the last real step (of every array of the warp)
+            const bool fin = ws_get( WS_DRY ) && t0 >= ws_get( WS_LAST ) + BLK;
+            if( G == 32 ? fin : __all_sync( FULL, fin ) ) break;
+        }
 
 #pragma unroll 1
-        for( uint32_t t = t0; t < t0 + 32; t++ ) {
-            const uint32_t slot4 = ( ( t - lane ) & ( SW32_RING - 1 ) ) * 4;   // lane l works on virtual step t - l
+        for( uint32_t t = t0; t < t0 + BLK; t++ ) {
+            const uint32_t slot4 = ( ( t - gl ) & ( RING - 1 ) ) * 4;   // lane l of an array works on virtual step t - l
             const uint32_t w = lds32( ring_w + slot4 );
             const uint32_t cia = w & 0xffffu, cib = w >> 16;
 
-            T ha_in = __shfl_up_sync( FULL, ha_out, 1 );
-            T fa_in = __shfl_up_sync( FULL, fa_out, 1 );
-            T hb_in = __shfl_up_sync( FULL, hb_out, 1 );
-            T fb_in = __shfl_up_sync( FULL, fb_out, 1 );
+            T ha_in = __shfl_up_sync( FULL, ha_out, 1, G );
+            T fa_in = __shfl_up_sync( FULL, fa_out, 1, G );
+            T hb_in = __shfl_up_sync( FULL, hb_out, 1, G );
+            T fb_in = __shfl_up_sync( FULL, fb_out, 1, G );
             T s_in = 0;
-            if( !NW ) s_in = __shfl_up_sync( FULL, s_out, 1 );
+            if( !NW ) s_in = __shfl_up_sync( FULL, s_out, 1, G );
             if( is_top ) {
                 if( MULTIPASS && !( NW && first_pass ) ) {
                     const uint4 b = lds128( ring_b + slot4 * 4 );
@@ -349,7 +394,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                             E[4 * q + 2] = e.z;
                             E[4 * q + 3] = e.w;
                         }
-                        const int row0 = (int) ( a.pass0 + pp ) * 32 * R + lane * R;
+                        const int row0 = (int) ( a.pass0 + pp ) * 32 * R + gl * R;
                         diag = A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset );
                     }
                     else {
@@ -362,8 +407,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                         S = 0;
                     }
                 }
-                const uint32_t ra = cia & 31u, rb = ( cia >> 5 ) & 31u, sa = cib & 31u, sb = ( cib >> 5 ) & 31u;
-                if( NW && is_cap && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) {
+                const uint32_t ra = ( cia >> hs ) & 31u, rb = ( cia >> 5 ) & 31u, sa = ( cib >> hs ) & 31u, sb = ( cib >> 5 ) & 31u;
+                if( NW && is_cap && ( cia & ( DUAL ? end_mask : ( COL_LAST_A | COL_LAST_B ) ) ) ) {
                     // ---- Needleman-Wunsch, the lane with the query's last row, a sequence ends in the FIRST column of the step:
                     // the result has to be read between the two columns, so this lane (alone) goes column by column ----
                     auto single_column = [&]( const uint32_t r0, const uint32_t r1, const T h_in, const T f_in, T & h_last, T & f_last ) {
@@ -386,9 +431,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                         };
 #pragma unroll
                         for( int q = 0; q < MR / 4; q++ ) {
-                            const uint4 la = lds128( prof_base + ( r0 << 9 ) + q * 16384 ), lb = lds128( prof_base + ( r1 << 9 ) + q * 16384 );
-                            dp_pair1( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
-                            dp_pair1( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+                            const uint4 la = lds128( prof_base + ( r0 << 9 ) + q * 16384 );
+                            if( DUAL ) {
+                                dp_pair1( 2 * q, la.x, la.y );
+                                dp_pair1( 2 * q + 1, la.z, la.w );
+                            }
+                            else {
+                                const uint4 lb = lds128( prof_base + ( r1 << 9 ) + q * 16384 );
+                                dp_pair1( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
+                                dp_pair1( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
+                            }
                         }
 #pragma unroll
                         for( int q = 0; q < NQ16; q++ ) {
@@ -449,10 +501,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 };
 #pragma unroll
                 for( int q = 0; q < MR / 4; q++ ) {
-                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lba = lds128( prof_base + ( rb << 9 ) + q * 16384 );
-                    const uint4 lab = lds128( prof_base + ( sa << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
-                    dp_pair( 2 * q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y );
-                    dp_pair( 2 * q + 1, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
+                    const uint4 laa = lds128( prof_base + ( ra << 9 ) + q * 16384 ), lab = lds128( prof_base + ( sa << 9 ) + q * 16384 );
+                    if( DUAL ) {   // the entry holds the (q1 : q2) words of four rows
+                        dp_pair( 2 * q, laa.x, laa.y, lab.x, lab.y );
+                        dp_pair( 2 * q + 1, laa.z, laa.w, lab.z, lab.w );
+                    }
+                    else {
+                        const uint4 lba = lds128( prof_base + ( rb << 9 ) + q * 16384 ), lbb = lds128( prof_base + ( sb << 9 ) + q * 16384 );
+                        dp_pair( 2 * q, laa.x * K65536 + lba.x, laa.y * K65536 + lba.y, lab.x * K65536 + lbb.x, lab.y * K65536 + lbb.y );
+                        dp_pair( 2 * q + 1, laa.z * K65536 + lba.z, laa.w * K65536 + lba.w, lab.z * K65536 + lbb.z, lab.w * K65536 + lbb.w );
+                    }
                 }
 #pragma unroll
                 for( int q = 0; q < NQ16; q++ ) {
@@ -471,10 +529,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 }
 
                 // ---- the pair ends in this step: the running maximum travels down the lanes with the wavefront ----
-                if( !NW && ( ( cia | cib ) & COL_LAST_A ) ) {
+                if( !NW && ( ( cia | cib ) & end_mask ) ) {
                     s_out = A::max2( s_in, S );
                     if( is_bottom ) {   // (the earlier pass may have run on another SM: read around L1)
-                        uint32_t * o = a.out_by_col + lds32( ring_g + slot4 );
+                        uint32_t * o = out + lds32( ring_g + slot4 );
                         *o = first_pass ? s_out : __vmaxs2( __ldcg( o ), s_out );
                     }
                 }

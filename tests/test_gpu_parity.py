@@ -113,13 +113,15 @@ def test_exact_scores_vs_oracle_port(prod, port, tmp_path, qlen):
         prod.free_sequence(qh)
 
 
+@pytest.mark.parametrize("G", [32, 16])
 @pytest.mark.parametrize("R", [4, 8, 12, 16, 20, 24, 28, 32])
-def test_full_warp_kernel_every_shape(prod, port, tmp_path, monkeypatch, R):
-    """sw32_kernel<R, MULTIPASS, NW>: every rows-per-lane instantiation forced with LIBSSA_B200_SHAPE=32,R, one pass (query fills
-    the array, ends in its last / first / a middle row) and several passes, SW and NW, pairs of equal / odd / even lengths"""
+def test_full_warp_kernel_every_shape(prod, port, tmp_path, monkeypatch, R, G):
+    """sw32_kernel<R, MULTIPASS, NW, G>: every rows-per-lane instantiation forced with LIBSSA_B200_SHAPE=G,R - arrays of 32 and of 16
+    lanes (two chains per warp) - one pass (query fills the array, ends in its last / first / a middle row) and several passes
+    (always full warps), SW and NW, pairs of equal / odd / even lengths"""
     from libssa_b200 import synth
-    rng = np.random.default_rng(100 + R)
-    monkeypatch.setenv("LIBSSA_B200_SHAPE", "32,%d" % R)
+    rng = np.random.default_rng(100 + R + G)
+    monkeypatch.setenv("LIBSSA_B200_SHAPE", "%d,%d" % (G, R))
     base = synth.random_protein(rng, 3 * 32 * R)
     seqs = synth.protein_db(200, 7 * R, query=base[:32 * R], homolog_frac=0.15, n_dup=8, mu=4.6, sigma=0.9, min_len=1, max_len=2500)
     seqs += [base[:40], base[:40], base[:41], base[5:46], base[:1], base[:2], base[:32 * R], base[:32 * R + 1]]   # equal, odd/even neighbours
@@ -131,7 +133,7 @@ def test_full_warp_kernel_every_shape(prod, port, tmp_path, monkeypatch, R):
     prod.init_score_matrix(cases.MATRIX_BUILDIN, "blosum62")
     prod.init_gap_penalties(-11, -1)
     prod.init_db(str(path))
-    for qlen in (32 * R, 32 * R - R, 32 * R - R + 1, 17 * R + 3, 32 * R + 1, 2 * 32 * R + R // 2 + 1, 3 * 32 * R):
+    for qlen in (G * R, G * R - R, G * R - R + 1, (G // 2 + 1) * R + 3, G * R + 1, 2 * 32 * R + R // 2 + 1, 3 * 32 * R):
         q = base[:qlen]
         qc = port.map_query(q, False)
         qh = prod.init_sequence_fasta(cases.READ_FROM_STRING, q)
