@@ -266,7 +266,7 @@ def peak_gcups(sm_mhz):
 def roofline_block(cells_local, kernel_s, sm_mhz, extra=None):
     peak = peak_gcups(sm_mhz)
     achieved = cells_local / kernel_s / 1e9 if kernel_s > 0 else 0.0
-    r = {"bound": "int_alu", "kernel": "ssa::score_kernel<PACKED,...> (s16x2, DPX)", "achieved": round(achieved, 1),
+    r = {"bound": "int_alu", "kernel": "ssa::sw32_kernel<R, MULTIPASS, NW, G, DUAL> / ssa::score_kernel<PACKED, ...> (s16x2, DPX)", "achieved": round(achieved, 1),
          "peak": round(peak, 1), "unit": "GCUPS", "frac": round(achieved / peak, 4),
          "peak_formula": "SMs x f_clk x L x c / I = %d x %.0f MHz x %d lane-ops/clk/SM x %d cells/word / %.1f ALU-pipe ops/word"
                          % (SM_COUNT, sm_mhz, LANE_OPS_PER_CLK_PER_SM, CELLS_PER_WORD, ALU_OPS_PER_WORD),
@@ -349,7 +349,10 @@ def config2_record(lib, L, ref, sm_mhz, cores):
         "e2e_single_calls": {"value": round(cells_ns / t_single / 1e9, 1), "unit": "GCUPS", "ms_per_query": round(t_single / NS * 1e3, 3),
                              "note": "one nw_align call per query (the reference API), %d-query subset" % NS},
         "gpu_launches": launches,
-        "roofline": roofline_block(cells_ns, kernel_ms / 1e3, sm_mhz, {"note": "kernel time of the %d single calls" % NS}),
+        "roofline": roofline_block(cells, dev_score_s, sm_mhz, {
+            "note": "device time of the batch call (scoring two queries per word, selection, copies) against the Smith-Waterman "
+                    "roofline of one query per word (4.5 ALU-pipe instructions per word; the two-query NW recurrence needs 3)",
+            "single_call_kernel_gcups": round(cells_ns / (kernel_ms / 1e3) / 1e9, 1) if kernel_ms > 0 else None}),
     }
     parity = {}
     if ref is not None:
@@ -579,9 +582,10 @@ def run_ours(steps, warmup, n_gpus, per_config, parity_checks=True):
             "clocks": clocks,
             "roofline": roofline_block(local_cells, m["kernel_s"], sm_mhz, {
                 "traffic": traffic,
-                "traffic_note": "ncu dram bytes per launch of the dominant kernel = one 32 x 32-row pass of the 5147-aa query over the whole "
-                                "database: the column stream plus the pass-boundary rows it reads from the previous pass and writes for "
-                                "the next one - HBM is not the bound",
+                "traffic_note": "ncu dram bytes per launch of the dominant kernel, sw32_kernel<32, true, false>: ALL five full passes "
+                                "(5 x 1024 rows) of the 5147-aa query over the whole database in one launch = the column stream five times "
+                                "(0.94 GB) plus the pass-boundary rows every pass writes for the next one and reads from the previous one "
+                                "(16 bytes per column pair and pass); 52 GB/s - HBM is not the bound (profiles/prof_r02_top.md)",
                 "per_search_kernel_gcups": {"%s_bw%d" % (HEAD["queries"][qi], bw):
                                             (round(qlens[qi] * meta["residues"] / n_gpus * steps / (ms / 1e3) / 1e9, 1) if ms > 0 else None)
                                             for (bw, qi), ms in zip(searches, acc.kernel_ms_by_search)},

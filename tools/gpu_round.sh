@@ -5,6 +5,7 @@ tag=${1:-r02}; out=${2:-gpurun_out}
 mkdir -p $out
 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest_gpu_$tag.log
 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; echo "bench ref rc=$?"
 python bench.py --steps 2 --warmup 1 --no-per-config --no-parity > $out/bench_short_$tag.json 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 1 --no-per-config --no-parity > $out/ncu_launches_$tag.log 2>&1; echo "launch list rc=$?"

@@ -37,6 +37,29 @@ for name in ("O74807", "P07327", "P04775", "P33450"):
     print(name, h[0].score, flush=True)
     lib.free_sequence(q)
 
+# round 2: the pipelined 32-bit tier (match 127: every pair longer than 257 residues is beyond the static int16 bound; SW
+# speculates and recomputes, NW splits statically) and two queries per word (a batch against a length-matched database)
+lib.init_constant_scores(127, -1)
+lib.init_gap_penalties(-1, -1)
+lib.init_db(prot)
+q = lib.init_sequence_fasta(L.READ_FROM_STRING, synth.random_protein(__import__("numpy").random.default_rng(3), 700))
+print("wide pipe", lib.sw_align(q, 10, 16, L.COMPUTE_SCORE)[0].score, lib.nw_align(q, 10, 16, L.COMPUTE_SCORE)[0].score, flush=True)
+lib.free_sequence(q)
+import numpy as np  # noqa: E402
+lm = os.path.join(tmp, "lm.fas")
+synth.write_fasta(lm, synth.protein_db(1200, 9, mu=float(np.log(300)), sigma=0.04, min_len=250, max_len=360, n_dup=10))
+lib.init_score_matrix(L.MATRIX_BUILDIN, "blosum62")
+lib.init_gap_penalties(-11, -1)
+lib.init_db(lm)
+rng = np.random.default_rng(4)
+qs = [lib.init_sequence_fasta(L.READ_FROM_STRING, synth.random_protein(rng, n)) for n in (300, 310, 64, 350, 900, 1000, 17)]
+for nw in (False, True):
+    res = lib.align_batch(qs, 10, 16, L.COMPUTE_SCORE, nw=nw)
+    print("dual batch", nw, [r[0].score for r in res], flush=True)
+for q in qs:
+    lib.free_sequence(q)
+lib.init_db(prot)
+
 # nucleotide, long query (multi-pass shapes) and both strands (several frames, host replay)
 nuc = os.path.join(tmp, "nuc.fas")
 synth.write_fasta(nuc, synth.nucleotide_db(300, 11, max_len=4000))

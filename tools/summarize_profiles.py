@@ -124,6 +124,12 @@ def round2():
                "algorithmic_cells_per_launch": residues * float(rows), "algorithmic_bytes_per_launch": residues * 1.0 * 5 + 4.0 * 570000,
                "passes_per_launch": 5, "instructions_per_word_row": top[-1]["instructions"] / (residues * float(rows) / 64.0),
                "score_kernel_share_of_step": share, "source": "profiles/prof_%s_top.md" % tag}, open(os.path.join(P, "roofline_%s.json" % tag), "w"), indent=1)
+    if os.path.exists(os.path.join(G, "prof_%s_P07327.ncu-rep" % tag)):
+        q375 = kernel_report("prof_%s_P07327.ncu-rep" % tag, "ncu --set full: chained kernel on half-warp arrays, 375-aa query (P07327: two arrays of 16 lanes x 24 rows per warp)",
+                             residues * 375.0, "`ncu --set full ... -k regex:sw32_kernel -s 2 -c 1 python tools/profile_target.py P07327 sw 570000` "
+                             "(plain run first: `kernel_ms 11.83 gcups 5937`).", "prof_%s_q375.md" % tag)
+        stall_breakdown("prof_%s_P07327.ncu-rep" % tag, "prof_%s_q375.md" % tag)
+        print(q375[-1])
     print("share", share, top[-1])
 
 
