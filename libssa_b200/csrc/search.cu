@@ -1532,7 +1532,8 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
                 if( (size_t) g * opts[i] >= qlen ) r = opts[i];
             if( r == 0 ) continue;
             // pairs longer than this many columns would dominate the tail of a launch with groups of g lanes
-            const int64_t long_len = g == 32 ? INT64_MAX : std::max<int64_t>( 64, (int64_t) ( (double) db.total_cols * g / ( 1165.0 * sms ) ) );
+            static const double long_div = getenv( "LIBSSA_B200_LONG_DIV" ) ? atof( getenv( "LIBSSA_B200_LONG_DIV" ) ) : 1165.0;
+            const int64_t long_len = g == 32 ? INT64_MAX : std::max<int64_t>( 64, (int64_t) ( (double) db.total_cols * g / ( long_div * sms ) ) );
             const size_t pl_end = std::max( p_safe, first_pair_not_longer( long_len ) );
             const double cols_long = (double) ( db.pair_col[pl_end] - db.pair_col[p_safe] );
             const double cols_bulk = (double) ( db.total_cols - db.pair_col[pl_end] );
@@ -2655,7 +2656,10 @@ static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh
 // (src/util/util_sequence.c:384-417): nucleotide records always come back as the forward strand, and a translated
 // record of a one-strand search is translated from the complementary strand whichever strand was scored.  The
 // alignment is computed on that sequence; reproduced as is.
-static void finish_results( const SearchRequest & req, const std::vector<FrameHit> & fh, std::vector<HitAlignment> & out, cudaStream_t tb_stream ) {
+// defer: if set, the alignment is left to the caller (gpu_search_batch aligns the hits of many queries together) and
+// *defer receives whether the alignment runs on the very sequence that was scored
+static void finish_results( const SearchRequest & req, const std::vector<FrameHit> & fh, std::vector<HitAlignment> & out, cudaStream_t tb_stream,
+        bool * defer = nullptr ) {
     const uint32_t bm = (uint32_t) ctx().db.buffer_max;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     const bool translate_db = g_symtype == TRANS_DB || g_symtype == TRANS_BOTH;
@@ -2688,6 +2692,10 @@ static void finish_results( const SearchRequest & req, const std::vector<FrameHi
             out[i].db_codes.resize( rec->seqlen );
             map_db_sequence( rec->seq, rec->seqlen, out[i].db_codes.data(), map );
         }
+    }
+    if( defer ) {
+        *defer = scored_sequence;
+        return;
     }
     if( req.align_type == COMPUTE_ALIGNMENT && !out.empty() ) {
         if( req.frames.size() == 1 ) {
@@ -2790,6 +2798,38 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
     }
     bool armed[4] = { false, false, false, false };
     const size_t chunk = g_chunk_size;
+    // Alignments: the hits of many queries are aligned together (traceback_hits_multi) - the tile launches of one query's ten
+    // hits are latency-bound and, queued behind the persistent scoring launch of the next unit, would stall the pipeline once
+    // per query.  Pending queries are flushed when ~2000 hits (or ~1.5 GB of traceback scratch) have accumulated, and at the end.
+    struct PendingAlign {
+        size_t query;
+        bool scored_sequence;
+    };
+    std::vector<PendingAlign> pending;
+    size_t pending_hits = 0, pending_cells = 0;
+    auto flush_alignments = [&]() {
+        if( pending.empty() ) return;
+        const bool nw = reqs[pending[0].query].search_type == NEEDLEMAN_WUNSCH;
+        std::vector<TbQuery> queries;
+        std::vector<uint32_t> query_of_hit;
+        std::vector<char> scored;
+        std::vector<HitAlignment> all;
+        for( const PendingAlign & pa : pending ) {
+            const SearchRequest & r = reqs[pa.query];
+            queries.push_back( TbQuery{ r.frames[0].seq, r.frames[0].len } );
+            for( HitAlignment & h : outs[pa.query] ) {
+                query_of_hit.push_back( (uint32_t) ( queries.size() - 1 ) );
+                scored.push_back( pa.scored_sequence ? 1 : 0 );
+                all.push_back( std::move( h ) );
+            }
+        }
+        traceback_hits_multi( ctx().stream_aux, queries, query_of_hit, nw, all, &ctx().stats, scored );
+        size_t k = 0;
+        for( const PendingAlign & pa : pending )
+            for( HitAlignment & h : outs[pa.query] ) h = std::move( all[k++] );
+        pending.clear();
+        pending_hits = pending_cells = 0;
+    };
     auto enqueue_selection = [&]( size_t i, const int32_t * d_all ) {
         const SearchRequest & r = reqs[i];
         const int rslot = (int) ( i & 3 );
@@ -2837,9 +2877,22 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
             cells += (uint64_t) r.frames[0].len * process_residues();
             std::vector<FrameHit> fh( hits.size() );
             for( size_t k = 0; k < hits.size(); k++ ) fh[k] = FrameHit{ (uint32_t) hits[k].db_id, 0, hits[k].score };
-            finish_results( r, fh, outs[i], ctx().stream_aux );
+            if( r.align_type == COMPUTE_ALIGNMENT ) {
+                if( !pending.empty() && reqs[pending[0].query].search_type != r.search_type ) flush_alignments();
+                bool scored_sequence = true;
+                finish_results( r, fh, outs[i], ctx().stream_aux, &scored_sequence );
+                if( !outs[i].empty() ) {
+                    pending.push_back( PendingAlign{ i, scored_sequence } );
+                    pending_hits += outs[i].size();
+                    for( const HitAlignment & h : outs[i] ) pending_cells += r.frames[0].len * h.db_codes.size();
+                    if( pending_hits >= 2000 || pending_cells >= ( 1ull << 30 ) ) flush_alignments();
+                }
+            }
+            else
+                finish_results( r, fh, outs[i], ctx().stream_aux );
         }
     }
+    flush_alignments();
     CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
     g_stage_slot = 0;
     merge_call_stats();
