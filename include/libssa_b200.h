@@ -130,7 +130,8 @@ size_t ssa_b200_host_frames_replay( const uint64_t * slot_lens, size_t nslots, s
 /*
  * Batched searches (the reference API has one call per query, src/libssa.h:229-251): out[i] receives
  * exactly what sw_align / nw_align( queries[i], hitcount, bit_width, align_type ) returns (free each with
- * free_alignment).  The library overlaps the host's share of query i with the GPU's work on query i+1.
+ * free_alignment).  The library overlaps the host's share of query i with the GPU's work on query i+1, scores
+ * consecutive one-pass queries two per packed word, and aligns the hits of many queries together.
  * nw: 0 = Smith-Waterman, 1 = Needleman-Wunsch.
  */
 void ssa_b200_align_batch( int nw, const p_query * queries, size_t nqueries, size_t hitcount, int bit_width, int align_type,
