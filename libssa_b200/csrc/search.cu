@@ -1358,6 +1358,7 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
                 s32.gap_open = g_gapO;
                 s32.gap_extend = g_gapE;
                 s32.offset = offset;
+                s32.rowbase = (int32_t) ps.rowbase;
                 for( int c = p; c < p + run; c++ )   // the pass (of this launch) that holds the query's last row
                     if( passes[c].rowbase <= qlen - 1 && qlen - 1 < passes[c].rowbase + (size_t) ps.G * ps.R ) {
                         s32.cap_pass = c;
@@ -1411,10 +1412,12 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
 // that are left, so that at most a few rows are padding (5147 rows: 5 x 1024 + 4 x 8 instead of 6 x 896).  Narrow groups
 // process a pair from its first to its last column on G lanes: the longest pair must not outlast the rest of the pass.
 // Costs in the units of pick_shape (instructions per stream column and warp).
-std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_uniform, uint64_t total_cols, uint64_t longest_cols, int sms ) {
+// full_R: rows per lane of the full passes (32; LIBSSA_B200_NW_FULL_R sets another value for Needleman-Wunsch, A/B measurements)
+std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_uniform, uint64_t total_cols, uint64_t longest_cols, int sms, int full_R = 32 ) {
     std::vector<PassLaunch> v;
     const double uniform_cost = npass_uniform * ( 7.5 * R_uniform + 60 ) * 1.03;
-    const size_t full = qlen / 1024, rem = qlen % 1024;
+    const size_t full_rows = (size_t) 32 * full_R;
+    const size_t full = qlen / full_rows, rem = qlen % full_rows;
     double best = 1e300;
     int bg = 0, br = 0;
     if( rem > 0 )
@@ -1431,7 +1434,7 @@ std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_unifo
                     br = R;
                 }
             }
-    const double mixed_cost = full * ( 7.5 * 32 + 60 ) * 1.03 + ( rem > 0 ? best : 0.0 );
+    const double mixed_cost = full * ( 7.5 * full_R + 60 ) * 1.03 + ( rem > 0 ? best : 0.0 );
     if( getenv( "LIBSSA_B200_SHAPE" ) || getenv( "LIBSSA_B200_UNIFORM_PASSES" ) || full == 0 || mixed_cost >= uniform_cost ) {
         for( int p = 0; p < npass_uniform; p++ ) {
             PassLaunch ps;
@@ -1445,15 +1448,15 @@ std::vector<PassLaunch> plan_passes( size_t qlen, int R_uniform, int npass_unifo
     for( size_t p = 0; p < full; p++ ) {
         PassLaunch ps;
         ps.G = 32;
-        ps.R = 32;
-        ps.rowbase = p * 1024;
+        ps.R = full_R;
+        ps.rowbase = p * full_rows;
         v.push_back( ps );
     }
     if( rem > 0 ) {
         PassLaunch ps;
         ps.G = bg;
         ps.R = br;
-        ps.rowbase = full * 1024;
+        ps.rowbase = full * full_rows;
         v.push_back( ps );
     }
     return v;
@@ -1611,7 +1614,11 @@ void score_shard( const uint8_t * q, size_t qlen, bool nw ) {
     if( b0 < bt.batches.size() ) {
         std::vector<PassLaunch> passes;
         if( npass > 1 ) {
-            passes = plan_passes( qlen, R, npass, db.total_cols - db.pair_col[bulk_pair0], db.sorted_len[2 * bulk_pair0], sms );
+            // (measured [B200]: NW full passes of 28 rows per lane +0.9 % for the 5147-aa protein query, -3.6 % for the 10 kbp
+            // nucleotide query - the default stays 32)
+            static const int nw_full_R = getenv( "LIBSSA_B200_NW_FULL_R" ) ? atoi( getenv( "LIBSSA_B200_NW_FULL_R" ) ) : 32;
+            passes = plan_passes( qlen, R, npass, db.total_cols - db.pair_col[bulk_pair0], db.sorted_len[2 * bulk_pair0], sms,
+                    nw && sw32_enabled( true ) ? nw_full_R : 32 );
             ctx().d_bnd.reserve( 4 * db.total_cols + 256 );   // 2 buffers x ( total_cols / 2 + 1 ) entries x 4 words
         }
         else {

@@ -55,6 +55,7 @@ struct Sw32Args {
     // Needleman-Wunsch
     int32_t gap_open, gap_extend;   // gapO, gapE (non-positive)
     int32_t offset;                 // values are stored minus this offset (centres the value range on 0)
+    int32_t rowbase;                // first query row of this launch's first pass (its later passes follow at 32 R rows each)
     int32_t cap_pass;               // pass of the QUERY (not of the launch) that holds the query's last row ...
     int32_t cap_lane, cap_row;      // ... and the lane / row in the lane
     // DUAL (two QUERIES per packed word, score_kernel.cuh): one launch per sequence of the pairs
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     if( NW ) {   // start values of this pass' rows: H(i, -1) = gapO + (i + 1) gapE, E = H + gapO + gapE (both minus the offset)
         for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
             const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;   // word i of the H half: [row quad][lane][row in quad]
-            const int row = (int) ( a.pass0 + pp ) * 32 * R + ( l & ( G - 1 ) ) * R + r;
+            const int row = a.rowbase + (int) pp * 32 * R + ( l & ( G - 1 ) ) * R + r;
             const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
             smem[NW_TAB + i] = A::bcast( h );
             smem[NW_TAB + R * 32 + i] = A::bcast( h + a.gap_open + a.gap_extend );
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                             E[4 * q + 2] = e.z;
                             E[4 * q + 3] = e.w;
                         }
-                        const int row0 = (int) ( a.pass0 + pp ) * 32 * R + gl * R;
+                        const int row0 = a.rowbase + (int) pp * 32 * R + gl * R;
                         diag = A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset );
                     }
                     else {
