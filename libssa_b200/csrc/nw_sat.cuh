@@ -1,9 +1,14 @@
 // Emulation of ONE channel of the reference's saturating 8-/16-bit NW kernel per database sequence
 // (reference src/algo/simd/search_simd_nw.c:180-316 ALIGNCORE / aligncolumns_first / aligncolumns_rest,
-// :390-500 boundary injection, per-block overflow test, result read-out).  It exists only to reproduce the
-// ORDER in which the reference's narrow NW tiers hand records to the heap: a record that overflows a tier
-// leaves its SIMD channel after the 4-column block in which the overflow is detected and is re-run in the
-// next tier after the chunk.  Scores never come from here (the exact tiers compute them).
+// :390-500 boundary injection, per-block overflow test, result read-out).  It reproduces two things the exact
+// tiers cannot know.  (1) The ORDER in which the reference's narrow NW tiers hand records to the heap: a record
+// that overflows a tier leaves its SIMD channel after the 4-column block in which the overflow is detected and
+// is re-run in the next tier after the chunk.  (2) The SCORE a narrow tier reports for a record it does NOT flag:
+// the injected top boundary H(-1, j) saturates silently (it is not part of the overflow test), so a short query
+// against a sequence of more than ~120 columns can finish the 8-bit tier with a score that is too high - e.g.
+// query "AA", match 5, gaps -1/-1, a 150-nt record: -118 instead of -139 - and the reference reports that value
+// (found by the differential fuzz campaign of round 2).  sat_score receives it; the search substitutes it for the
+// exact score of every record the entry tier (or the 16-bit tier behind it) accepts.
 // One thread per sequence, 4 columns per block exactly like the reference, H/E of the previous block in
 // global scratch laid out [row][thread] (coalesced); a thread stops at its first overflowing block.
 #pragma once
@@ -27,6 +32,7 @@ struct NwSatArgs {
     int16_t * scratch_h;          // [qlen][count]
     int16_t * scratch_e;
     int32_t * first_col;          // out, by local sorted position: 4 * overflow block, untouched if no overflow
+    int32_t * sat_score;          // out (may be null), by local sorted position: the tier's own result if it does not overflow
 };
 
 __device__ __forceinline__ int sat_clamp( int v, int lo, int hi ) { return v < lo ? lo : ( v > hi ? hi : v ); }
@@ -112,7 +118,11 @@ __global__ void __launch_bounds__( 128 ) nw_sat_kernel( const NwSatArgs a ) {
         const int score = Sm[( dlen + 3 ) % 4];  // :423-426
         if( !( score > LO && score < HI ) ) ovf = nblocks ? (int) nblocks - 1 : 0;
     }
-    if( ovf >= 0 ) a.first_col[s] = 4 * ovf;
+    if( dlen == 0 ) ovf = 0;   // (no such records: empty ones are dropped when the database is packed)
+    if( ovf >= 0 )
+        a.first_col[s] = 4 * ovf;
+    else if( a.sat_score )
+        a.sat_score[s] = Sm[( dlen + 3 ) % 4];
 }
 
 }  // namespace ssa

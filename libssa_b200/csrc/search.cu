@@ -170,6 +170,7 @@ struct Ctx {
     DevBuf<int32_t> d_cand_score;
     PinBuf<Batch> h_wide_batches[2][2];
     DevBuf<uint32_t> d_pass_state;        // sw32_kernel, several passes per launch: [SW32_MAX_PASSES] queue heads | [nbatches] passes done
+    DevBuf<int32_t> d_nw_tier;            // NW narrow tiers: overflow columns and tier scores of the records static bounds cannot clear
     DevBuf<uint32_t> d_wide_progress[2];  // pipelined 32-bit tier: [batch][pass] progress counters
     DevBuf<uint32_t> d_spec_list;         // speculative packed tier: sequences listed for the 32-bit tier
     PinBuf<uint32_t> h_spec_count[2];
@@ -875,6 +876,13 @@ __global__ void iota_kernel( uint32_t * p, uint32_t first, uint32_t n ) {
 }
 
 // counts the entries that are not INT_MAX (records that overflow a tier)
+// NW entered at 8 / 16 bit: a record the narrow tier accepts (first == INT_MAX among the n emulated ones) is reported with THAT
+// tier's score (nw_sat.cuh), not with the exact one
+__global__ void nw_apply_sat_kernel( const int32_t * first, const int32_t * sat, uint32_t n, int32_t * scores ) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i < n && first[i] == INT_MAX ) scores[i] = sat[i];
+}
+
 __global__ void count_set_kernel( const int32_t * p, uint32_t n, uint32_t * out ) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if( i < n && p[i] != 0x7fffffff ) atomicAdd( out, 1u );
@@ -1868,7 +1876,7 @@ size_t sorted_prefix_longer_than( int64_t len ) {
 
 // emulates the `bits`-wide saturating NW kernel for the first `count` local sorted positions; first_col[s] receives
 // 4 * (overflow block) for the records that overflow
-void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t * d_first_col ) {
+void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t * d_first_col, int32_t * d_sat_score = nullptr ) {
     PackedDb & db = ctx().db;
     if( count == 0 ) return;
     upload_matrix32();
@@ -1896,6 +1904,7 @@ void run_nw_sat( const uint8_t * q, size_t qlen, int bits, size_t count, int32_t
         a.scratch_h = ctx().d_nw_scratch.p;
         a.scratch_e = ctx().d_nw_scratch.p + qlen * n;
         a.first_col = d_first_col;
+        a.sat_score = d_sat_score;
         nw_sat_kernel<<<(unsigned) ( ( n + 127 ) / 128 ), 128, 0, ctx().stream>>>( a );
         ctx().stats.launches += 2;
     }
@@ -2067,6 +2076,7 @@ static void release_ctx( Ctx & c ) {
     c.d_cand_id.release();
     c.d_cand_score.release();
     c.d_spec_list.release();
+    c.d_nw_tier.release();
     c.d_wide_progress[0].release();
     c.d_wide_progress[1].release();
     c.d_pass_state.release();
@@ -2284,13 +2294,38 @@ static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & 
 // One query frame against the entry stream: top-k with the reference's one-thread tie behaviour.  Hit ids are entry
 // (slot) indices.  Every key (score, id) is distinct, so the final order does not depend on the sort algorithm.
 // scores of this shard's entries -> every rank; returns the gathered score vector (rank-major blocks of `stride`)
-static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw ) {
+// whether the reference's saturating NW tiers can report something else than the exact score for some record of this database
+static bool nw_narrow_scores_needed( size_t qlen, bool nw, int bit_width ) {
+    PackedDb & db = ctx().db;
+    if( !nw || db.sorted_all.empty() || ( bit_width != 8 && bit_width != 16 ) ) return false;
+    const int64_t longest = (int64_t) db.lens_all[db.sorted_all[0]];
+    return ( bit_width == 8 && longest > nw_tier_safe_len( qlen, 8 ) ) || longest > nw_tier_safe_len( qlen, 16 );
+}
+
+static int32_t * score_query( const uint8_t * query, size_t qlen, bool nw, int bit_width ) {
     const size_t nglob = ctx().db.sorted_all.size();
     const size_t world = (size_t) ctx().world;
     const size_t stride = ( nglob + world - 1 ) / world;  // local positions per rank, padded
+    const bool narrow = nw_narrow_scores_needed( qlen, nw, bit_width );   // the same on every rank (global longest record)
     run_on_all( [&]() {
         ctx().d_scores.reserve( stride + 2 );
         score_shard( query, qlen, nw );
+        if( narrow ) {   // the scores the reference's 8- / 16-bit NW tiers report for the records they accept (nw_sat.cuh)
+            const size_t n8 = bit_width == 8 ? sorted_prefix_longer_than( nw_tier_safe_len( qlen, 8 ) ) : 0;
+            const size_t n16 = sorted_prefix_longer_than( nw_tier_safe_len( qlen, 16 ) );
+            ctx().d_nw_tier.reserve( 4 * stride + 4 );   // first8 | first16 | score8 | score16
+            int32_t * d_f = ctx().d_nw_tier.p, * d_s = d_f + 2 * stride;
+            launch_fill( d_f, INT_MAX, 2 * stride );
+            if( n16 ) {
+                run_nw_sat( query, qlen, 16, n16, d_f + stride, d_s + stride );
+                nw_apply_sat_kernel<<<(unsigned) ( ( n16 + 255 ) / 256 ), 256, 0, ctx().stream>>>( d_f + stride, d_s + stride, (uint32_t) n16, ctx().d_scores.p );
+            }
+            if( n8 ) {   // (after the 16-bit tier: a record the 8-bit tier accepts never reaches it)
+                run_nw_sat( query, qlen, 8, n8, d_f, d_s );
+                nw_apply_sat_kernel<<<(unsigned) ( ( n8 + 255 ) / 256 ), 256, 0, ctx().stream>>>( d_f, d_s, (uint32_t) n8, ctx().d_scores.p );
+            }
+            ctx().stats.launches += 2;
+        }
         // ---- shard results -> every rank (ncclAllGather over NVLink / NVSwitch, on this context's stream) ----
         if( world > 1 ) {
             ctx().d_gathered.reserve( stride * world + 2 );
@@ -2316,7 +2351,7 @@ static void search_single( const uint8_t * query, size_t qlen, const SearchReque
     PackedDb & db = ctx().db;
     const bool nw = req.search_type == NEEDLEMAN_WUNSCH;
     ctx().stats.cells = (uint64_t) qlen * process_residues();
-    const int32_t * d_all = score_query( query, qlen, nw );
+    const int32_t * d_all = score_query( query, qlen, nw, req.bit_width );
     // ---- top-k on the device (see enqueue_topk) ----
     const size_t chunk = g_chunk_size * (size_t) db.buffer_max;  // entries per reference chunk (db_adapter.c:196)
     PackedDb::Arrival & base = arrival_for( req.bit_width, chunk, chunk <= (size_t) ARRIVAL_MAX_CHUNK );  // validity: records the reference reaches
@@ -2591,7 +2626,7 @@ static void search_frames( const SearchRequest & req, std::vector<FrameHit> & fh
         scores[q].assign( nslots, 0 );
         ctx().stats.cells += (uint64_t) f.len * process_residues();
         if( nglob == 0 ) continue;
-        const int32_t * d_all = score_query( f.seq, f.len, nw );
+        const int32_t * d_all = score_query( f.seq, f.len, nw, req.bit_width );
         ctx().h_scores.reserve( total + 1 );
         CUDA_OK( cudaMemcpyAsync( ctx().h_scores.p, d_all, total * sizeof( int32_t ), cudaMemcpyDeviceToHost, ctx().stream ) );
         CUDA_OK( cudaStreamSynchronize( ctx().stream ) );
@@ -2797,7 +2832,10 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
     std::vector<DualPlan> plans;
     for( size_t i = 0; i < n; ) {
         DualPlan dp;
+        const bool nwq = reqs[i].search_type == NEEDLEMAN_WUNSCH;
         const bool pair = i + 1 < n && reqs[i].search_type == reqs[i + 1].search_type && world == 1 && g_devs.size() == 1 &&
+                !nw_narrow_scores_needed( reqs[i].frames[0].len, nwq, reqs[i].bit_width ) &&
+                !nw_narrow_scores_needed( reqs[i + 1].frames[0].len, nwq, reqs[i + 1].bit_width ) &&
                 dual_plan( reqs[i].frames[0].len, reqs[i + 1].frames[0].len, reqs[i].search_type == NEEDLEMAN_WUNSCH, dp );
         units.push_back( Unit{ i, pair ? 2 : 1 } );
         plans.push_back( dp );
@@ -2860,7 +2898,7 @@ void gpu_search_batch( const std::vector<SearchRequest> & reqs, std::vector<std:
             enqueue_selection( un.first + 1, ctx().d_scores2.p );
         }
         else
-            enqueue_selection( un.first, score_query( r0.frames[0].seq, r0.frames[0].len, nw ) );
+            enqueue_selection( un.first, score_query( r0.frames[0].seq, r0.frames[0].len, nw, r0.bit_width ) );
     };
     CUDA_OK( cudaEventRecord( ctx().ev_begin, ctx().stream ) );
     enqueue( 0 );

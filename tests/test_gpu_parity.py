@@ -83,6 +83,35 @@ def test_live_reference_random_inputs(prod, ref, tmp_path):
             assert_same_hits(g, e, run[0], run[1], ("trial", trial, n, qlen, scoring, gaps, run))
 
 
+def test_nw_narrow_tier_reports_saturated_scores(prod, ref, tmp_path):
+    """The reference's 8-bit NW tier injects a top boundary H(-1, j) that saturates silently: a 2-residue query against records of
+    more than ~125 columns finishes the tier unflagged with a score that is too high (-118 instead of -139), and the reference
+    reports it.  The library substitutes the tier's own result (nw_sat.cuh) for the records a narrow tier accepts.  Found by the
+    differential fuzz campaign (seed 20261019, trial 9)."""
+    from libssa_b200 import synth
+    seqs = synth.nucleotide_db(400, 4242, mu=4.9, sigma=0.25, min_len=60, max_len=400, iupac_rate=0.01)
+    path = tmp_path / "nt.fas"
+    synth.write_fasta(str(path), seqs)
+    differs = 0
+    for q, gaps in (("AA", (-1, -1)), ("ACG", (-2, -1)), ("T", (0, -1))):
+        lists = {}
+        for lib in (ref, prod):
+            lib.set_output_mode(0)
+            if lib is ref:
+                lib.set_thread_count(1)
+            lib.init_symbol_translation(cases.NUCLEOTIDE, 1, 1, 1)
+            lib.init_constant_scores(5, -4)
+            lib.init_gap_penalties(*gaps)
+            lib.set_chunk_size(1000)
+            lib.init_db(str(path))
+            qh = lib.init_sequence_fasta(cases.READ_FROM_STRING, q)
+            lists[lib is ref] = {bw: [(h.score, h.db_id) for h in lib.nw_align(qh, len(seqs), bw, cases.COMPUTE_SCORE)] for bw in (8, 16, 64)}
+            lib.free_sequence(qh)
+        assert lists[False] == lists[True], (q, gaps)
+        differs += sorted(lists[True][8]) != sorted(lists[True][64])
+    assert differs > 0   # the case is real: at 8 bit the reference itself reports other scores than at 64 bit
+
+
 @pytest.mark.parametrize("qlen", [1, 3, 64, 127, 128, 130, 255, 384, 385, 500, 768, 1024, 1025, 1100, 1500, 2048, 2100, 3100])
 def test_exact_scores_vs_oracle_port(prod, port, tmp_path, qlen):
     """every kernel shape (rows per lane 4..32, one and several passes, remainder passes on narrow groups), both tiers, SW and NW"""
