@@ -202,10 +202,16 @@ def search(seqs, q, M, gapO, gapE, nw, k, bit_width=64, chunk=1000):
         for i in range(len(seqs)):
             if len(seqs[i]) == 0:
                 continue
+            # a record a saturating tier ACCEPTS is reported with that tier's own score: the injected top boundary saturates
+            # silently, so it can differ from the exact one (search_simd_nw.c:423-426, 445-453; e.g. -118 for an exact -139)
             if bit_width == 8:
-                ovf8[i] = nw_simd_channel(seqs[i], q, M, gapO, gapE, 8)[1]
+                s8, ovf8[i] = nw_simd_channel(seqs[i], q, M, gapO, gapE, 8)
+                if ovf8[i] < 0:
+                    scores[i] = s8
             if bit_width == 16 or ovf8[i] >= 0:
-                ovf16[i] = nw_simd_channel(seqs[i], q, M, gapO, gapE, 16)[1]
+                s16, ovf16[i] = nw_simd_channel(seqs[i], q, M, gapO, gapE, 16)
+                if ovf16[i] < 0:
+                    scores[i] = s16
     order = arrival_order(lens, chunk, bit_width, ovf8, ovf16)
     return topk_replay(scores, order, k)
 

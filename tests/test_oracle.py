@@ -169,3 +169,21 @@ def test_port_matches_live_reference(port, ref, tmp_path):
             for e in exp[:5]:
                 region, cig = port.cigar(qc, codes[e[1]], M, -5, -2, mode == "nw")
                 assert (cig, region) == (e[2], (e[3], e[4], e[5], e[6]))
+
+
+def test_port_nw_narrow_tier_scores_match_live_reference(port, ref, tmp_path):
+    """NW entered at 8 bit with a 2-residue query: the reference's 8-bit tier accepts records of ~130-160 columns with a score
+    that is too high (its injected top boundary saturates silently) and reports it; the port does the same (search())."""
+    from libssa_b200 import synth
+    seqs = synth.nucleotide_db(300, 4242, mu=4.9, sigma=0.25, min_len=60, max_len=400, iupac_rate=0.01)
+    path = tmp_path / "nt.fas"
+    synth.write_fasta(str(path), seqs)
+    case = {"symtype": cases.NUCLEOTIDE, "scoring": [5, -4], "gaps": [-1, -1], "db": str(path), "query_string": "AA",
+            "runs": [["nw", w, len(seqs), cases.COMPUTE_SCORE] for w in (64, 16, 8)]}
+    expected = cases.run_case(ref, case)
+    codes = [port.map_db(s, True) for s in seqs]
+    qc = port.map_query("AA", True)
+    M = matrix_of([5, -4])
+    for (mode, bw, k, _), exp in zip(case["runs"], expected):
+        assert port.search(codes, qc, M, -1, -1, True, k, bw) == [(e[0], e[1]) for e in exp], bw
+    assert sorted(e[0] for e in expected[2]) != sorted(e[0] for e in expected[0])   # 8 bit really reports other scores than 64 bit
