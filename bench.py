@@ -212,14 +212,49 @@ def reference_protein_steps(ref, cfg, path, meta, steps, warmup, cores):
     return cells_per_step * steps / dt / 1e9, dt / steps
 
 
+def run_reference_port(path, meta, steps, warmup, n_gpus):
+    """oracle/_ref is not there (the reference was not compiled on this machine): the oracle's C restatement of the same algorithm,
+    one scalar thread, on a bounded sample of the same database - the other place bench.py may execute oracle/."""
+    from oracle import port
+    n_sample = 600
+    import numpy as np
+    codes = [port.map_db(s, False) for _, s in port.read_fasta(path)[:n_sample]]
+    residues = sum(len(c) for c in codes)
+    M = np.array(json.load(open(os.path.join(ROOT, "tests", "golden", "matrices.json")))["blosum62"], dtype=np.int64).reshape(32, 32)
+    qcodes = [port.map_query(query_text(q), False) for q in HEAD["queries"]]
+
+    def step():
+        for bw in HEAD["bit_widths"]:
+            for qc in qcodes:
+                port.search(codes, qc, M, -11, -1, False, HITCOUNT, bw)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    gcups = sum(qlens_of(HEAD)) * len(HEAD["bit_widths"]) * residues * steps / dt / 1e9
+    sample = "oracle port (oracle/restate.c, scalar, 1 thread) on the first %d records / %d residues of the %d-record database, same %d searches per step" % (
+        len(codes), residues, meta["n_seqs"], len(HEAD["queries"]) * len(HEAD["bit_widths"]))
+    return {
+        "impl": "reference", "metric": "GCUPS", "value": round(gcups, 3), "unit": "GCUPS", "n_gpus": n_gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(HEAD, n_gpus, meta),
+        "cpu_baseline": {"value": round(gcups, 3), "unit": "GCUPS", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gcups, 3), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def run_reference(steps, warmup, n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
     ref = reference_api()
-    if ref is None:
-        return {"impl": "reference", "unavailable": "oracle/_ref/libssa_ref.so was not built (needs /root/reference at build time)"}
     path, meta = protein_db_file(HEAD["db_seqs"], HEAD["seed"])
+    if ref is None:
+        return run_reference_port(path, meta, steps, warmup, n_gpus)
+    
     cores = os.cpu_count() or 1
     gcups, s_per_step = reference_protein_steps(ref, HEAD, path, meta, steps, warmup, cores)
     sample = "the full workload: all %d records / %d residues, %d searches per timed step, %d threads, chunk size 1000 (warm-up steps: one search each)" % (
