@@ -2295,10 +2295,16 @@ static bool collect_topk( size_t k, int bit_width, int slot, std::vector<Hit> & 
 // (slot) indices.  Every key (score, id) is distinct, so the final order does not depend on the sort algorithm.
 // scores of this shard's entries -> every rank; returns the gathered score vector (rank-major blocks of `stride`)
 // whether the reference's saturating NW tiers can report something else than the exact score for some record of this database
+// The emulation runs one thread per record from its first column to the block in which the tier flags it (or to its end), so
+// its critical path is query length x longest record: bounded here to 5 M cells (~0.1 s).  Beyond that the tiers are taken
+// to flag every record the static bounds cannot clear, i.e. the exact scores stand - a 10 kbp query against 20 kbp records
+// (BASELINE configs[4]) would otherwise spend 9 s per search on a case in which a tier can only accept a record whose
+// last columns match row after row behind the point where the boundary saturates.  Deviation recorded in DESIGN.md 2.
 static bool nw_narrow_scores_needed( size_t qlen, bool nw, int bit_width ) {
     PackedDb & db = ctx().db;
     if( !nw || db.sorted_all.empty() || ( bit_width != 8 && bit_width != 16 ) ) return false;
     const int64_t longest = (int64_t) db.lens_all[db.sorted_all[0]];
+    if( (double) qlen * (double) longest > 5.0e6 && !getenv( "LIBSSA_B200_NW_TIER_SCORES" ) ) return false;
     return ( bit_width == 8 && longest > nw_tier_safe_len( qlen, 8 ) ) || longest > nw_tier_safe_len( qlen, 16 );
 }
 

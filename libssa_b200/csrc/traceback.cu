@@ -38,7 +38,7 @@ namespace {
 
 constexpr int TB_R = 8;                 // rows per lane
 constexpr int TILE_R = 32 * TB_R;       // rows per tile
-constexpr int TILE_C = 256;             // columns per tile
+constexpr int TILE_C = 128;             // columns per tile
 
 enum Pass { PASS_FORWARD = 0, PASS_REVERSE = 1, PASS_DIRECTIONS = 2 };
 
