@@ -141,7 +141,7 @@ struct Ctx {
     int ss = 0;
     PinBuf<Batch> h_long_batches[2];
     PinBuf<uint32_t> h_profile_long[2];
-    DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_guard, d_pos_tmp;
+    DevBuf<int32_t> d_first_compact, d_scores, d_gathered, d_arrival_scores, d_first, d_pos_tmp;
     DevBuf<int32_t> d_all_slot[4];      // batch: the gathered scores of the (up to four) queries in flight
     DevBuf<int32_t> d_scores2;          // two queries per word: scores of the second query
     DevBuf<uint32_t> d_profile_dual;
@@ -2060,7 +2060,6 @@ static void release_ctx( Ctx & c ) {
     c.d_gathered.release();
     c.d_arrival_scores.release();
     c.d_first.release();
-    c.d_guard.release();
     c.d_pos_tmp.release();
     c.d_order.release();
     c.d_wave_list.release();
