@@ -378,9 +378,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 s_in = 0;
             }
 
-            T ha_last = 0, fa_last = 0, hb_last = 0, fb_last = 0;
             s_out = 0;
             if( cia & COL_VALID ) {
+                T ha_last, fa_last, hb_last, fb_last;   // (an idle step leaves the hand-over registers alone: the next lane's step is idle too)
                 if( cia & COL_FIRST ) {   // a new pair of sequences starts in this lane (always in column A)
                     if( NW ) {   // H(i, -1) and E of this lane's rows from the pass' table, H(row0 - 1, -1) as the first diagonal
 #pragma unroll
@@ -612,11 +612,11 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                         }
                     }
                 }
+                ha_out = ha_last;
+                fa_out = fa_last;
+                hb_out = hb_last;
+                fb_out = fb_last;
             }
-            ha_out = ha_last;
-            fa_out = fa_last;
-            hb_out = hb_last;
-            fb_out = fb_last;
         }
     }
   }
