@@ -85,6 +85,8 @@ struct ScoreArgs {
     uint32_t dual_half;        // 0 = the launch scores sequence A of every pair (bits 0-4), 1 = sequence B (bits 5-9)
     uint32_t out_stride;       // words between the result arrays of the two halves
     int32_t cap_lane2, cap_row2;   // NW: lane / row of the SECOND query's last row (cap_lane / cap_row: the first query's)
+    int32_t nw_shift, nw_shift2;   // packed NW: virtual rows on top of the (first / second) query, so that the query's last row is
+                                   // the LAST row of a lane (search.cu:fill_profile_packed); rowbase counts array positions
     const uint4 * bnd_in;       // boundary row from the previous pass (nullptr in pass 0): one entry per column pair,
                                 // { H column A, H column B, F column A, F column B } of the pass' last query row
     uint4 * bnd_out;            // boundary row for the next pass (nullptr in the last pass)
@@ -149,6 +151,14 @@ template<bool PACKED, int R> __host__ __device__ constexpr int profile_words() {
     return PACKED ? merge_rows( R ) * 1024 + ( ( R - merge_rows( R ) ) / 2 ) * 1024 : R * 1024;
 }
 
+// Packed NW: H of array position `pos` in column -1 (query row pos - shift; `shift` virtual rows on top); pos = -1 is the row
+// above the array
+__host__ __device__ __forceinline__ int nw_start( int pos, int shift, int gap_open, int gap_extend ) {
+    if( pos < shift - 1 ) return gap_open;                                // virtual rows (and the boundary row above them): gapO
+    if( pos == shift - 1 ) return 0;                                       // last virtual row, or the boundary row above row 0: the corner
+    return gap_open + ( pos - shift + 1 ) * gap_extend;
+}
+
 // dynamic shared memory of a kernel instance: the profile and, for packed Needleman-Wunsch, the start-value table
 template<bool PACKED, int R> __host__ __device__ constexpr int score_smem_bytes( bool nw ) {
     return ( profile_words<PACKED, R>() + ( PACKED && nw ? 2 * R * 32 : 0 ) ) * 4;
@@ -180,10 +190,12 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     if( NW && PACKED ) {
         for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
             const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;
-            const int row = a.rowbase + ( l & ( (int) a.group - 1 ) ) * R + r;
-            const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
-            prof[NW_TAB + i] = (uint32_t) A::bcast( h );
-            prof[NW_TAB + R * 32 + i] = (uint32_t) A::bcast( h + a.gap_open + a.gap_extend );
+            const int pos = a.rowbase + ( l & ( (int) a.group - 1 ) ) * R + r;
+            const int h1 = nw_start( pos, a.nw_shift, a.gap_open, a.gap_extend ) - a.offset;
+            const int h2 = DUAL ? nw_start( pos, a.nw_shift2, a.gap_open, a.gap_extend ) - a.offset : h1;
+            const int qr = a.gap_open + a.gap_extend;
+            prof[NW_TAB + i] = ( (uint32_t) (uint16_t) (int16_t) h1 << 16 ) | (uint32_t) (uint16_t) (int16_t) h2;
+            prof[NW_TAB + R * 32 + i] = ( (uint32_t) (uint16_t) (int16_t) ( h1 + qr ) << 16 ) | (uint32_t) (uint16_t) (int16_t) ( h2 + qr );
         }
     }
     __syncthreads();
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     // and the per-step work (shuffles, flags, loads) is shared by 2R cells.  Sequence pairs are padded to an even
     // number of columns in the stream, so a sequence always starts in column A.
     // PACKED Smith-Waterman has no one-column path: pairs are padded with a harmless column (PAD_RESIDUE)
-    constexpr bool HAS_SLOW = !PACKED || NW;
+    constexpr bool HAS_SLOW = !PACKED;   // (packed NW reads its result from the values a lane hands on: nw_shift)
     // passes of a long query on full-warp arrays: the group IS the warp, known at compile time
     constexpr bool FULLWARP = MULTI == 1;
     const int lane = threadIdx.x & 31;
@@ -508,7 +520,13 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                         }
                     }
                 }
-                diag = NW ? A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset ) : A::bcast( 0 );
+                if( NW && PACKED ) {   // first diagonal: H of the array position above, column -1 (virtual rows on top: nw_start)
+                    const int d1 = nw_start( row0 - 1, a.nw_shift, a.gap_open, a.gap_extend ) - a.offset;
+                    const int d2 = DUAL ? nw_start( row0 - 1, a.nw_shift2, a.gap_open, a.gap_extend ) - a.offset : d1;
+                    diag = (T) ( ( (uint32_t) (uint16_t) (int16_t) d1 << 16 ) | (uint32_t) (uint16_t) (int16_t) d2 );
+                }
+                else
+                    diag = NW ? A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset ) : A::bcast( 0 );
                 if( !NW ) S = A::bcast( 0 );
                 jcol = 0;
                 f8 = 0x7fffffff;
@@ -516,9 +534,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             }
 
             const bool b_valid = ( cib & COL_VALID ) != 0;
-            const bool slow = HAS_SLOW && ( !PACKED || !b_valid ||
-                    ( NW && !DUAL && gl == a.cap_lane && ( cia & ( COL_LAST_A | COL_LAST_B ) ) ) ||
-                    ( NW && DUAL && ( gl == a.cap_lane || gl == a.cap_lane2 ) && ( cia & ( half ? COL_LAST_B : COL_LAST_A ) ) ) );
+            const bool slow = HAS_SLOW;
             if( slow ) {
                 // column by column: the wide tier, and NW results that must be read between the two columns - only in the
                 // lane that owns the query's last row (a sequence end in column A makes ONE lane of the group leave the
@@ -615,7 +631,28 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 fa_last = fa;
                 hb_last = Hp[R - 1];
                 fb_last = fb;
-                if( NW ) nw_capture( cib );
+                if( NW ) {   // packed NW: the query's last row is the last row of its lane - H of that row is what the lane hands on
+                    const uint32_t pos = bnd_base + (uint32_t) ( t - gl );
+                    if( DUAL ) {
+                        uint16_t * o = (uint16_t *) ( (uint32_t *) a.out + half * a.out_stride + pos );
+#pragma unroll
+                        for( int c = 0; c < 2; c++ ) {
+                            if( ( c ? cib : cia ) & ( half ? COL_LAST_B : COL_LAST_A ) ) {
+                                const uint32_t v = (uint32_t) ( c ? hb_last : ha_last );
+                                if( gl == a.cap_lane ) o[1] = (uint16_t) ( v >> 16 );       // first query = high half
+                                if( gl == a.cap_lane2 ) o[0] = (uint16_t) ( v & 0xffffu );
+                            }
+                        }
+                    }
+                    else if( gl == a.cap_lane ) {
+#pragma unroll
+                        for( int c = 0; c < 2; c++ ) {
+                            const uint32_t ci = c ? cib : cia, v = (uint32_t) ( c ? hb_last : ha_last );
+                            if( ci & COL_LAST_B ) cap_b = (T) v;
+                            if( ci & COL_LAST_A ) ( (uint32_t *) a.out )[pos] = __byte_perm( (uint32_t) cap_b, v, 0x7610 );
+                        }
+                    }
+                }
             }
 
             // ---- SW results at sequence ends (rare, divergent) ----

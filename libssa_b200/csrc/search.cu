@@ -971,14 +971,21 @@ Plan make_plan( size_t qlen ) {
 // word (low half = even row).  Rows beyond the query get pad_score.
 size_t packed_profile_words( int R ) { return (size_t) merge_rows( R ) * 1024 + (size_t) ( ( R - merge_rows( R ) ) / 2 ) * 1024; }
 
-void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G, int R, size_t rowbase, int pad_score ) {
+// Packed Needleman-Wunsch shifts the query DOWN by `shift` rows so that its last row is the last row of a lane (the result is
+// then the value the lane hands to the next one - no row has to be picked out of the registers, no column has to be run on its
+// own; nw_row_shift).  The `shift` VIRTUAL rows on top score gapE against every residue: with start values gapO (0 in the last
+// of them) they carry the matrix' top boundary H(-1, j) = gapO + (j + 1) gapE down unchanged - H = diagonal + gapE, E and F stay
+// below - and hand row 0 exactly the boundary it expects (H, and F = H + gapO + gapE).  Position p of the array = query row p - shift.
+void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G, int R, size_t rowbase, int pad_score, size_t shift = 0 ) {
     const int MR = merge_rows( R );
     uint32_t * out16 = out + (size_t) MR * 1024;
     for( int d = 0; d < 32; d++ )
         for( int lane = 0; lane < 32; lane++ ) {
             const size_t row0 = rowbase + (size_t) ( lane % G ) * R;
             auto score = [&]( int r ) {
-                return row0 + r < qlen && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q[row0 + r]] : pad_score;
+                const size_t pos = row0 + r;
+                if( pos < shift ) return (int) g_gapE;
+                return pos - shift < qlen && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q[pos - shift]] : pad_score;
             };
             for( int r = 0; r < MR; r++ )
                 out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = (uint32_t) (uint16_t) (int16_t) score( r );
@@ -992,14 +999,19 @@ void fill_profile_packed( uint32_t * out, const uint8_t * q, size_t qlen, int G,
 
 // Profile of the two-queries-per-word kernels: 128-bit entries [row quad][residue][lane] of four rows, each word = (score of
 // query 1 : score of query 2) for that row and residue; rows beyond a query's end hold pad_score in its half.
-void fill_profile_dual( uint32_t * out, const uint8_t * q1, size_t len1, const uint8_t * q2, size_t len2, int G, int R, int pad_score ) {
+// shift1 / shift2: NW, virtual rows on top of each query (fill_profile_packed)
+void fill_profile_dual( uint32_t * out, const uint8_t * q1, size_t len1, const uint8_t * q2, size_t len2, int G, int R, int pad_score,
+        size_t shift1 = 0, size_t shift2 = 0 ) {
+    auto score = [&]( const uint8_t * q, size_t len, size_t shift, size_t pos, int d ) {
+        if( pos < shift ) return (int) g_gapE;
+        return pos - shift < len && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q[pos - shift]] : pad_score;
+    };
     for( int d = 0; d < 32; d++ )
         for( int lane = 0; lane < 32; lane++ ) {
             const size_t row0 = (size_t) ( lane % G ) * R;
             for( int r = 0; r < R; r++ ) {
                 const size_t row = row0 + r;
-                const int s1 = row < len1 && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q1[row]] : pad_score;
-                const int s2 = row < len2 && d != (int) PAD_RESIDUE ? (int) g_matrix.m[( d << 5 ) + q2[row]] : pad_score;
+                const int s1 = score( q1, len1, shift1, row, d ), s2 = score( q2, len2, shift2, row, d );
                 out[( ( ( r / 4 ) * 32 + d ) * 32 + lane ) * 4 + ( r & 3 )] = ( (uint32_t) (uint16_t) (int16_t) s1 << 16 ) | (uint32_t) (uint16_t) (int16_t) s2;
             }
         }
@@ -1294,13 +1306,18 @@ bool sw32_enabled( bool nw ) {
 }
 // whether groups of G lanes run on the chained kernel (sw32_kernel.cuh): full warps, and half warps for one-pass queries
 // (LIBSSA_B200_NO_G16=1: half warps on the generic kernel, A/B measurements)
-// Measured [B200], 375-aa query: Smith-Waterman on half-warp chains +1.6 % (570 k records) / +4 % (71 k records) over the generic
-// kernel, Needleman-Wunsch -4 % (its instantiation sits at the register limit) - so NW keeps the generic kernel for G = 16
-// unless two queries share the word (dual: +4 %).
+// Measured [B200], 375-aa query, half-warp chains against the generic kernel: Smith-Waterman +1.6 % (570 k records) / +4 % (71 k
+// records); Needleman-Wunsch -4 % while its kernel carried a one-column path (128 registers), +1.1 % / +2.2 % since the query's
+// last row is the last row of a lane (nw_row_shift); two queries per word +4 %.
 bool chained_shape( int G, bool nw, bool one_pass, bool dual = false ) {
     static const bool g16 = getenv( "LIBSSA_B200_NO_G16" ) == nullptr;
-    return sw32_enabled( nw ) && ( G == 32 || ( G == 16 && one_pass && g16 && ( !nw || dual ) ) );
+    (void) dual;
+    return sw32_enabled( nw ) && ( G == 32 || ( G == 16 && one_pass && g16 ) );
 }
+
+// Packed NW: virtual rows on top of a query of qlen rows whose last pass starts at array position rowbase_last and has R rows per
+// lane - as many as it takes for the query's last row to be the last row of a lane (fill_profile_packed)
+size_t nw_row_shift( size_t qlen, size_t rowbase_last, int R ) { return ( (size_t) R - ( qlen - rowbase_last ) % (size_t) R ) % (size_t) R; }
 
 // The packed tier over one class of pairs: all passes of the query, one launch each.
 void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, bool nw, const Plan & pl, const std::vector<PassLaunch> & passes,
@@ -1314,8 +1331,13 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
     d_profile_buf.reserve( words_total );
     uint32_t * const h_profile = h_profile_buf.p, * const d_profile = d_profile_buf.p;
     size_t w0 = 0;
+    size_t shift = 0;
+    if( nw )   // from the pass that holds the query's last row (the last one, unless a forced shape added an empty pass)
+        for( const PassLaunch & ps : passes )
+            if( ps.rowbase <= qlen - 1 && qlen - 1 < ps.rowbase + (size_t) ps.G * ps.R ) shift = nw_row_shift( qlen, ps.rowbase, ps.R );
+    const size_t cap_pos = qlen + shift - 1;   // array position of the query's last row: last row of a lane of the last pass
     for( const PassLaunch & ps : passes ) {
-        fill_profile_packed( h_profile + w0, q, qlen, ps.G, ps.R, ps.rowbase, pl.pad_score );
+        fill_profile_packed( h_profile + w0, q, qlen, ps.G, ps.R, ps.rowbase, pl.pad_score, shift );
         w0 += packed_profile_words( ps.R );
     }
     CUDA_OK( cudaMemcpyAsync( d_profile, h_profile, words_total * 4, cudaMemcpyHostToDevice, stream ) );
@@ -1367,11 +1389,12 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
                 s32.gap_extend = g_gapE;
                 s32.offset = offset;
                 s32.rowbase = (int32_t) ps.rowbase;
+                s32.nw_shift = s32.nw_shift2 = (int32_t) shift;
                 for( int c = p; c < p + run; c++ )   // the pass (of this launch) that holds the query's last row
-                    if( passes[c].rowbase <= qlen - 1 && qlen - 1 < passes[c].rowbase + (size_t) ps.G * ps.R ) {
+                    if( passes[c].rowbase <= cap_pos && cap_pos < passes[c].rowbase + (size_t) ps.G * ps.R ) {
                         s32.cap_pass = c;
-                        s32.cap_lane = (int) ( ( qlen - 1 - passes[c].rowbase ) / ps.R );
-                        s32.cap_row = (int) ( ( qlen - 1 - passes[c].rowbase ) % ps.R );
+                        s32.cap_lane = (int) ( ( cap_pos - passes[c].rowbase ) / ps.R );
+                        s32.cap_row = (int) ( ( cap_pos - passes[c].rowbase ) % ps.R );   // = R - 1
                     }
             }
             launch_sw32( ps.R, nw, multi && ps.G == 32, s32, stream, ps.G );
@@ -1399,9 +1422,10 @@ void launch_packed_class( cudaStream_t stream, const uint8_t * q, size_t qlen, b
         a.offset = offset;
         a.rowbase = (int32_t) ps.rowbase;
         a.cap_lane = -1;
-        if( nw && ps.rowbase <= qlen - 1 && qlen - 1 < ps.rowbase + (size_t) ps.G * ps.R ) {
-            a.cap_lane = (int) ( ( qlen - 1 - ps.rowbase ) / ps.R );
-            a.cap_row = (int) ( ( qlen - 1 - ps.rowbase ) % ps.R );
+        a.nw_shift = a.nw_shift2 = (int32_t) shift;
+        if( nw && ps.rowbase <= cap_pos && cap_pos < ps.rowbase + (size_t) ps.G * ps.R ) {
+            a.cap_lane = (int) ( ( cap_pos - ps.rowbase ) / ps.R );
+            a.cap_row = (int) ( ( cap_pos - ps.rowbase ) % ps.R );   // = R - 1
         }
         a.first_pass = ( p == 0 );
         a.out = ctx().d_out_packed.p;
@@ -1751,7 +1775,8 @@ void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size
     const size_t words = (size_t) R * 1024;
     ctx().h_profile_dual[g_stage_slot].reserve( words );
     ctx().d_profile_dual.reserve( words );
-    fill_profile_dual( ctx().h_profile_dual[g_stage_slot].p, q1, len1, q2, len2, G, R, pl.pad_score );
+    const size_t shift1 = nw ? nw_row_shift( len1, 0, R ) : 0, shift2 = nw ? nw_row_shift( len2, 0, R ) : 0;
+    fill_profile_dual( ctx().h_profile_dual[g_stage_slot].p, q1, len1, q2, len2, G, R, pl.pad_score, shift1, shift2 );
     CUDA_OK( cudaMemcpyAsync( ctx().d_profile_dual.p, ctx().h_profile_dual[g_stage_slot].p, words * 4, cudaMemcpyHostToDevice, ctx().stream ) );
     ctx().stats.h2d_bytes += words * 4;
     const uint32_t out_stride = (uint32_t) ( db.total_cols / 2 + 64 );
@@ -1783,10 +1808,11 @@ void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size
             s32.cap_pass = nw ? 0 : -1;
             s32.cap_lane = s32.cap_lane2 = -1;
             if( nw ) {
-                s32.cap_lane = (int) ( ( len1 - 1 ) / R );
-                s32.cap_row = (int) ( ( len1 - 1 ) % R );
-                s32.cap_lane2 = (int) ( ( len2 - 1 ) / R );
-                s32.cap_row2 = (int) ( ( len2 - 1 ) % R );
+                s32.cap_lane = (int) ( ( len1 + shift1 - 1 ) / R );
+                s32.cap_lane2 = (int) ( ( len2 + shift2 - 1 ) / R );
+                s32.cap_row = s32.cap_row2 = R - 1;
+                s32.nw_shift = (int32_t) shift1;
+                s32.nw_shift2 = (int32_t) shift2;
             }
             s32.dual_half = half;
             s32.out_stride = out_stride;
@@ -1812,10 +1838,11 @@ void score_shard_dual( const uint8_t * q1, size_t len1, const uint8_t * q2, size
         a.rowbase = 0;
         a.cap_lane = a.cap_lane2 = -1;
         if( nw ) {
-            a.cap_lane = (int) ( ( len1 - 1 ) / R );
-            a.cap_row = (int) ( ( len1 - 1 ) % R );
-            a.cap_lane2 = (int) ( ( len2 - 1 ) / R );
-            a.cap_row2 = (int) ( ( len2 - 1 ) % R );
+            a.cap_lane = (int) ( ( len1 + shift1 - 1 ) / R );
+            a.cap_lane2 = (int) ( ( len2 + shift2 - 1 ) / R );
+            a.cap_row = a.cap_row2 = R - 1;
+            a.nw_shift = (int32_t) shift1;
+            a.nw_shift2 = (int32_t) shift2;
         }
         a.first_pass = 1;
         a.out = ctx().d_out_packed.p;

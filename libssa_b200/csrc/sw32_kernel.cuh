@@ -55,7 +55,9 @@ struct Sw32Args {
     // Needleman-Wunsch
     int32_t gap_open, gap_extend;   // gapO, gapE (non-positive)
     int32_t offset;                 // values are stored minus this offset (centres the value range on 0)
-    int32_t rowbase;                // first query row of this launch's first pass (its later passes follow at 32 R rows each)
+    int32_t rowbase;                // array position of the first row of this launch's first pass (its later passes follow at 32 R rows each)
+    int32_t nw_shift, nw_shift2;    // virtual rows on top of the query (DUAL: of the first / second query): query row = position - shift,
+                                    // chosen so that the query's last row is the LAST row of a lane (search.cu:fill_profile_packed)
     int32_t cap_pass;               // pass of the QUERY (not of the launch) that holds the query's last row ...
     int32_t cap_lane, cap_row;      // ... and the lane / row in the lane
     // DUAL (two QUERIES per packed word, score_kernel.cuh): one launch per sequence of the pairs
@@ -263,13 +265,16 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
         const uint32_t * src = a.profile + (size_t) pp * PW;
         for( int i = threadIdx.x; i < PW; i += blockDim.x ) smem[i] = src[i];
     }
-    if( NW ) {   // start values of this pass' rows: H(i, -1) = gapO + (i + 1) gapE, E = H + gapO + gapE (both minus the offset)
+    if( NW ) {   // start values of this pass' rows (column -1; both minus the offset): real rows H(i, -1) = gapO + (i + 1) gapE, virtual
+                 // rows gapO, the last virtual row 0 (= the corner H(-1, -1) row 0 takes as its first diagonal); E = H + gapO + gapE
         for( int i = threadIdx.x; i < R * 32; i += blockDim.x ) {
             const int r = ( i >> 7 ) * 4 + ( i & 3 ), l = ( i >> 2 ) & 31;   // word i of the H half: [row quad][lane][row in quad]
-            const int row = a.rowbase + (int) pp * 32 * R + ( l & ( G - 1 ) ) * R + r;
-            const int h = a.gap_open + ( row + 1 ) * a.gap_extend - a.offset;
-            smem[NW_TAB + i] = A::bcast( h );
-            smem[NW_TAB + R * 32 + i] = A::bcast( h + a.gap_open + a.gap_extend );
+            const int pos = a.rowbase + (int) pp * 32 * R + ( l & ( G - 1 ) ) * R + r;
+            const int h1 = nw_start( pos, a.nw_shift, a.gap_open, a.gap_extend ) - a.offset;
+            const int h2 = DUAL ? nw_start( pos, a.nw_shift2, a.gap_open, a.gap_extend ) - a.offset : h1;
+            const int qr = a.gap_open + a.gap_extend;
+            smem[NW_TAB + i] = ( (uint32_t) (uint16_t) (int16_t) h1 << 16 ) | (uint32_t) (uint16_t) (int16_t) h2;
+            smem[NW_TAB + R * 32 + i] = ( (uint32_t) (uint16_t) (int16_t) ( h1 + qr ) << 16 ) | (uint32_t) (uint16_t) (int16_t) ( h2 + qr );
         }
     }
     __syncthreads();
@@ -293,43 +298,20 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
     stage( t0 );
     stage( t0 + BLK );
 
-    // Needleman-Wunsch: the lane that owns the query's last row records H of that row at the last column of sequence B / A
-    // (the score of B waits in shared memory until the pair ends)
-    auto nw_capture = [&]( const uint32_t ci, const uint32_t slot4 ) {
-        if( DUAL ) {   // the sequence this launch scores ends here: each query's last row may live in another lane
+    // Needleman-Wunsch: the query's last row is the last row of a lane (nw_shift), so the result is what that lane hands to the next
+    // one: H of its last row in the column in which sequence B / A ends (the score of B waits in shared memory until the pair
+    // ends).  DUAL: the sequence of this launch half ends; each query's last row may live in another lane (16-bit stores).
+    auto nw_capture = [&]( const uint32_t ci, const T v, const uint32_t slot4 ) {
+        if( DUAL ) {
             if( ci & end_mask ) {
                 uint16_t * o = (uint16_t *) ( out + lds32( ring_g + slot4 ) );
-#pragma unroll
-                for( int which = 0; which < 2; which++ ) {
-                    if( gl == ( which ? a.cap_lane2 : a.cap_lane ) ) {
-                        const int row = which ? a.cap_row2 : a.cap_row;
-                        T sel = Hp[0];
-#pragma unroll
-                        for( int r = 1; r < R; r++ ) {
-                            T cand = Hp[r];
-                            asm volatile( "" : "+r"( cand ) );
-                            if( r == row ) sel = cand;
-                            asm volatile( "" : "+r"( sel ) );
-                        }
-                        o[which ? 0 : 1] = (uint16_t) ( which ? sel & 0xffffu : sel >> 16 );   // first query = high half
-                    }
-                }
+                if( gl == a.cap_lane ) o[1] = (uint16_t) ( v >> 16 );        // first query = high half
+                if( gl == a.cap_lane2 ) o[0] = (uint16_t) ( v & 0xffffu );
             }
             return;
         }
-        if( ci & ( COL_LAST_A | COL_LAST_B ) ) {
-            // H of the query's last row without turning Hp[] into an indexable (local-memory) array: a chain of predicated moves
-            T sel = Hp[0];
-#pragma unroll
-            for( int r = 1; r < R; r++ ) {
-                T cand = Hp[r];
-                asm volatile( "" : "+r"( cand ) );
-                if( r == a.cap_row ) sel = cand;
-                asm volatile( "" : "+r"( sel ) );
-            }
-            if( ci & COL_LAST_B ) sts32( ring_cap, sel );
-            if( ci & COL_LAST_A ) out[lds32( ring_g + slot4 )] = __byte_perm( lds32( ring_cap ), sel, 0x7610 );
-        }
+        if( ci & COL_LAST_B ) sts32( ring_cap, v );
+        if( ci & COL_LAST_A ) out[lds32( ring_g + slot4 )] = __byte_perm( lds32( ring_cap ), v, 0x7610 );
     };
 
     for( ;; t0 += BLK ) {
@@ -395,8 +377,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                             E[4 * q + 2] = e.z;
                             E[4 * q + 3] = e.w;
                         }
-                        const int row0 = a.rowbase + (int) pp * 32 * R + gl * R;
-                        diag = A::bcast( ( row0 == 0 ? 0 : a.gap_open + row0 * a.gap_extend ) - a.offset );
+                        const int pos0 = a.rowbase + (int) pp * 32 * R + gl * R;   // first diagonal: H of the position above, column -1
+                        const int d1 = nw_start( pos0 - 1, a.nw_shift, a.gap_open, a.gap_extend ) - a.offset;
+                        const int d2 = DUAL ? nw_start( pos0 - 1, a.nw_shift2, a.gap_open, a.gap_extend ) - a.offset : d1;
+                        diag = ( (uint32_t) (uint16_t) (int16_t) d1 << 16 ) | (uint32_t) (uint16_t) (int16_t) d2;
                     }
                     else {
 #pragma unroll
@@ -409,55 +393,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                     }
                 }
                 const uint32_t ra = ( cia >> hs ) & 31u, rb = ( cia >> 5 ) & 31u, sa = ( cib >> hs ) & 31u, sb = ( cib >> 5 ) & 31u;
-                if( NW && is_cap && ( cia & ( DUAL ? end_mask : ( COL_LAST_A | COL_LAST_B ) ) ) ) {
-                    // ---- Needleman-Wunsch, the lane with the query's last row, a sequence ends in the FIRST column of the step:
-                    // the result has to be read between the two columns, so this lane (alone) goes column by column ----
-                    auto single_column = [&]( const uint32_t r0, const uint32_t r1, const T h_in, const T f_in, T & h_last, T & f_last ) {
-                        T f = f_in;
-                        T hd = diag;
-                        diag = h_in;
-                        auto dp_pair1 = [&]( const int k, const uint32_t v0, const uint32_t v1 ) {
-                            const T t0 = A::add( hd, v0 );
-                            const T t1 = A::add( Hp[2 * k], v1 );
-                            hd = Hp[2 * k + 1];
-                            T hq;
-                            Hp[2 * k] = A::max3( t0, E[2 * k], f );
-                            hq = A::add( Hp[2 * k], QR );
-                            E[2 * k] = A::addmax( E[2 * k], RG, hq );
-                            f = A::addmax( f, RG, hq );
-                            Hp[2 * k + 1] = A::max3( t1, E[2 * k + 1], f );
-                            hq = A::add( Hp[2 * k + 1], QR );
-                            E[2 * k + 1] = A::addmax( E[2 * k + 1], RG, hq );
-                            f = A::addmax( f, RG, hq );
-                        };
-#pragma unroll
-                        for( int q = 0; q < MR / 4; q++ ) {
-                            const uint4 la = lds128( prof_base + ( r0 << 9 ) + q * 16384 );
-                            if( DUAL ) {
-                                dp_pair1( 2 * q, la.x, la.y );
-                                dp_pair1( 2 * q + 1, la.z, la.w );
-                            }
-                            else {
-                                const uint4 lb = lds128( prof_base + ( r1 << 9 ) + q * 16384 );
-                                dp_pair1( 2 * q, la.x * K65536 + lb.x, la.y * K65536 + lb.y );
-                                dp_pair1( 2 * q + 1, la.z * K65536 + lb.z, la.w * K65536 + lb.w );
-                            }
-                        }
-#pragma unroll
-                        for( int q = 0; q < NQ16; q++ ) {
-                            const uint2 la = lds64( prof_base16 + ( r0 << 8 ) + q * 8192 ), lb = lds64( prof_base16 + ( r1 << 8 ) + q * 8192 );
-                            dp_pair1( MR / 2 + 2 * q, __byte_perm( lb.x, la.x, 0x5410 ), __byte_perm( lb.x, la.x, 0x7632 ) );
-                            dp_pair1( MR / 2 + 2 * q + 1, __byte_perm( lb.y, la.y, 0x5410 ), __byte_perm( lb.y, la.y, 0x7632 ) );
-                        }
-                        h_last = Hp[R - 1];
-                        f_last = f;
-                    };
-                    single_column( ra, rb, ha_in, fa_in, ha_last, fa_last );
-                    nw_capture( cia, slot4 );
-                    single_column( sa, sb, hb_in, fb_in, hb_last, fb_last );
-                    nw_capture( cib, slot4 );
-                }
-                else {
+                {
                 // ---- two columns per step (see score_kernel.cuh for the recurrence and its instruction selection) ----
                 // Full-warp arrays with 64-bit profile entries (R >= 20, the shapes of long queries): every diagonal candidate of
                 // column A (old H of the row above + substitution score) is formed BEFORE the pair of rows that overwrites that H
@@ -591,7 +527,10 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<true, R>() ) sw32_k
                 fa_last = fa;
                 hb_last = Hp[R - 1];
                 fb_last = fb;
-                if( NW && is_cap ) nw_capture( cib, slot4 );
+                if( NW && is_cap ) {
+                    nw_capture( cia, ha_last, slot4 );
+                    nw_capture( cib, hb_last, slot4 );
+                }
                 }
 
                 // ---- the pair ends in this step: the running maximum travels down the lanes with the wavefront ----
