@@ -206,7 +206,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
     // F chains are independent, which doubles the instruction-level parallelism of the otherwise serial row loop,
     // and the per-step work (shuffles, flags, loads) is shared by 2R cells.  Sequence pairs are padded to an even
     // number of columns in the stream, so a sequence always starts in column A.
-    // PACKED Smith-Waterman has no one-column path: pairs are padded with a harmless column (PAD_RESIDUE)
+    // The packed tier has no one-column path: SW pairs are padded with a harmless column (PAD_RESIDUE); packed NW reads its result
+    // from the values the lane with the query's last row hands on (that row is the lane's last one: ScoreArgs::nw_shift)
     constexpr bool HAS_SLOW = !PACKED;   // (packed NW reads its result from the values a lane hands on: nw_shift)
     // passes of a long query on full-warp arrays: the group IS the warp, known at compile time
     constexpr bool FULLWARP = MULTI == 1;

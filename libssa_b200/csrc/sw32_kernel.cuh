@@ -16,8 +16,8 @@
 //   * results are stored by stream position (the column pair in which a pair of sequences ends), boundary rows as one
 //     16-byte entry {H col A, H col B, F col A, F col B} per column pair, so no lane has to know which batch it is in;
 //   * there is no one-column path (pairs are padded with a PAD_RESIDUE column) and no per-step exit vote.  Needleman-Wunsch
-//     reads its result between the two columns of a step when a sequence ends in the first of them: only the ONE lane that
-//     holds the query's last row leaves the two-column path for that step;
+//     needs none either: the query is shifted down by virtual rows so that its last row is the last row of a lane, and the
+//     result - H of that row in the column in which a sequence ends - is a value the lane hands on anyway (Sw32Args::nw_shift);
 //   * ALL full passes of a long query run in ONE launch: a CTA works through the passes in order (its warps meet at a CTA
 //     barrier to swap the query profile in shared memory), every pass has its own work queue over the same batches, and a
 //     batch of pass p+1 starts as soon as the SAME batch of pass p is finished (a per-batch counter in global memory,
