@@ -340,3 +340,51 @@ def test_reference_translated_query_vectors_oracle(prod_host, port):
     assert sorted((int(port.nw_score(rec, c, M, -1, -1)) for c, _, _ in qf), reverse=True) == [-109, -109, -110, -110, -110, -113]
     assert sorted((int(port.sw_score(rec, c, M, -1, -1)) for c, _, _ in qf), reverse=True) == [2, 2, 2, 2, 2, 1]
     prod_host.init_symbol_translation(cases.AMINOACID, 1, 1, 1)
+
+
+def test_nw_virtual_rows_carry_the_boundary(port):
+    """The packed NW kernels shift the query down by `shift` virtual rows so that its last row is the last row of a lane
+    (search.cu:fill_profile_packed, score_kernel.cuh:nw_start).  Scalar model of exactly that array - virtual rows score gapE against
+    every residue, start at gapO (the last one at 0), real rows start at gapO + (i + 1) gapE, E starts at H + gapO + gapE, the top
+    boundary gapO + (j + 1) gapE with F = H + gapO + gapE is fed in above the first row, the first diagonal is gapO (0 without
+    virtual rows) - against the oracle's exact NW score, for every shift and several gap settings (including gapO = 0)."""
+    rng = np.random.default_rng(11)
+    M = rng.integers(-4, 6, size=(32, 32)).astype(np.int64)
+    M = (M + M.T) // 2
+
+    def nw_start(pos, shift, gO, gE):
+        if pos < shift - 1:
+            return gO
+        if pos == shift - 1:
+            return 0
+        return gO + (pos - shift + 1) * gE
+
+    def shifted_score(q, d, gO, gE, shift):
+        qr = gO + gE
+        rows = shift + len(q)
+        H = [nw_start(p, shift, gO, gE) for p in range(rows)]       # column -1
+        E = [h + qr for h in H]                                      # E entering column 0
+        diag_top = nw_start(-1, shift, gO, gE)                       # H of the row above the array, column -1
+        for j in range(len(d)):
+            h_up = gO + (j + 1) * gE                                 # top boundary, fed in above the first row
+            f = h_up + qr
+            hd = diag_top
+            diag_top = h_up
+            for p in range(rows):
+                v = gE if p < shift else int(M[d[j], q[p - shift]])
+                t = hd + v
+                hd = H[p]
+                h = max(t, E[p], f)
+                hq = h + qr
+                E[p] = max(E[p] + gE, hq)
+                f = max(f + gE, hq)
+                H[p] = h
+        return H[rows - 1]
+
+    for gO, gE in ((-11, -1), (-3, -2), (0, -2), (-5, -5)):
+        for _ in range(6):
+            q = rng.integers(1, 24, size=int(rng.integers(1, 40))).astype(np.uint8)
+            d = rng.integers(1, 24, size=int(rng.integers(1, 60))).astype(np.uint8)
+            exact = int(port.score_db([d], q, M, gO, gE, True)[0])
+            for shift in (0, 1, 2, 5, 11):
+                assert shifted_score(q, d, gO, gE, shift) == exact, (gO, gE, len(q), len(d), shift)
