@@ -329,29 +329,9 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
         f_last = f;
     };
 
-    // NW: the lane that owns the query's last row records H at the last column of sequence A / B
+    // NW, 32-bit tier: the lane that owns the query's last row records H at the last column of its sequence (the packed tier reads
+    // its result from the values a lane hands on, see the two-column path)
     auto nw_capture = [&]( const uint32_t ci ) {
-        if( DUAL ) {   // the sequence of this launch half ends here: each query's last row may live in another lane
-            if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) {
-                uint16_t * o = (uint16_t *) ( (uint32_t *) a.out + half * a.out_stride + bnd_base + (uint32_t) ( t - gl ) );
-#pragma unroll
-                for( int which = 0; which < 2; which++ ) {
-                    if( gl == ( which ? a.cap_lane2 : a.cap_lane ) ) {
-                        const int row = which ? a.cap_row2 : a.cap_row;
-                        T sel = Hp[0];
-#pragma unroll
-                        for( int r = 1; r < R; r++ ) {
-                            T cand = Hp[r];
-                            asm volatile( "" : "+r"( cand ) );
-                            if( r == row ) sel = cand;
-                            asm volatile( "" : "+r"( sel ) );
-                        }
-                        o[which ? 0 : 1] = (uint16_t) ( which ? (uint32_t) sel & 0xffffu : (uint32_t) sel >> 16 );   // first query = high half
-                    }
-                }
-            }
-            return;
-        }
         if( gl == a.cap_lane && ( ci & ( COL_LAST_A | COL_LAST_B ) ) ) {
             // pick H of the query's last row without turning Hp[] into an indexable (local-memory) array:
             // a chain of predicated moves, kept opaque to the optimiser
@@ -363,13 +343,7 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
                 if( r == a.cap_row ) sel = cand;
                 asm volatile( "" : "+r"( sel ) );
             }
-            if( PACKED ) {
-                if( ci & COL_LAST_B ) cap_b = sel;
-                if( ci & COL_LAST_A ) ( (uint32_t *) a.out )[bnd_base + (uint32_t) ( t - gl )] = __byte_perm( (uint32_t) cap_b, (uint32_t) sel, 0x7610 );
-            }
-            else {
-                if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
-            }
+            if( ci & ( half ? COL_LAST_B : COL_LAST_A ) ) ( (int32_t *) a.out )[out_idx] = (int32_t) sel + a.offset;
         }
     };
 
@@ -537,9 +511,8 @@ __global__ void __launch_bounds__( SCORE_THREADS, min_blocks<PACKED, R>() ) scor
             const bool b_valid = ( cib & COL_VALID ) != 0;
             const bool slow = HAS_SLOW;
             if( slow ) {
-                // column by column: the wide tier, and NW results that must be read between the two columns - only in the
-                // lane that owns the query's last row (a sequence end in column A makes ONE lane of the group leave the
-                // two-column path for one step; the other lanes compute the same cells two columns at a time)
+                // column by column: the 32-bit tier (one sequence per group; NW reads its result after the column in which the
+                // sequence ends)
                 single_column( cia, ha_in, fa_in, ha_last, fa_last );
                 if( NW ) nw_capture( cia );
                 if( b_valid ) {
